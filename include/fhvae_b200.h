@@ -1,0 +1,200 @@
+/* fhvae_b200.h -- C ABI of libfhvae_b200.so: the sm_100a kernels behind the ScalableFHVAE
+ * train / inference step.
+ *
+ * The reference (BurnhamG/PyTorch-ScalableFHVAE) is pure Python and has NO operator registry, FFI
+ * or plugin API: its drop-in boundary is the nn.Module surface
+ * (simple_fhvae.py:8-124, fhvae.py:4-14).  This header is therefore the layer *below* that
+ * surface: each entry point names the reference ATen op group it replaces (file:line into the
+ * reference).  The Python mirror (pytorch_scalablefhvae_b200/model.py) binds these with ctypes --
+ * see INTEGRATION.md for the stub a maintainer would add to the reference.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; every pointer is DEVICE memory owned by the caller
+ *    (PyTorch); the library never allocates, frees or retains a pointer past the call;
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises,
+ *    nothing reads device memory on the host => every call is CUDA-graph capturable;
+ *  - return 0 on success; <0 = argument error (FHVAE_E*); >0 = cudaError_t of the launch.
+ *    fhvae_last_error_string() describes the last failure of the calling thread;
+ *  - fp32 everywhere at the boundary; int64 indices (torch.long), exact;
+ *  - LSTM-internal tensors are TIME-MAJOR: (T, B, *).
+ */
+#ifndef FHVAE_B200_H
+#define FHVAE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FHVAE_EINVAL (-1)   /* bad size / null pointer */
+#define FHVAE_ENOSUP (-2)   /* shape not supported by this kernel */
+
+/* GEMM compute modes (fhvae_gemm_batch `mode`, fhvae_lstm_* `mode`) */
+#define FHVAE_MODE_F32_SIMT 0   /* fp32 FFMA, exact-order reference kernels                  */
+#define FHVAE_MODE_BF16X3   1   /* tcgen05 kind::f16, hi/lo bf16 split x3 (fp32-parity mode)   */
+#define FHVAE_MODE_BF16     2   /* tcgen05 kind::f16, single bf16 pass ("bf16 input-GEMM mode") */
+
+const char* fhvae_last_error_string(void);
+int fhvae_version(void);
+/* compile-time facts the host may assert on */
+int fhvae_built_for_sm(void);              /* 100 */
+
+/* ---------------------------------------------------------------------------------------------
+ * K1/K3/K5/K8 dense contractions.  Replaces nn.Linear addmm (simple_fhvae.py:130-134,208-212),
+ * the nn.LSTM input projections of the FHVAE restatement, and their autograd dgrad/wgrad mm's.
+ *   C[m,n] = sum_k A(m,k) * B(k,n) + bias[n] + beta * C[m,n];   optional ReLU.
+ *   A(m,k) = A[m*sa_m + k*sa_k],  B(k,n) = B[k*sb_k + n*sb_n]  (element strides; one of each pair is 1)
+ * Up to FHVAE_GEMM_MAX_BATCH independent problems per launch (grouped GEMM: one grid).
+ * ------------------------------------------------------------------------------------------- */
+#define FHVAE_GEMM_MAX_BATCH 24
+typedef struct fhvae_gemm_problem {
+    const float* A;
+    const float* B;
+    float*       C;
+    const float* bias;          /* (N,) or NULL */
+    int32_t M, N, K;
+    int32_t relu;               /* 1: C = max(C, 0) */
+    int64_t sa_m, sa_k;
+    int64_t sb_k, sb_n;
+    int64_t ldc;
+    float   beta;               /* 0 or 1 (any value accepted) */
+    int32_t reserved;
+} fhvae_gemm_problem;
+int fhvae_gemm_batch(const fhvae_gemm_problem* problems, int n_problems, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LSTM recurrence (PyTorch nn.LSTM cell, gate order i,f,g,o; zero initial state).
+ *   gates_t = P[t] (T,B,4H, may be NULL) + Q (B,4H, time-invariant, may be NULL) + h_{t-1} W_hh^T
+ *   (biases are folded into P or Q by the projection GEMM).
+ * Saves for BPTT: h_all (T,B,H), c_all (T,B,H), acts (T,B,4H) = post-activation i,f,g,o.
+ * ------------------------------------------------------------------------------------------- */
+int fhvae_lstm_fwd(const float* P, const float* Q, const float* W_hh,
+                   float* h_all, float* c_all, float* acts,
+                   int T, int B, int H, int mode, void* stream);
+/* BPTT.  dh_all (T,B,H) = dL/dh_t from the consumer of all outputs (may be NULL);
+ * dh_last (B,H) = extra dL/dh_{T-1} from the final-state consumer (may be NULL).
+ * Outputs: dgates (T,B,4H) pre-activation gate gradients; dgsum (B,4H) = sum_t dgates (may be NULL).
+ * Scratch: dh_rec (2,B,H) and dc (B,H), caller-allocated, contents undefined on entry. */
+int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
+                   const float* c_all, const float* acts,
+                   float* dgates, float* dgsum, float* dh_rec, float* dc,
+                   int T, int B, int H, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2/K4/K6: reparameterisation + ELBO terms (simple_fhvae.py:56-69, :106-116, :213-216).
+ * ------------------------------------------------------------------------------------------- */
+/* head (B, 2Z) = [mu | logvar] rows of leading dim ld_head;  sample[b*ld_s + d] = mu + eps*exp(.5 logvar) */
+int fhvae_reparam_fwd(const float* head, int64_t ld_head, const float* eps,
+                      float* sample, int64_t ld_s, int B, int Z, void* stream);
+/* dhead[b, 0:Z] (+)= dsample ; dhead[b, Z:2Z] (+)= dsample * 0.5*eps*exp(.5 logvar).
+ * accumulate=0 overwrites dhead, 1 adds to it. */
+int fhvae_reparam_bwd(const float* head, int64_t ld_head, const float* eps,
+                      const float* dsample, int64_t ld_ds,
+                      float* dhead, int64_t ld_dh, int accumulate, int B, int Z, void* stream);
+
+/* One CTA per segment.  x (B,T,F) contiguous.  Decoder head element (b,t,f):
+ *   mu = xhead[b*xs_b + t*xs_t + f],  logvar = xhead[b*xs_b + t*xs_t + lv_off + f].
+ * z1head / z2head: (B, 2Z) rows [mu | logvar].  mu2 (B,Z2) = gathered table rows (fhvae_mu2_gather),
+ * nsegs (B,) int64.
+ * out5 (5,B): lower_bound, log_px_z, neg_kld_z1, neg_kld_z2, log_pmu2.
+ * nan_flag (may be NULL): set to 1 if any lower_bound is NaN (train_model.py:464-466 guard). */
+int fhvae_elbo_fwd(const float* x, const float* xhead, int64_t xs_b, int64_t xs_t, int64_t lv_off,
+                   const float* z1head, const float* z2head,
+                   const float* mu2, const int64_t* nsegs,
+                   float* out5, int* nan_flag,
+                   int B, int T, int F, int Z1, int Z2, void* stream);
+/* coef (4,B): dL/d{log_px_z, neg_kld_z1, neg_kld_z2, log_pmu2} with dL/dlower_bound already folded
+ * in by the host ( c_px = g_lb + g_px, ..., c_pmu2 = g_lb/nsegs + g_pmu2 ).
+ * Writes dxhead (same layout as xhead), dz1head, dz2head (B,2Z) (overwrite), dmu2 (B,Z2) (overwrite). */
+int fhvae_elbo_bwd(const float* x, const float* xhead, int64_t xs_b, int64_t xs_t, int64_t lv_off,
+                   const float* z1head, const float* z2head,
+                   const float* mu2, const float* coef,
+                   float* dxhead, float* dz1head, float* dz2head, float* dmu2,
+                   int B, int T, int F, int Z1, int Z2, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K7: discriminative log q(i|z2) over all table rows (simple_fhvae.py:119-122), never
+ * materialising (B,N,Z) or (B,N).  z2mu rows have leading dim ld_z (the [mu|logvar] head).
+ * fwd: partial (max, sumexp) per N-split -> part (nsplit,B,2); then combine.  Z in {8,16,32,64}.
+ * ------------------------------------------------------------------------------------------- */
+int fhvae_disc_nsplit(int B, int64_t N);
+int fhvae_disc_fwd_partial(const float* z2mu, int64_t ld_z, const float* table, int64_t N, int Z,
+                           float* part, int nsplit, int B, void* stream);
+/* tgt (B,) = target logit -||z_b - mu2_b||^2 / (2 s2) in direct form; mu2 (B,Z) = gathered rows. */
+int fhvae_disc_target(const float* z2mu, int64_t ld_z, const float* mu2, float* tgt, int B, int Z,
+                      void* stream);
+/* combine `nparts` partial (max,sumexp) sets (nparts = nsplit, or nsplit*world after an all-gather).
+ * Writes log_qy (B,) = tgt - lse, and lse (B,). */
+int fhvae_disc_combine(const float* part, int nparts, const float* tgt,
+                       float* log_qy, float* lse, int B, void* stream);
+/* bwd, g (B,) = dL/dlog_qy, p_bn = exp(s_bn - lse_b):
+ *   rows:   dtable (N,Z) overwritten with -sum_b g_b p_bn (z_b - m_n)/s2  (dense softmax part; owner-local)
+ *   segs:   sumpm_part (nsplit,B,Z) = per-N-split partial sums of p_bn m_n
+ *   finish: dz2mu[b*ld_dz + d] += g_b/s2 * (mu2_b - sum_parts sumpm);  dmu2 (B,Z) += g_b (z_b - mu2_b)/s2
+ *           (the sparse target part, reduced into the table by fhvae_mu2_scatter_reduce). */
+int fhvae_disc_bwd_rows(const float* z2mu, int64_t ld_z, const float* table, int64_t N, int Z,
+                        const float* lse, const float* g, float* dtable, int B, void* stream);
+int fhvae_disc_bwd_segs(const float* z2mu, int64_t ld_z, const float* table, int64_t N, int Z,
+                        const float* lse, float* sumpm_part, int nsplit, int B, void* stream);
+int fhvae_disc_bwd_finish(const float* z2mu, int64_t ld_z, const float* mu2, const float* sumpm_part,
+                          int nparts, const float* g, float* dz2mu, int64_t ld_dz, float* dmu2,
+                          int B, int Z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K0: mu2 table (simple_fhvae.py:39-54).  Exact int64 indexing; deterministic reductions.
+ * ------------------------------------------------------------------------------------------- */
+int fhvae_mu2_gather(const float* table, const int64_t* idx, float* mu2, int B, int Z, int64_t N,
+                     void* stream);
+/* dtable[idx[b]] += sum over duplicates (ascending b, fixed order).  touched (B,) int32: 1 at the
+ * first occurrence of each distinct row, else 0 (the "rows touched" set). */
+int fhvae_mu2_scatter_reduce(const float* dmu2, const int64_t* idx, float* dtable, int32_t* touched,
+                             int B, int Z, int64_t N, void* stream);
+/* utils.py:45-60 batched: zsum (K,Z) += z2mu rows, cnt (K,) += 1  (deterministic per row), then
+ * fhvae_mu2_estimate_finish: table[k] = zsum[k] / (cnt[k] + r) where cnt>0.  */
+int fhvae_mu2_accumulate(const float* z2mu, int64_t ld_z, const int64_t* idx, float* zsum, float* cnt,
+                         int B, int Z, int64_t K, void* stream);
+int fhvae_mu2_estimate_finish(const float* zsum, const float* cnt, float* table, float r,
+                              int64_t K, int Z, void* stream);
+/* sparse row write-back / fetch between a master shard and the active cache (hierarchical sampling):
+ * dst[dst_rows[i]] = src[src_rows[i]] for i < n; rows with dst_rows[i] < 0 are skipped. */
+int fhvae_rows_copy(const float* src, const int64_t* src_rows, float* dst, const int64_t* dst_rows,
+                    int64_t n, int Z, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K9: Adam on a flat fp32 buffer (train_model.py:409-411,454: lr 1e-3, betas (0.95,0.999), eps 1e-8).
+ * `step` is a DEVICE int32 counter (number of steps already taken); the kernel bumps it at the end
+ * so the same launch can be replayed from a CUDA graph.  grad_scale multiplies g (1/world for DP).
+ * ------------------------------------------------------------------------------------------- */
+int fhvae_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
+                    float lr, float beta1, float beta2, float eps, float grad_scale,
+                    int32_t* step, uint32_t* done_counter, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * small data-movement helpers
+ * ------------------------------------------------------------------------------------------- */
+/* (B,T,F) -> (T,B,F) */
+int fhvae_transpose_bt(const float* src, float* dst, int B, int T, int F, void* stream);
+/* out[c] = sum_r in[r*ld + c]  (r < R); deterministic.  out2 (may be NULL) receives a second copy
+ * (nn.LSTM keeps b_ih and b_hh: both get the same gradient).  Up to FHVAE_COLSUM_MAX_BATCH per launch. */
+#define FHVAE_COLSUM_MAX_BATCH 16
+typedef struct fhvae_colsum_problem {
+    const float* in;
+    float*       out;
+    float*       out2;
+    int64_t      ld;
+    int32_t      R, C;
+} fhvae_colsum_problem;
+int fhvae_colsum_batch(const fhvae_colsum_problem* problems, int n_problems, void* stream);
+/* out = a + b */
+int fhvae_add2(float* out, const float* a, const float* b, int64_t n, void* stream);
+/* dpre = dout * (out > 0), in place on dout */
+int fhvae_relu_bwd(float* dout, const float* out, int64_t n, void* stream);
+/* y = a*x + y */
+int fhvae_axpy(float* y, const float* x, float a, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FHVAE_B200_H */

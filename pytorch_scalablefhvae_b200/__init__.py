@@ -1,0 +1,9 @@
+"""B200-native ScalableFHVAE train / inference step (drop-in for BurnhamG/PyTorch-ScalableFHVAE's
+``SimpleFHVAE`` / ``FHVAE`` modules).  Hand-written sm_100a CUDA behind a C ABI; no CPU fallback."""
+from . import _lib
+from ._lib import MODE_BF16, MODE_BF16X3, MODE_F32_SIMT, build
+from .model import FHVAE, SimpleFHVAE, loss_function
+from .optim import FusedAdam
+
+__all__ = ["FHVAE", "SimpleFHVAE", "FusedAdam", "loss_function", "build", "MODE_F32_SIMT", "MODE_BF16X3",
+           "MODE_BF16"]

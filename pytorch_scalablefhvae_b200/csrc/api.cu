@@ -1,0 +1,64 @@
+// C-ABI plumbing: error string, version, and the mode dispatch of the GEMM / LSTM entry points.
+#include <stdarg.h>
+#include "common.cuh"
+
+namespace fhvae {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int gemm_batch_simt(const fhvae_gemm_problem* problems, int n, cudaStream_t st);
+int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStream_t st);
+int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
+                  float* acts, int T, int B, int H, cudaStream_t st);
+int lstm_bwd_simt(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
+                  const float* acts, float* dgates, float* dgsum, float* dc, int T, int B, int H,
+                  cudaStream_t st);
+
+}  // namespace fhvae
+
+using namespace fhvae;
+
+extern "C" const char* fhvae_last_error_string(void) { return g_err; }
+extern "C" int fhvae_version(void) { return 1; }
+extern "C" int fhvae_built_for_sm(void) { return 100; }
+
+extern "C" int fhvae_gemm_batch(const fhvae_gemm_problem* problems, int n_problems, int mode,
+                                void* stream) {
+    FHVAE_CHECK_ARG(problems && n_problems > 0 && n_problems <= FHVAE_GEMM_MAX_BATCH,
+                    "gemm_batch: need 1..%d problems", FHVAE_GEMM_MAX_BATCH);
+    for (int i = 0; i < n_problems; ++i) {
+        const fhvae_gemm_problem& p = problems[i];
+        FHVAE_CHECK_ARG(p.A && p.B && p.C && p.M >= 0 && p.N >= 0 && p.K >= 0,
+                        "gemm_batch: problem %d has a null pointer or negative size", i);
+        FHVAE_CHECK_ARG((p.sa_m == 1 || p.sa_k == 1) && (p.sb_k == 1 || p.sb_n == 1),
+                        "gemm_batch: problem %d: one stride of A and of B must be 1", i);
+    }
+    if (mode == FHVAE_MODE_F32_SIMT) return gemm_batch_simt(problems, n_problems, as_stream(stream));
+    if (mode == FHVAE_MODE_BF16X3 || mode == FHVAE_MODE_BF16)
+        return gemm_batch_tc(problems, n_problems, mode, as_stream(stream));
+    set_error("gemm_batch: unknown mode %d", mode);
+    return FHVAE_EINVAL;
+}
+
+extern "C" int fhvae_lstm_fwd(const float* P, const float* Q, const float* W_hh, float* h_all,
+                              float* c_all, float* acts, int T, int B, int H, int mode, void* stream) {
+    FHVAE_CHECK_ARG(W_hh && h_all && c_all && acts && (P || Q), "lstm_fwd: null pointer");
+    FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_fwd: need T,B>0 and H %% 8 == 0");
+    return lstm_fwd_simt(P, Q, W_hh, h_all, c_all, acts, T, B, H, as_stream(stream));
+}
+
+extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
+                              const float* c_all, const float* acts, float* dgates, float* dgsum,
+                              float* dh_rec, float* dc, int T, int B, int H, int mode, void* stream) {
+    FHVAE_CHECK_ARG(W_hh && c_all && acts && dgates && dc && (dh_all || dh_last), "lstm_bwd: null pointer");
+    FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_bwd: need T,B>0 and H %% 8 == 0");
+    return lstm_bwd_simt(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dc, T, B, H,
+                         as_stream(stream));
+}

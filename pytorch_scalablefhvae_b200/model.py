@@ -1,0 +1,850 @@
+"""``SimpleFHVAE`` / ``FHVAE``: drop-in ``nn.Module`` surface of the reference, computed by
+hand-written sm_100a kernels behind the C ABI of ``include/fhvae_b200.h``.
+
+Mirrors (file:line into BurnhamG/PyTorch-ScalableFHVAE):
+* constructors            simple_fhvae.py:9-37, fhvae.py:5-13 (``FHVAE`` is a stub upstream: the LSTM
+                          architecture is SURVEY.md Appendix B, frozen in oracle/fhvae_oracle.py)
+* ``forward`` 4-arg call  simple_fhvae.py:71-124, called from train_model.py:447-449 / utils.py:51
+* attribute surface       ``.model .z1_hus .z2_hus .z1_dim .z2_dim .x_hus .pz1 .pmu2`` (utils.py:72-77,
+                          134-141) plus ``.qz2_x .qz1_x .px_z .pz2`` which utils.estimate_mu2_dict reads
+                          (utils.py:52,58) but the reference forgets to set.
+
+There is no CPU path: parameters live in one flat fp32 HBM buffer (``nn.Parameter`` views of it, so
+``named_parameters()`` / ``state_dict()`` / ``.grad`` behave as usual), a forward/backward is a
+replayed list of kernel launches on preallocated workspaces, optionally captured in a CUDA graph.
+"""
+from __future__ import annotations
+
+import math
+import weakref
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import ColsumProblem
+from .plan import CallList, current_stream_ptr, gemm_nn, gemm_nt, gemm_tn, ptr
+
+PZ2_LOGVAR = math.log(0.5 ** 2)      # simple_fhvae.py:88
+PMU2_LOGVAR = math.log(1.0 ** 2)     # simple_fhvae.py:23
+_OUT_ORDER = (0, 5, 1, 2, 3, 4)      # rows of the (6,B) out buffer -> reference return order
+
+
+class _Holder(nn.Module):
+    """Name-space node so that parameter keys match the reference's state_dict."""
+
+
+def _prod(shape):
+    n = 1
+    for s in shape:
+        n *= int(s)
+    return n
+
+
+def _as_int_list(v) -> List[int]:
+    # train_model.py:145-168 forgets type=int for --z1-hus/--z2-hus/--x-hus: strings may arrive
+    return [int(h) for h in v]
+
+
+class _FHVAECore(nn.Module):
+    """Flat parameter storage, plan cache, autograd glue and the shared forward tail."""
+
+    model = "base"
+
+    # ------------------------------------------------------------------ parameters
+    def _init_flat(self, specs: Sequence[Tuple[str, Tuple[int, ...]]], init: Dict[str, torch.Tensor]):
+        off = 0
+        self._off: Dict[str, int] = {}
+        self._shape: Dict[str, Tuple[int, ...]] = {}
+        for name, shape in specs:
+            self._off[name] = off
+            self._shape[name] = tuple(shape)
+            off += (_prod(shape) + 3) // 4 * 4          # 16-byte aligned slots
+        self._n_flat = off
+        self._names = [n for n, _ in specs]
+        flat = torch.zeros(off, dtype=torch.float32)
+        self._plist: List[nn.Parameter] = []
+        for name, shape in specs:
+            view = flat[self._off[name]:self._off[name] + _prod(shape)].view(shape)
+            view.copy_(init[name].detach().float())
+            p = nn.Parameter(view)
+            p._fhvae = (weakref.ref(self), name)
+            node = self
+            parts = name.split(".")
+            for part in parts[:-1]:
+                if not hasattr(node, part):
+                    node.add_module(part, _Holder())
+                node = getattr(node, part)
+            node.register_parameter(parts[-1], p)
+            self._plist.append(p)
+        self._flat = flat
+        self._gflat: List[Optional[torch.Tensor]] = [None, None]
+        self._plans: Dict[Tuple, "_Plan"] = {}
+        self._anchor = None
+
+    def _ensure_flat(self) -> torch.Tensor:
+        """(Re)pack parameters into one flat buffer after .to()/.cuda()/load; keeps Parameter identity."""
+        p0, pl = self._plist[0], self._plist[-1]
+        ok = (self._flat.device == p0.device
+              and p0.data_ptr() == ptr(self._flat, self._off[self._names[0]])
+              and pl.data_ptr() == ptr(self._flat, self._off[self._names[-1]]))
+        if ok:
+            return self._flat
+        dev = p0.device
+        flat = torch.zeros(self._n_flat, dtype=torch.float32, device=dev)
+        for name, p in zip(self._names, self._plist):
+            if p.dtype != torch.float32:
+                raise RuntimeError("the sm_100a path is fp32 only (SURVEY.md §8b dtype contract)")
+            o, n = self._off[name], p.numel()
+            view = flat[o:o + n].view(self._shape[name])
+            view.copy_(p.data)
+            p.data = view
+        self._flat = flat
+        self._gflat = [None, None]
+        self._plans.clear()
+        return flat
+
+    def double(self):          # train_model.py:438 -- unsupported on the CUDA path (Appendix A8)
+        raise RuntimeError(
+            "FHVAE sm_100a kernels are fp32; model.double() (train_model.py:438) is not supported. "
+            "fp32 matches the fp64 reference to ~1e-6 relative (SURVEY.md Appendix D).")
+
+    def poff(self, name: str, extra: int = 0) -> int:
+        return ptr(self._flat, self._off[name] + extra)
+
+    def _grad_buffer(self, k: int) -> torch.Tensor:
+        if self._gflat[k] is None or self._gflat[k].device != self._flat.device:
+            self._gflat[k] = torch.zeros(self._n_flat, dtype=torch.float32, device=self._flat.device)
+        return self._gflat[k]
+
+    def _free_grad_slot(self) -> int:
+        """Index of a flat grad buffer that no live ``.grad`` aliases (autograd glue)."""
+        g = self._plist[0].grad
+        if g is None:
+            return 0
+        for k in (0, 1):
+            buf = self._gflat[k]
+            if buf is None or g.data_ptr() != ptr(buf, self._off[self._names[0]]):
+                return k
+        return 0
+
+    def packed_grads(self) -> torch.Tensor:
+        """Flat gradient buffer equal to every ``p.grad`` (zeros where None); zero-copy on the fast path."""
+        self._ensure_flat()
+        for k in (0, 1):
+            buf = self._gflat[k]
+            if buf is None:
+                continue
+            if all(p.grad is not None and p.grad.data_ptr() == ptr(buf, self._off[n])
+                   for n, p in zip(self._names, self._plist)):
+                return buf
+        k = self._free_grad_slot()
+        buf = self._grad_buffer(k)
+        buf.zero_()
+        for n, p in zip(self._names, self._plist):
+            if p.grad is not None:
+                buf[self._off[n]:self._off[n] + p.numel()].view_as(p).copy_(p.grad)
+        return buf
+
+    # ------------------------------------------------------------------ forward
+    def _plan(self, B: int, T: int, F: int) -> "_Plan":
+        self._ensure_flat()
+        key = (B, T, F, self.gemm_mode, self._flat.data_ptr())
+        plan = self._plans.get(key)
+        if plan is None:
+            plan = self._make_plan(B, T, F)
+            self._plans[key] = plan
+        return plan
+
+    def forward(self, x: torch.Tensor, mu_idx: torch.Tensor, num_seqs: int, num_segs, eps=None):
+        """simple_fhvae.py:71-124.  Returns (lower_bound (B,), log_qy, log_px_z (B,), neg_kld_z1 (B,),
+        neg_kld_z2 (B,), log_pmu2 (B,)); ``log_qy`` is per-segment -CE_b unless ``ref_log_qy``."""
+        if not x.is_cuda:
+            raise RuntimeError("pytorch_scalablefhvae_b200 has no CPU path: move the batch and the "
+                               "model to a CUDA device (train_model.py:413,444)")
+        if self._plist[0].device != x.device:
+            raise RuntimeError(f"model parameters are on {self._plist[0].device}, input on {x.device}: "
+                               "call model.to(device) first (train_model.py:413)")
+        if int(num_seqs) != self.mu2_table.shape[0]:
+            raise ValueError(f"num_seqs={num_seqs} but the mu2 table has {self.mu2_table.shape[0]} rows")
+        B, T, F = x.shape
+        if not mu_idx.is_cuda:
+            # the reference keeps idxs on the CPU (train_model.py:445); torch.gather would raise on
+            # out-of-range rows (simple_fhvae.py:53) -- same error behaviour, checked on the host
+            if mu_idx.numel() != B or int(mu_idx.min()) < 0 or int(mu_idx.max()) >= int(num_seqs):
+                raise IndexError("mu_idx out of range for the mu2 table")
+        plan = self._plan(B, T, F)
+        plan.load_inputs(x, mu_idx, num_segs, eps)
+        grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in self._plist)
+        if grad_on:
+            if self._anchor is None or self._anchor.device != x.device:
+                self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
+            out = _StepFn.apply(self, plan, self._anchor, *self._plist)
+        else:
+            plan.run_forward()
+            out = plan.out.clone()
+        self._publish(plan)
+        lb, log_qy, log_px_z, nk1, nk2, log_pmu2 = (out[i] for i in _OUT_ORDER)
+        if self.ref_log_qy:                      # reference returns mean(+CE) (simple_fhvae.py:37,122)
+            log_qy = -log_qy.mean()
+        return lb, log_qy, log_px_z, nk1, nk2, log_pmu2
+
+    def _publish(self, plan: "_Plan"):
+        """Attributes the reference's callers read (utils.py:52,58)."""
+        z1h, z2h = plan.z1head, plan.z2head
+        Z1, Z2 = self.z1_dim, self.z2_dim
+        self.qz1_x = [z1h[:, :Z1], z1h[:, Z1:]]
+        self.qz2_x = [z2h[:, :Z2], z2h[:, Z2:]]
+        self.px_z = plan.px_views()
+        self.pz2 = [plan.mu2, np.float32(PZ2_LOGVAR)]
+        self.z1_sample, self.z2_sample = plan.zcat[:, :Z1], plan.zcat[:, Z1:]
+        self.nan_flag = plan.nan_flag
+
+    # subclasses: _make_plan(B, T, F)
+
+
+class _StepFn(torch.autograd.Function):
+    """One autograd node for the whole step: forward replays the forward call list, backward the
+    BPTT/wgrad list, returning views of one flat gradient buffer (no per-parameter kernels)."""
+
+    @staticmethod
+    def forward(ctx, model, plan, anchor, *params):
+        plan.run_forward()
+        ctx.model, ctx.plan = model, plan
+        return plan.out.clone()               # (6,B): lb, log_px, nk1, nk2, log_pmu2, log_qy
+
+    @staticmethod
+    def backward(ctx, gout):
+        model, plan = ctx.model, ctx.plan
+        k = model._free_grad_slot()
+        gflat = plan.run_backward(gout, k)
+        grads = [gflat[model._off[n]:model._off[n] + p.numel()].view(model._shape[n])
+                 if p.requires_grad else None
+                 for n, p in zip(model._names, model._plist)]
+        return (None, None, None, *grads)
+
+
+# =====================================================================================
+# plans
+# =====================================================================================
+class _Plan:
+    """Workspaces + call lists for one (model, B, T, F).  Sub-classes fill fwd / bwd lists."""
+
+    def __init__(self, m: _FHVAECore, B: int, T: int, F: int):
+        self.m, self.B, self.T, self.F = m, B, T, F
+        self.dev = m._flat.device
+        self.mode = m.gemm_mode
+        Z1, Z2, N = m.z1_dim, m.z2_dim, m.mu2_table.shape[0]
+        self.Z1, self.Z2, self.N = Z1, Z2, N
+        f = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
+        self.f = f
+        # static inputs
+        self.x = f(B, T, F)
+        self.idx = torch.zeros(B, dtype=torch.int64, device=self.dev)
+        self.nsegs = torch.ones(B, dtype=torch.int64, device=self.dev)
+        self.eps1, self.eps2 = f(B, Z1), f(B, Z2)
+        # forward state
+        self.z1head, self.z2head = f(B, 2 * Z1), f(B, 2 * Z2)
+        self.zcat = f(B, Z1 + Z2)                     # [z1_sample | z2_sample]
+        self.mu2 = f(B, Z2)
+        self.out = f(6, B)                            # lb, log_px, nk1, nk2, log_pmu2, log_qy
+        self.nsplit = _lib.fn("fhvae_disc_nsplit")(B, N)
+        self.part = f(self.nsplit, B, 2)
+        self.tgt, self.lse = f(B), f(B)
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=self.dev)
+        self.fwd = CallList()
+        self.bwd: List[Optional[CallList]] = [None, None]
+        self.gout = f(6, B)
+        self._graph_fwd = None
+        self._graph_bwd = [None, None]
+
+    # ---- inputs / outputs
+    def load_inputs(self, x, mu_idx, num_segs, eps):
+        self.x.copy_(x, non_blocking=True)
+        self.idx.copy_(mu_idx, non_blocking=True)
+        if torch.is_tensor(num_segs):
+            self.nsegs.copy_(num_segs, non_blocking=True)
+        else:
+            self.nsegs.fill_(int(num_segs))
+        if eps is not None:
+            self.eps1.copy_(eps["z1"].reshape(self.eps1.shape), non_blocking=True)
+            self.eps2.copy_(eps["z2"].reshape(self.eps2.shape), non_blocking=True)
+        else:                                        # torch.randn_like, simple_fhvae.py:214
+            self.eps2.normal_()
+            self.eps1.normal_()
+
+    # ---- execution
+    def run_forward(self):
+        if self.m.use_cuda_graphs:
+            if self._graph_fwd is None:
+                self._graph_fwd = self._capture(lambda: self.fwd.run(current_stream_ptr()))
+            self._graph_fwd.replay()
+        else:
+            self.fwd.run(current_stream_ptr())
+
+    def run_backward(self, gout, k: int) -> torch.Tensor:
+        gflat = self.m._grad_buffer(k)
+        if self.bwd[k] is None:
+            self.bwd[k] = self._build_bwd(gflat)
+        self.gout.copy_(gout)
+        if self.m.use_cuda_graphs:
+            if self._graph_bwd[k] is None:
+                self._graph_bwd[k] = self._capture(lambda: self.bwd[k].run(current_stream_ptr()))
+            self._graph_bwd[k].replay()
+        else:
+            self.bwd[k].run(current_stream_ptr())
+        return gflat
+
+    def _capture(self, f):
+        # warm up on a side stream (lazy module loading must not happen inside capture), then capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            f()
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            f()
+        return g
+
+    # ---- shared tail: gather + ELBO + discriminative term
+    def _tail_fwd(self, xhead, xs_b, xs_t, lv_off):
+        c, m, B = self.fwd, self.m, self.B
+        tab = ptr(m.mu2_table)
+        c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N)
+        c.add("fhvae_elbo_fwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
+              ptr(self.z2head), ptr(self.mu2), ptr(self.nsegs), ptr(self.out), ptr(self.nan_flag),
+              B, self.T, self.F, self.Z1, self.Z2)
+        c.add("fhvae_disc_fwd_partial", ptr(self.z2head), 2 * self.Z2, tab, self.N, self.Z2,
+              ptr(self.part), self.nsplit, B)
+        c.add("fhvae_disc_target", ptr(self.z2head), 2 * self.Z2, ptr(self.mu2), ptr(self.tgt), B, self.Z2)
+        c.add("fhvae_disc_combine", ptr(self.part), self.nsplit, ptr(self.tgt), ptr(self.out, 5 * B),
+              ptr(self.lse), B)
+
+    def _tail_bwd(self, c: CallList, gflat, xhead, dxhead, xs_b, xs_t, lv_off):
+        """coef from upstream grads; ELBO bwd; disc bwd; table gradient (dense + sparse rows)."""
+        m, B, Z2 = self.m, self.B, self.Z2
+        f = self.f
+        if not hasattr(self, "coef"):
+            self.coef = f(4, B)
+            self.dz1head, self.dz2head = f(B, 2 * self.Z1), f(B, 2 * Z2)
+            self.dmu2 = f(B, Z2)
+            self.sumpm = f(self.nsplit, B, Z2)
+            self.touched = torch.zeros(B, dtype=torch.int32, device=self.dev)
+            self.nsegs_f = f(B)
+        gout, coef = self.gout, self.coef
+        detach_px, prior_grad = m.detach_px, m.prior_grad
+
+        def prep():
+            # out rows: 0 lb, 1 log_px, 2 nk1, 3 nk2, 4 log_pmu2, 5 log_qy
+            torch.add(gout[1:4], gout[0], out=coef[0:3])
+            if detach_px:
+                coef[0].zero_()
+            if prior_grad:
+                self.nsegs_f.copy_(self.nsegs)
+                torch.div(gout[0], self.nsegs_f, out=coef[3])
+                coef[3].add_(gout[4])
+            else:
+                coef[3].zero_()
+        c.torch_op(prep)
+        dtab = ptr(gflat, m._off["mu2_table"])
+        tab = ptr(m.mu2_table)
+        c.add("fhvae_elbo_bwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
+              ptr(self.z2head), ptr(self.mu2), ptr(coef), ptr(dxhead), ptr(self.dz1head),
+              ptr(self.dz2head), ptr(self.dmu2), B, self.T, self.F, self.Z1, Z2)
+        g_qy = ptr(gout, 5 * B)
+        c.add("fhvae_disc_bwd_segs", ptr(self.z2head), 2 * Z2, tab, self.N, Z2, ptr(self.lse),
+              ptr(self.sumpm), self.nsplit, B)
+        c.add("fhvae_disc_bwd_rows", ptr(self.z2head), 2 * Z2, tab, self.N, Z2, ptr(self.lse), g_qy,
+              dtab, B)
+        c.add("fhvae_disc_bwd_finish", ptr(self.z2head), 2 * Z2, ptr(self.mu2), ptr(self.sumpm),
+              self.nsplit, g_qy, ptr(self.dz2head), 2 * Z2, ptr(self.dmu2), B, Z2)
+        c.add("fhvae_mu2_scatter_reduce", ptr(self.dmu2), ptr(self.idx), dtab, ptr(self.touched), B, Z2,
+              self.N)
+
+    def _head_fwd(self, c, srcs, wname, bname, head, Z):
+        """head (B,2Z) = sum_l src_l @ W[:, cols_l]^T + b, W = [mulayer.weight ; logvar_layer.weight]."""
+        m, B = self.m, self.B
+        ldw = sum(k for _, _, k in srcs)
+        col = 0
+        for i, (src, lds, K) in enumerate(srcs):
+            c.gemm([gemm_nt(src, lds, m.poff(wname, col), ldw, ptr(head), 2 * Z, B, 2 * Z, K,
+                            bias=m.poff(bname) if i == 0 else 0, beta=0.0 if i == 0 else 1.0)], self.mode)
+            col += K
+
+
+def _lstm_names(prefix: str, l: int):
+    return (f"{prefix}.lstm.weight_ih_l{l}", f"{prefix}.lstm.weight_hh_l{l}",
+            f"{prefix}.lstm.bias_ih_l{l}", f"{prefix}.lstm.bias_hh_l{l}")
+
+
+class _FHVAEPlan(_Plan):
+    NETS = (("z2", "z2_pre_encoder"), ("z1", "z1_pre_encoder"), ("dec", "pre_decoder"))
+
+    def __init__(self, m: "FHVAE", B, T, F):
+        super().__init__(m, B, T, F)
+        f, Z1, Z2 = self.f, self.Z1, self.Z2
+        self.H = {"z2": m.z2_hus[0], "z1": m.z1_hus[0], "dec": m.x_hus[0]}
+        self.L = {"z2": len(m.z2_hus), "z1": len(m.z1_hus), "dec": len(m.x_hus)}
+        self.x_tm = f(T, B, F)
+        self.bsum = f(m._bias_block_len)
+        self.h, self.c, self.acts, self.P = {}, {}, {}, {}
+        for k, _ in self.NETS:
+            H = self.H[k]
+            for l in range(self.L[k]):
+                self.h[k, l], self.c[k, l] = f(T, B, H), f(T, B, H)
+                self.acts[k, l] = f(T, B, 4 * H)
+                if not (k == "dec" and l == 0):
+                    self.P[k, l] = f(T, B, 4 * H)
+        self.Q = {"z1": f(B, 4 * self.H["z1"]), "dec": f(B, 4 * self.H["dec"])}
+        self.xhead = f(T, B, 2 * F)
+        self._build_fwd()
+
+    def px_views(self):
+        F = self.F
+        xh = self.xhead.permute(1, 0, 2)             # (B,T,2F) view of the time-major buffer
+        return [xh[..., :F], xh[..., F:]]
+
+    def _bs(self, k, l):                             # fused (b_ih + b_hh) pointer
+        return ptr(self.bsum, self.m._bias_off[k, l])
+
+    def _build_fwd(self):
+        c, m, B, T, F = self.fwd, self.m, self.B, self.T, self.F
+        Z1, Z2, mode = self.Z1, self.Z2, self.mode
+        TB = T * B
+        pre = dict(self.NETS)
+        c.add("fhvae_transpose_bt", ptr(self.x), ptr(self.x_tm), B, T, F)
+        c.add("fhvae_add2", ptr(self.bsum), m.poff(m._bias_first[0]), m.poff(m._bias_first[1]),
+              m._bias_block_len)
+        Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
+        wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
+        wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
+        # both encoders' layer-0 projections of x in one grouped launch
+        c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z2), F, ptr(self.P["z2", 0]), 4 * Hz2, TB, 4 * Hz2, F,
+                        bias=self._bs("z2", 0)),
+                gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
+                        4 * Hz1, F, bias=self._bs("z1", 0))], mode)
+
+        def stack(k, q0):
+            H = self.H[k]
+            for l in range(self.L[k]):
+                wih, whh, _, _ = _lstm_names(pre[k], l)
+                if l > 0:
+                    c.gemm([gemm_nt(ptr(self.h[k, l - 1]), H, m.poff(wih), H, ptr(self.P[k, l]), 4 * H, TB,
+                                    4 * H, H, bias=self._bs(k, l))], mode)
+                Pp = ptr(self.P[k, l]) if (k, l) in self.P else None
+                Qp = q0 if l == 0 else None
+                c.add("fhvae_lstm_fwd", Pp, Qp, m.poff(whh), ptr(self.h[k, l]), ptr(self.c[k, l]),
+                      ptr(self.acts[k, l]), T, B, H, mode)
+
+        def final_h(k):
+            H = self.H[k]
+            return [(ptr(self.h[k, l], (T - 1) * B * H), H, H) for l in range(self.L[k])]
+
+        # z2 encoder -> head -> sample (into zcat[:, Z1:])
+        stack("z2", None)
+        self._head_fwd(c, final_h("z2"), "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias",
+                       self.z2head, Z2)
+        c.add("fhvae_reparam_fwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.zcat, Z1), Z1 + Z2, B, Z2)
+        # z1 encoder: time-invariant z2 part of the input projection is done once (Q)
+        c.gemm([gemm_nt(ptr(self.zcat, Z1), Z1 + Z2, m.poff(wih_z1, F), F + Z2, ptr(self.Q["z1"]), 4 * Hz1,
+                        B, 4 * Hz1, Z2)], mode)
+        stack("z1", ptr(self.Q["z1"]))
+        self._head_fwd(c, final_h("z1"), "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias",
+                       self.z1head, Z1)
+        c.add("fhvae_reparam_fwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.zcat), Z1 + Z2, B, Z1)
+        # decoder: the whole layer-0 input is time-invariant
+        wih_d, _, _, _ = _lstm_names(pre["dec"], 0)
+        c.gemm([gemm_nt(ptr(self.zcat), Z1 + Z2, m.poff(wih_d), Z1 + Z2, ptr(self.Q["dec"]), 4 * Hd, B,
+                        4 * Hd, Z1 + Z2, bias=self._bs("dec", 0))], mode)
+        stack("dec", ptr(self.Q["dec"]))
+        Ld = self.L["dec"]
+        c.gemm([gemm_nt(ptr(self.h["dec", Ld - 1]), Hd, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
+                        ptr(self.xhead), 2 * F, TB, 2 * F, Hd,
+                        bias=m.poff("dec_gauss_layer.mulayer.bias"))], mode)
+        self._tail_fwd(self.xhead, 2 * F, B * 2 * F, F)
+
+    def _build_bwd(self, gflat) -> CallList:
+        c, m, B, T, F = CallList(), self.m, self.B, self.T, self.F
+        Z1, Z2, mode, f = self.Z1, self.Z2, self.mode, self.f
+        TB = T * B
+        pre = dict(self.NETS)
+        g = lambda name, extra=0: ptr(gflat, m._off[name] + extra)
+        if not hasattr(self, "dxhead"):
+            Hmax = max(self.H.values())
+            self.dxhead = f(T, B, 2 * F)
+            self.dhA, self.dhB = f(T, B, Hmax), f(T, B, Hmax)
+            self.dhT = {(k, l): f(B, self.H[k]) for k in ("z1", "z2") for l in range(self.L[k])}
+            self.dg, self.dgsum = {}, {}
+            for k, _ in self.NETS:
+                for l in range(self.L[k]):
+                    self.dg[k, l] = f(T, B, 4 * self.H[k])
+                    self.dgsum[k, l] = f(B, 4 * self.H[k])
+            self.dzcat = f(B, Z1 + Z2)
+            self.dh_rec, self.dc = f(2, B, Hmax), f(B, Hmax)
+        self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
+        wg: List = []          # deferred weight-gradient GEMMs (one grouped launch at the end)
+        cs: List = []          # deferred bias column sums
+
+        def stack_bwd(k, dh_all_top, dh_last_of):
+            """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum."""
+            H = self.H[k]
+            dh_all = dh_all_top
+            for l in reversed(range(self.L[k])):
+                wih, whh, bih, bhh = _lstm_names(pre[k], l)
+                c.add("fhvae_lstm_bwd", dh_all, dh_last_of(l), m.poff(whh), ptr(self.c[k, l]),
+                      ptr(self.acts[k, l]), ptr(self.dg[k, l]), ptr(self.dgsum[k, l]), ptr(self.dh_rec),
+                      ptr(self.dc), T, B, H, mode)
+                # dW_hh = dg[1:]^T @ h[:-1]
+                if T > 1:
+                    wg.append(gemm_tn(ptr(self.dg[k, l], B * 4 * H), 4 * H, ptr(self.h[k, l]), H, g(whh), H,
+                                      4 * H, H, (T - 1) * B))
+                else:
+                    c.torch_op(lambda o=m._off[whh], n=4 * H * H: gflat[o:o + n].zero_())
+                cs.append(ColsumProblem(ptr(self.dgsum[k, l]), g(bih), g(bhh), 4 * H, B, 4 * H))
+                if l > 0:
+                    wg.append(gemm_tn(ptr(self.dg[k, l]), 4 * H, ptr(self.h[k, l - 1]), H, g(wih), H,
+                                      4 * H, H, TB))
+                    nxt = self.dhA if dh_all != ptr(self.dhA) else self.dhB
+                    c.gemm([gemm_nn(ptr(self.dg[k, l]), 4 * H, m.poff(wih), H, ptr(nxt), H, TB, H, 4 * H)], mode)
+                    dh_all = ptr(nxt)
+
+        def head_bwd(k, dhead, Z, wname, bname):
+            """dW/db of a Gaussian head on the final hidden states + the dh_last they receive."""
+            H, L = self.H[k], self.L[k]
+            cs.append(ColsumProblem(ptr(dhead), g(bname), None, 2 * Z, B, 2 * Z))
+            probs = []
+            for l in range(L):
+                hT = ptr(self.h[k, l], (T - 1) * B * H)
+                wg.append(gemm_tn(ptr(dhead), 2 * Z, hT, H, g(wname, l * H), L * H, 2 * Z, H, B))
+                probs.append(gemm_nn(ptr(dhead), 2 * Z, m.poff(wname, l * H), L * H, ptr(self.dhT[k, l]), H,
+                                     B, H, 2 * Z))
+            c.gemm(probs, mode)
+
+        # ---------------- decoder
+        Hd, Ld = self.H["dec"], self.L["dec"]
+        if not m.detach_px:
+            wg.append(gemm_tn(ptr(self.dxhead), 2 * F, ptr(self.h["dec", Ld - 1]), Hd,
+                              g("dec_gauss_layer.mulayer.weight"), Hd, 2 * F, Hd, TB))
+            cs.append(ColsumProblem(ptr(self.dxhead), g("dec_gauss_layer.mulayer.bias"), None, 2 * F, TB, 2 * F))
+            c.gemm([gemm_nn(ptr(self.dxhead), 2 * F, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
+                            ptr(self.dhA), Hd, TB, Hd, 2 * F)], mode)
+            stack_bwd("dec", ptr(self.dhA), lambda l: None)
+            wih_d = _lstm_names(pre["dec"], 0)[0]
+            wg.append(gemm_tn(ptr(self.dgsum["dec", 0]), 4 * Hd, ptr(self.zcat), Z1 + Z2, g(wih_d), Z1 + Z2,
+                              4 * Hd, Z1 + Z2, B))
+            c.gemm([gemm_nn(ptr(self.dgsum["dec", 0]), 4 * Hd, m.poff(wih_d), Z1 + Z2, ptr(self.dzcat),
+                            Z1 + Z2, B, Z1 + Z2, 4 * Hd)], mode)
+            c.add("fhvae_reparam_bwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.dzcat), Z1 + Z2,
+                  ptr(self.dz1head), 2 * Z1, 1, B, Z1)
+        else:
+            # reference behaviour (simple_fhvae.py:113-115): decoder and z samples get no gradient
+            dec_names = [n for n in m._names if n.startswith(("pre_decoder", "dec_gauss_layer"))]
+            lo = min(m._off[n] for n in dec_names)
+            hi = max(m._off[n] + _prod(m._shape[n]) for n in dec_names)
+            c.torch_op(lambda: (gflat[lo:hi].zero_(), self.dzcat.zero_()))
+            assert all(lo <= m._off[n] < hi for n in dec_names)
+        # ---------------- z1 encoder
+        Hz1 = self.H["z1"]
+        head_bwd("z1", self.dz1head, Z1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias")
+        stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]))
+        wih_z1 = _lstm_names(pre["z1"], 0)[0]
+        wg.append(gemm_tn(ptr(self.dg["z1", 0]), 4 * Hz1, ptr(self.x_tm), F, g(wih_z1), F + Z2, 4 * Hz1, F, TB))
+        wg.append(gemm_tn(ptr(self.dgsum["z1", 0]), 4 * Hz1, ptr(self.zcat, Z1), Z1 + Z2, g(wih_z1, F), F + Z2,
+                          4 * Hz1, Z2, B))
+        # dz2_sample = (decoder part, already in dzcat[:, Z1:]) + dQ @ W_z
+        c.gemm([gemm_nn(ptr(self.dgsum["z1", 0]), 4 * Hz1, m.poff(wih_z1, F), F + Z2, ptr(self.dzcat, Z1),
+                        Z1 + Z2, B, Z2, 4 * Hz1, beta=1.0)], mode)
+        c.add("fhvae_reparam_bwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.dzcat, Z1), Z1 + Z2,
+              ptr(self.dz2head), 2 * Z2, 1, B, Z2)
+        # ---------------- z2 encoder
+        Hz2 = self.H["z2"]
+        head_bwd("z2", self.dz2head, Z2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias")
+        stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]))
+        wih_z2 = _lstm_names(pre["z2"], 0)[0]
+        wg.append(gemm_tn(ptr(self.dg["z2", 0]), 4 * Hz2, ptr(self.x_tm), F, g(wih_z2), F, 4 * Hz2, F, TB))
+        # ---------------- deferred weight / bias gradients
+        c.gemm(wg, mode)
+        c.colsum(cs)
+        return c
+
+
+class _SimplePlan(_Plan):
+    """Fully-connected variant (simple_fhvae.py:127-244): Linear+ReLU pre-encoders / pre-decoder."""
+
+    def __init__(self, m: "SimpleFHVAE", B, T, F):
+        super().__init__(m, B, T, F)
+        f = self.f
+        TF = T * F
+        self.TF = TF
+        self.a = {("z2", 0): f(B, m.z2_hus[0]), ("z2", 1): f(B, m.z2_hus[1]),
+                  ("z1", 0): f(B, m.z1_hus[0]), ("z1", 1): f(B, m.z1_hus[1]),
+                  ("dec", 0): f(B, m.x_hus[0]), ("dec", 1): f(B, m.x_hus[1])}
+        self.xhead = f(B, 2 * TF)
+        self._build_fwd()
+
+    def px_views(self):
+        xh = self.xhead
+        return [xh[:, :self.TF].view(self.B, self.T, self.F), xh[:, self.TF:].view(self.B, self.T, self.F)]
+
+    def _build_fwd(self):
+        c, m, B, TF = self.fwd, self.m, self.B, self.TF
+        Z1, Z2, mode = self.Z1, self.Z2, self.mode
+        w = lambda n: m.poff(n + ".linear.weight")
+        bia = lambda n: m.poff(n + ".linear.bias")
+        h0, h1 = m.z2_hus
+        x = ptr(self.x)
+        c.gemm([gemm_nt(x, TF, w("z2_pre_encoder.fc1"), TF, ptr(self.a["z2", 0]), h0, B, h0, TF,
+                        bias=bia("z2_pre_encoder.fc1"), relu=1)], mode)
+        c.gemm([gemm_nt(ptr(self.a["z2", 0]), h0, w("z2_pre_encoder.fc2"), h0, ptr(self.a["z2", 1]), h1, B, h1,
+                        h0, bias=bia("z2_pre_encoder.fc2"), relu=1)], mode)
+        self._head_fwd(c, [(ptr(self.a["z2", 1]), h1, h1)], "z2_gauss_layer.mulayer.weight",
+                       "z2_gauss_layer.mulayer.bias", self.z2head, Z2)
+        c.add("fhvae_reparam_fwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.zcat, Z1), Z1 + Z2, B, Z2)
+        h0, h1 = m.z1_hus
+        ld1 = TF + Z2
+        c.gemm([gemm_nt(x, TF, w("z1_pre_encoder.fc1"), ld1, ptr(self.a["z1", 0]), h0, B, h0, TF,
+                        bias=bia("z1_pre_encoder.fc1"))], mode)
+        c.gemm([gemm_nt(ptr(self.zcat, Z1), Z1 + Z2, m.poff("z1_pre_encoder.fc1.linear.weight", TF), ld1,
+                        ptr(self.a["z1", 0]), h0, B, h0, Z2, beta=1.0, relu=1)], mode)
+        c.gemm([gemm_nt(ptr(self.a["z1", 0]), h0, w("z1_pre_encoder.fc2"), h0, ptr(self.a["z1", 1]), h1, B, h1,
+                        h0, bias=bia("z1_pre_encoder.fc2"), relu=1)], mode)
+        self._head_fwd(c, [(ptr(self.a["z1", 1]), h1, h1)], "z1_gauss_layer.mulayer.weight",
+                       "z1_gauss_layer.mulayer.bias", self.z1head, Z1)
+        c.add("fhvae_reparam_fwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.zcat), Z1 + Z2, B, Z1)
+        h0, h1 = m.x_hus
+        c.gemm([gemm_nt(ptr(self.zcat), Z1 + Z2, w("pre_decoder.fc1"), Z1 + Z2, ptr(self.a["dec", 0]), h0, B,
+                        h0, Z1 + Z2, bias=bia("pre_decoder.fc1"), relu=1)], mode)
+        c.gemm([gemm_nt(ptr(self.a["dec", 0]), h0, w("pre_decoder.fc2"), h0, ptr(self.a["dec", 1]), h1, B, h1,
+                        h0, bias=bia("pre_decoder.fc2"), relu=1)], mode)
+        c.gemm([gemm_nt(ptr(self.a["dec", 1]), h1, m.poff("dec_gauss_layer.mulayer.weight"), h1,
+                        ptr(self.xhead), 2 * TF, B, 2 * TF, h1,
+                        bias=m.poff("dec_gauss_layer.mulayer.bias"))], mode)
+        self._tail_fwd(self.xhead, 2 * TF, self.F, TF)
+
+    def _build_bwd(self, gflat) -> CallList:
+        c, m, B, TF = CallList(), self.m, self.B, self.TF
+        Z1, Z2, mode, f = self.Z1, self.Z2, self.mode, self.f
+        g = lambda name, extra=0: ptr(gflat, m._off[name] + extra)
+        if not hasattr(self, "dxhead"):
+            self.dxhead = f(B, 2 * TF)
+            self.da = {k: torch.zeros_like(v) for k, v in self.a.items()}
+            self.dzcat = f(B, Z1 + Z2)
+        self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * TF, self.F, TF)
+        wg, cs = [], []
+        W = lambda n: n + ".linear.weight"
+        Bn = lambda n: n + ".linear.bias"
+
+        def linear_bwd(dy, N, xin, ldx, K, wname, bname, ldw=None, wcol=0, dx=None, lddx=None, beta=0.0,
+                       bias=True):
+            """dy (B,N) -> dW (N,K) [+ db], optional dx (B,K)."""
+            ldw = ldw or K
+            wg.append(gemm_tn(dy, N, xin, ldx, g(wname, wcol), ldw, N, K, B))
+            if bias:
+                cs.append(ColsumProblem(dy, g(bname), None, N, B, N))
+            if dx is not None:
+                c.gemm([gemm_nn(dy, N, m.poff(wname, wcol), ldw, dx, lddx, B, K, N, beta=beta)], mode)
+
+        def relu_bwd(k):
+            c.add("fhvae_relu_bwd", ptr(self.da[k]), ptr(self.a[k]), self.a[k].numel())
+
+        # ---------------- decoder
+        h0, h1 = m.x_hus
+        if not m.detach_px:
+            linear_bwd(ptr(self.dxhead), 2 * TF, ptr(self.a["dec", 1]), h1, h1, "dec_gauss_layer.mulayer.weight",
+                       "dec_gauss_layer.mulayer.bias", dx=ptr(self.da["dec", 1]), lddx=h1)
+            relu_bwd(("dec", 1))
+            linear_bwd(ptr(self.da["dec", 1]), h1, ptr(self.a["dec", 0]), h0, h0, W("pre_decoder.fc2"),
+                       Bn("pre_decoder.fc2"), dx=ptr(self.da["dec", 0]), lddx=h0)
+            relu_bwd(("dec", 0))
+            linear_bwd(ptr(self.da["dec", 0]), h0, ptr(self.zcat), Z1 + Z2, Z1 + Z2, W("pre_decoder.fc1"),
+                       Bn("pre_decoder.fc1"), dx=ptr(self.dzcat), lddx=Z1 + Z2)
+            c.add("fhvae_reparam_bwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.dzcat), Z1 + Z2,
+                  ptr(self.dz1head), 2 * Z1, 1, B, Z1)
+        else:
+            dec_names = [n for n in m._names if n.startswith(("pre_decoder", "dec_gauss_layer"))]
+            lo = min(m._off[n] for n in dec_names)
+            hi = max(m._off[n] + _prod(m._shape[n]) for n in dec_names)
+            assert all(lo <= m._off[n] < hi for n in dec_names)
+            c.torch_op(lambda: (gflat[lo:hi].zero_(), self.dzcat.zero_()))
+        # ---------------- z1 encoder
+        h0, h1 = m.z1_hus
+        ld1 = TF + Z2
+        linear_bwd(ptr(self.dz1head), 2 * Z1, ptr(self.a["z1", 1]), h1, h1, "z1_gauss_layer.mulayer.weight",
+                   "z1_gauss_layer.mulayer.bias", dx=ptr(self.da["z1", 1]), lddx=h1)
+        relu_bwd(("z1", 1))
+        linear_bwd(ptr(self.da["z1", 1]), h1, ptr(self.a["z1", 0]), h0, h0, W("z1_pre_encoder.fc2"),
+                   Bn("z1_pre_encoder.fc2"), dx=ptr(self.da["z1", 0]), lddx=h0)
+        relu_bwd(("z1", 0))
+        linear_bwd(ptr(self.da["z1", 0]), h0, ptr(self.x), TF, TF, W("z1_pre_encoder.fc1"),
+                   Bn("z1_pre_encoder.fc1"), ldw=ld1)
+        linear_bwd(ptr(self.da["z1", 0]), h0, ptr(self.zcat, Z1), Z1 + Z2, Z2, W("z1_pre_encoder.fc1"), None,
+                   ldw=ld1, wcol=TF, dx=ptr(self.dzcat, Z1), lddx=Z1 + Z2, beta=1.0, bias=False)
+        c.add("fhvae_reparam_bwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.dzcat, Z1), Z1 + Z2,
+              ptr(self.dz2head), 2 * Z2, 1, B, Z2)
+        # ---------------- z2 encoder
+        h0, h1 = m.z2_hus
+        linear_bwd(ptr(self.dz2head), 2 * Z2, ptr(self.a["z2", 1]), h1, h1, "z2_gauss_layer.mulayer.weight",
+                   "z2_gauss_layer.mulayer.bias", dx=ptr(self.da["z2", 1]), lddx=h1)
+        relu_bwd(("z2", 1))
+        linear_bwd(ptr(self.da["z2", 1]), h1, ptr(self.a["z2", 0]), h0, h0, W("z2_pre_encoder.fc2"),
+                   Bn("z2_pre_encoder.fc2"), dx=ptr(self.da["z2", 0]), lddx=h0)
+        relu_bwd(("z2", 0))
+        linear_bwd(ptr(self.da["z2", 0]), h0, ptr(self.x), TF, TF, W("z2_pre_encoder.fc1"),
+                   Bn("z2_pre_encoder.fc1"))
+        c.gemm(wg, mode)
+        c.colsum(cs)
+        return c
+
+
+# =====================================================================================
+# public modules
+# =====================================================================================
+def _gauss_specs(prefix, in_dim, z):
+    return [(f"{prefix}.mulayer.weight", (z, in_dim)), (f"{prefix}.logvar_layer.weight", (z, in_dim)),
+            (f"{prefix}.mulayer.bias", (z,)), (f"{prefix}.logvar_layer.bias", (z,))]
+
+
+def _check_adjacent(off, shape, a, b):
+    assert off[b] == off[a] + _prod(shape[a]), f"{a} and {b} must be adjacent in the flat buffer"
+
+
+class SimpleFHVAE(_FHVAECore):
+    """simple_fhvae.py:8-124.  Extra keyword-only arguments (all optional) configure what the
+    reference leaves implicit: ``num_seqs`` (rows of the persistent mu2 table, Appendix A1),
+    ``detach_px`` / ``prior_grad`` / ``ref_log_qy`` (reproduce the reference's gradient flow and its
+    scalar +CE ``log_qy``: Appendix A2-A4), ``gemm_mode``, ``use_cuda_graphs``."""
+
+    model = "simple_fhvae"
+
+    def __init__(self, input_size, z1_hus=[128, 128], z2_hus=[128, 128], z1_dim=16, z2_dim=16,
+                 x_hus=[128, 128], *, num_seqs=1000, init_std=1.0, detach_px=False, prior_grad=True,
+                 ref_log_qy=False, gemm_mode=_lib.MODE_F32_SIMT, use_cuda_graphs=False):
+        super().__init__()
+        self.model = "simple_fhvae"
+        self.pz1 = [0.0, np.float32(0.0)]
+        self.pmu2 = [0.0, np.float32(PMU2_LOGVAR)]
+        self.z1_hus, self.z2_hus, self.x_hus = _as_int_list(z1_hus), _as_int_list(z2_hus), _as_int_list(x_hus)
+        self.z1_dim, self.z2_dim = int(z1_dim), int(z2_dim)
+        self.input_size = int(input_size)
+        self.detach_px, self.prior_grad, self.ref_log_qy = detach_px, prior_grad, ref_log_qy
+        self.gemm_mode, self.use_cuda_graphs = gemm_mode, use_cuda_graphs
+        assert len(self.z1_hus) == len(self.z2_hus) == len(self.x_hus) == 2, "two FC layers per block"
+        assert self.z1_dim % 4 == 0 and self.z2_dim % 4 == 0
+        I, Z1, Z2 = self.input_size, self.z1_dim, self.z2_dim
+        # default nn.Linear init drawn in the reference's construction order (simple_fhvae.py:31-36)
+        init, specs = {}, []
+
+        def lin(name, i, o):
+            l = nn.Linear(i, o)
+            init[name + ".weight"], init[name + ".bias"] = l.weight, l.bias
+            return [(name + ".weight", (o, i)), (name + ".bias", (o,))]
+
+        def gauss(prefix, i, z):
+            mu, lv = nn.Linear(i, z), nn.Linear(i, z)
+            init[prefix + ".mulayer.weight"], init[prefix + ".mulayer.bias"] = mu.weight, mu.bias
+            init[prefix + ".logvar_layer.weight"], init[prefix + ".logvar_layer.bias"] = lv.weight, lv.bias
+            return _gauss_specs(prefix, i, z)
+
+        specs += lin("z1_pre_encoder.fc1.linear", I + Z2, self.z1_hus[0])       # Appendix A6: z2 is concatenated
+        specs += lin("z1_pre_encoder.fc2.linear", self.z1_hus[0], self.z1_hus[1])
+        specs += lin("z2_pre_encoder.fc1.linear", I, self.z2_hus[0])
+        specs += lin("z2_pre_encoder.fc2.linear", self.z2_hus[0], self.z2_hus[1])
+        specs += gauss("z1_gauss_layer", self.z1_hus[1], Z1)
+        specs += gauss("z2_gauss_layer", self.z2_hus[1], Z2)
+        specs += lin("pre_decoder.fc1.linear", Z1 + Z2, self.x_hus[0])
+        specs += lin("pre_decoder.fc2.linear", self.x_hus[0], self.x_hus[1])
+        specs += gauss("dec_gauss_layer", self.x_hus[1], I)
+        specs.append(("mu2_table", (int(num_seqs), Z2)))
+        init["mu2_table"] = torch.empty(int(num_seqs), Z2).normal_(mean=0, std=init_std)   # :51
+        self._init_flat(specs, init)
+        for pfx in ("z1_gauss_layer", "z2_gauss_layer", "dec_gauss_layer"):
+            _check_adjacent(self._off, self._shape, pfx + ".mulayer.weight", pfx + ".logvar_layer.weight")
+            _check_adjacent(self._off, self._shape, pfx + ".mulayer.bias", pfx + ".logvar_layer.bias")
+
+    def _make_plan(self, B, T, F):
+        if T * F != self.input_size:
+            raise ValueError(f"x is (B,{T},{F}) but input_size={self.input_size}")
+        return _SimplePlan(self, B, T, F)
+
+
+class FHVAE(_FHVAECore):
+    """fhvae.py:4-14 signature; LSTM architecture per SURVEY.md Appendix B (the reference raises
+    NotImplementedError).  ``input_size`` is seg_len * feat_dim as passed by train_model.py:398-402."""
+
+    model = "fhvae"
+
+    def __init__(self, input_size: int, z1_hus: list = [256, 256], z2_hus: list = [256, 256],
+                 z1_dim: int = 32, z2_dim: int = 32, x_hus: list = [256, 256], *, seg_len=20,
+                 num_seqs=1000, init_std=1.0, detach_px=False, prior_grad=True, ref_log_qy=False,
+                 gemm_mode=_lib.MODE_F32_SIMT, use_cuda_graphs=False):
+        super().__init__()
+        self.model = "fhvae"
+        self.pz1 = [0.0, np.float32(0.0)]
+        self.pmu2 = [0.0, np.float32(PMU2_LOGVAR)]
+        self.z1_hus, self.z2_hus, self.x_hus = _as_int_list(z1_hus), _as_int_list(z2_hus), _as_int_list(x_hus)
+        self.z1_dim, self.z2_dim = int(z1_dim), int(z2_dim)
+        self.input_size, self.seg_len = int(input_size), int(seg_len)
+        if self.input_size % self.seg_len:
+            raise ValueError("input_size must be seg_len * feat_dim")
+        self.feat_dim = self.input_size // self.seg_len
+        self.detach_px, self.prior_grad, self.ref_log_qy = detach_px, prior_grad, ref_log_qy
+        self.gemm_mode, self.use_cuda_graphs = gemm_mode, use_cuda_graphs
+        for hus in (self.z1_hus, self.z2_hus, self.x_hus):
+            assert len(set(hus)) == 1 and hus[0] % 8 == 0, "one width per LSTM stack, multiple of 8"
+        F, Z1, Z2 = self.feat_dim, self.z1_dim, self.z2_dim
+        assert F % 4 == 0 and Z1 % 4 == 0 and Z2 % 4 == 0
+        nets = [("z1_pre_encoder", "z1", F + Z2, self.z1_hus), ("z2_pre_encoder", "z2", F, self.z2_hus),
+                ("pre_decoder", "dec", Z1 + Z2, self.x_hus)]
+        init: Dict[str, torch.Tensor] = {}
+        wspecs, bih, bhh, gspecs = [], [], [], {}
+
+        def lstm(prefix, in_dim, hus):
+            mod = nn.LSTM(in_dim, hus[0], num_layers=len(hus), batch_first=True)
+            for n, p in mod.named_parameters():
+                init[f"{prefix}.lstm.{n}"] = p
+                tgt = wspecs if n.startswith("weight") else (bih if n.startswith("bias_ih") else bhh)
+                tgt.append((f"{prefix}.lstm.{n}", tuple(p.shape)))
+
+        def gauss(prefix, i, z):
+            mu, lv = nn.Linear(i, z), nn.Linear(i, z)
+            init[prefix + ".mulayer.weight"], init[prefix + ".mulayer.bias"] = mu.weight, mu.bias
+            init[prefix + ".logvar_layer.weight"], init[prefix + ".logvar_layer.bias"] = lv.weight, lv.bias
+            gspecs[prefix] = _gauss_specs(prefix, i, z)
+
+        # construction order of the oracle (= reference order, simple_fhvae.py:31-36)
+        lstm(*[nets[0][0], nets[0][2], nets[0][3]])
+        lstm(*[nets[1][0], nets[1][2], nets[1][3]])
+        gauss("z1_gauss_layer", sum(self.z1_hus), Z1)
+        gauss("z2_gauss_layer", sum(self.z2_hus), Z2)
+        lstm(*[nets[2][0], nets[2][2], nets[2][3]])
+        gauss("dec_gauss_layer", self.x_hus[-1], F)
+        specs = wspecs + bih + bhh + gspecs["z1_gauss_layer"] + gspecs["z2_gauss_layer"] + gspecs["dec_gauss_layer"]
+        specs.append(("mu2_table", (int(num_seqs), Z2)))
+        init["mu2_table"] = torch.empty(int(num_seqs), Z2).normal_(mean=0, std=init_std)
+        self._init_flat(specs, init)
+        # fused-bias bookkeeping: b_ih block and b_hh block are contiguous and identically ordered
+        self._bias_first = (bih[0][0], bhh[0][0])
+        self._bias_block_len = sum(_prod(s) for _, s in bih)
+        assert self._off[bhh[0][0]] == self._off[bih[0][0]] + self._bias_block_len
+        self._bias_off = {}
+        short = {"z1_pre_encoder": "z1", "z2_pre_encoder": "z2", "pre_decoder": "dec"}
+        for name, _ in bih:
+            prefix, _, leaf = name.split(".")
+            self._bias_off[short[prefix], int(leaf.rsplit("l", 1)[1])] = self._off[name] - self._off[bih[0][0]]
+        for pfx in ("z1_gauss_layer", "z2_gauss_layer", "dec_gauss_layer"):
+            _check_adjacent(self._off, self._shape, pfx + ".mulayer.weight", pfx + ".logvar_layer.weight")
+            _check_adjacent(self._off, self._shape, pfx + ".mulayer.bias", pfx + ".logvar_layer.bias")
+
+    def _make_plan(self, B, T, F):
+        if T != self.seg_len or F != self.feat_dim:
+            raise ValueError(f"x is (B,{T},{F}) but the model was built for seg_len={self.seg_len}, "
+                             f"feat_dim={self.feat_dim}")
+        return _FHVAEPlan(self, B, T, F)
+
+
+def loss_function(lower_bound, log_qy, alpha=10.0):
+    """train_model.py:243-251."""
+    return -1 * torch.mean(lower_bound + alpha * log_qy)

@@ -1,0 +1,73 @@
+"""``FusedAdam``: drop-in for ``torch.optim.Adam(model.parameters(), lr, betas)`` as constructed at
+train_model.py:409-411, running one flat multi-tensor kernel (``fhvae_adam_flat``) per model instead
+of the reference's per-tensor foreach update (train_model.py:454)."""
+from __future__ import annotations
+
+from typing import Dict
+
+import torch
+
+from . import _lib
+from .plan import current_stream_ptr, ptr
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
+        defaults = dict(lr=lr, betas=betas, eps=eps)
+        super().__init__(params, defaults)
+        self.grad_scale = float(grad_scale)
+        self._flat_state: Dict[int, dict] = {}
+        self._modules = []
+        seen = set()
+        for group in self.param_groups:
+            for p in group["params"]:
+                owner = getattr(p, "_fhvae", None)
+                if owner is None:
+                    raise ValueError("FusedAdam only drives parameters of pytorch_scalablefhvae_b200 modules")
+                mod = owner[0]()
+                if id(mod) not in seen:
+                    seen.add(id(mod))
+                    self._modules.append(mod)
+        for mod in self._modules:
+            if len([p for g in self.param_groups for p in g["params"] if p._fhvae[0]() is mod]) != len(mod._plist):
+                raise ValueError("FusedAdam needs all parameters of a model (model.parameters())")
+
+    def _state_for(self, mod):
+        flat = mod._ensure_flat()
+        st = self._flat_state.get(id(mod))
+        if st is None or st["m"].device != flat.device:
+            old = st
+            st = {"m": torch.zeros_like(flat), "v": torch.zeros_like(flat),
+                  "step": torch.zeros(1, dtype=torch.int32, device=flat.device),
+                  "done": torch.zeros(1, dtype=torch.int32, device=flat.device)}
+            if old is not None:
+                st["m"].copy_(old["m"]); st["v"].copy_(old["v"]); st["step"].copy_(old["step"])
+            self._flat_state[id(mod)] = st
+        return st
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        g = self.param_groups[0]
+        lr, (b1, b2), eps = g["lr"], g["betas"], g["eps"]
+        for mod in self._modules:
+            self.step_flat(mod, mod.packed_grads(), lr, b1, b2, eps)
+        return loss
+
+    def step_flat(self, mod, gflat, lr=None, b1=None, b2=None, eps=None):
+        """Adam on the model's flat parameter buffer given a flat gradient buffer (graph-capturable)."""
+        g = self.param_groups[0]
+        lr = g["lr"] if lr is None else lr
+        b1 = g["betas"][0] if b1 is None else b1
+        b2 = g["betas"][1] if b2 is None else b2
+        eps = g["eps"] if eps is None else eps
+        st = self._state_for(mod)
+        flat = mod._flat
+        rc = _lib.fn("fhvae_adam_flat")(ptr(flat), ptr(gflat), ptr(st["m"]), ptr(st["v"]), flat.numel(),
+                                        lr, b1, b2, eps, self.grad_scale, ptr(st["step"]), ptr(st["done"]),
+                                        current_stream_ptr())
+        _lib.check(rc, "fhvae_adam_flat")
+
+    def steps_taken(self, mod=None) -> int:
+        mod = mod or self._modules[0]
+        return int(self._state_for(mod)["step"].item())

@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library builds, loads and exports every symbol include/fhvae_b200.h declares;
+host-side module logic that needs no GPU."""
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+import pytorch_scalablefhvae_b200 as P
+from pytorch_scalablefhvae_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    P.build()
+    return _lib.load()
+
+
+def test_header_and_binding_declare_same_symbols(lib):
+    hdr = open(os.path.join(ROOT, "include", "fhvae_b200.h")).read()
+    declared = set(re.findall(r"\b(fhvae_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+
+
+def test_library_exports_every_symbol(lib):
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = set(re.findall(r"\bT (fhvae_[a-z0-9_]+)", out))
+    assert set(_lib.EXPORTS) <= exported, set(_lib.EXPORTS) - exported
+    for name in _lib.EXPORTS:
+        assert getattr(lib, name) is not None
+
+
+def test_built_for_sm100a(lib):
+    assert lib.fhvae_built_for_sm() == 100
+    sass = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in sass
+
+
+def test_argument_errors_are_reported_not_thrown(lib):
+    rc = lib.fhvae_gemm_batch(None, 0, 0, None)
+    assert rc == -1 and b"gemm_batch" in lib.fhvae_last_error_string()
+    with pytest.raises(_lib.FhvaeError):
+        _lib.check(rc, "fhvae_gemm_batch")
+
+
+def test_module_surface_matches_reference():
+    torch.manual_seed(0)
+    m = P.SimpleFHVAE(1600)
+    assert m.model == "simple_fhvae" and m.z1_hus == [128, 128] and m.z1_dim == 16
+    keys = set(m.state_dict())
+    for k in ["z1_pre_encoder.fc1.linear.weight", "z2_pre_encoder.fc2.linear.bias", "pre_decoder.fc1.linear.weight",
+              "dec_gauss_layer.logvar_layer.weight", "z1_gauss_layer.mulayer.bias"]:
+        assert k in keys
+    assert m.state_dict()["z1_pre_encoder.fc1.linear.weight"].shape == (128, 1616)
+    assert m.state_dict()["dec_gauss_layer.mulayer.weight"].shape == (1600, 128)
+    assert sum(p.numel() for n, p in m.named_parameters() if n != "mu2_table") == 886720
+    f = P.FHVAE(1600, ["256", "256"], [256, 256], 32, 32, [256, 256])      # string hus (train_model.py:145)
+    assert f.model == "fhvae" and f.z2_hus == [256, 256]
+    assert sum(p.numel() for n, p in f.named_parameters() if n != "mu2_table") == 2740512
+    assert f.state_dict()["z1_pre_encoder.lstm.weight_ih_l0"].shape == (1024, 112)
+
+
+def test_same_seed_same_init_as_oracle():
+    from oracle import fhvae_oracle as O
+    torch.manual_seed(3)
+    a = P.FHVAE(4 * 8, [16, 16], [16, 16], 8, 8, [16, 16], seg_len=4, num_seqs=5)
+    torch.manual_seed(3)
+    b = O.FHVAEOracle(4 * 8, [16, 16], [16, 16], 8, 8, [16, 16], seg_len=4, num_seqs=5)
+    sa, sb = a.state_dict(), b.state_dict()
+    assert set(sa) == set(sb)
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    b.load_state_dict(a.state_dict(), strict=True)
+
+
+def test_no_cpu_fallback():
+    m = P.SimpleFHVAE(24, [8, 8], [8, 8], 8, 8, [8, 8], num_seqs=4)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        m(torch.randn(2, 4, 6), torch.tensor([0, 1]), 4, torch.tensor([1, 1]))
+    with pytest.raises(RuntimeError, match="double"):
+        m.double()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "pytorch_scalablefhvae_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "import oracle" not in src and "from oracle" not in src

@@ -1,0 +1,308 @@
+"""GPU: each C-ABI kernel against a torch fp64/fp32 statement of the same op (sizes the CPU does in
+seconds) + exact-index / edge cases (duplicates, first/last row, ragged sizes)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fhvae_oracle as O
+from pytorch_scalablefhvae_b200 import _lib
+from pytorch_scalablefhvae_b200._lib import ColsumProblem, GemmProblem
+from pytorch_scalablefhvae_b200.plan import ptr
+from util import FP32_RTOL, assert_close, call, gemm, relerr
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def rnd(*s, seed=0, scale=1.0):
+    g = torch.Generator().manual_seed(seed)
+    return (torch.randn(*s, generator=g) * scale).to(DEV)
+
+
+# ------------------------------------------------------------------------------- GEMM
+@pytest.mark.parametrize("M,N,K", [(64, 64, 16), (5120, 1024, 80), (37, 129, 53), (256, 64, 512), (1, 7, 3)])
+def test_gemm_nt_bias_relu(M, N, K):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2), rnd(N, seed=3)
+    Cc = torch.zeros(M, N, device=DEV)
+    gemm(A, W, Cc, M, N, K, (K, 1), (1, K), N, bias=b, relu=1)
+    ref = torch.relu(A.double() @ W.double().t() + b.double())
+    assert_close(Cc, ref, 1e-5, "gemm_nt")
+
+
+def test_gemm_nn_tn_beta_strided():
+    M, N, K = 200, 96, 300
+    G, W = rnd(M, K, seed=4), rnd(K, N + 8, seed=5)              # W has ld N+8, use cols [4, 4+N)
+    C0 = rnd(M, N, seed=6)
+    Cc = C0.clone()
+    p = GemmProblem(ptr(G), ptr(W, 4), ptr(Cc), None, M, N, K, 0, K, 1, N + 8, 1, N, 1.0, 0)
+    call("fhvae_gemm_batch", (GemmProblem * 1)(p), 1, 0)
+    assert_close(Cc, C0.double() + G.double() @ W[:, 4:4 + N].double(), 1e-5, "gemm_nn beta")
+    # wgrad: dW[N,K2] = dY[R,N]^T X[R,K2]
+    R, Nn, K2 = 777, 40, 24
+    dY, X = rnd(R, Nn, seed=7), rnd(R, K2, seed=8)
+    dW = torch.zeros(Nn, K2, device=DEV)
+    gemm(dY, X, dW, Nn, K2, R, (1, Nn), (K2, 1), K2)
+    assert_close(dW, dY.double().t() @ X.double(), 1e-5, "gemm_tn")
+
+
+def test_gemm_grouped_launch():
+    shapes = [(100, 64, 32), (5, 200, 77), (300, 16, 16)]
+    probs, outs, refs = [], [], []
+    for i, (M, N, K) in enumerate(shapes):
+        A, W = rnd(M, K, seed=10 + i), rnd(N, K, seed=20 + i)
+        Cc = torch.zeros(M, N, device=DEV)
+        probs.append(GemmProblem(ptr(A), ptr(W), ptr(Cc), None, M, N, K, 0, K, 1, 1, K, N, 0.0, 0))
+        outs.append(Cc); refs.append(A.double() @ W.double().t()); outs.append(A); outs.append(W)
+    call("fhvae_gemm_batch", (GemmProblem * 3)(*probs), 3, 0)
+    for i in range(3):
+        assert_close(outs[3 * i], refs[i], 1e-5, f"group {i}")
+
+
+# ------------------------------------------------------------------------------- LSTM
+def _lstm_ref(P, Q, W, R_all, R_last):
+    """fp64 autograd statement of the recurrence used for both fwd and bwd checks."""
+    T, B, H4 = P.shape
+    H = H4 // 4
+    h = torch.zeros(B, H, dtype=torch.float64)
+    c = torch.zeros(B, H, dtype=torch.float64)
+    hs, cs = [], []
+    for t in range(T):
+        g = P[t] + Q + h @ W.t()
+        i, f, gg, o = torch.sigmoid(g[:, :H]), torch.sigmoid(g[:, H:2 * H]), torch.tanh(g[:, 2 * H:3 * H]), torch.sigmoid(g[:, 3 * H:])
+        c = f * c + i * gg
+        h = o * torch.tanh(c)
+        hs.append(h); cs.append(c)
+    hs, cs = torch.stack(hs), torch.stack(cs)
+    loss = (hs * R_all).sum() + (hs[-1] * R_last).sum()
+    return hs, cs, loss
+
+
+@pytest.mark.parametrize("T,B,H", [(5, 19, 16), (20, 64, 64), (20, 256, 256)])
+def test_lstm_fwd_bwd_vs_fp64(T, B, H):
+    g = torch.Generator().manual_seed(T * 1000 + B)
+    P = (torch.randn(T, B, 4 * H, generator=g) * 0.7).double().requires_grad_(True)
+    Q = (torch.randn(B, 4 * H, generator=g) * 0.3).double().requires_grad_(True)
+    W = (torch.randn(4 * H, H, generator=g) / math.sqrt(H)).double().requires_grad_(True)
+    R_all = torch.randn(T, B, H, generator=g).double()
+    R_last = torch.randn(B, H, generator=g).double()
+    hs, cs, loss = _lstm_ref(P, Q, W, R_all, R_last)
+    loss.backward()
+    d = lambda t: t.detach().float().to(DEV).contiguous()
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    h_all, c_all, acts = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
+    Pd, Qd, Wd = d(P), d(Q), d(W)
+    call("fhvae_lstm_fwd", ptr(Pd), ptr(Qd), ptr(Wd), ptr(h_all), ptr(c_all), ptr(acts), T, B, H, 0)
+    assert_close(h_all, hs, 2e-5, "h_all")
+    assert_close(c_all, cs, 2e-5, "c_all")
+    dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(2, B, H), f(B, H)
+    call("fhvae_lstm_bwd", ptr(d(R_all)), ptr(d(R_last)), ptr(Wd), ptr(c_all), ptr(acts), ptr(dg), ptr(dgsum),
+         ptr(dh_rec), ptr(dc), T, B, H, 0)
+    assert_close(dg, P.grad, 5e-5, "dgates")
+    assert_close(dgsum, Q.grad, 5e-5, "dgsum")
+    # dW_hh = dg[1:]^T h[:-1] through the library GEMM
+    dW = f(4 * H, H)
+    gemm(dg[1:], h_all, dW, 4 * H, H, (T - 1) * B, (1, 4 * H), (H, 1), H)
+    assert_close(dW, W.grad, 5e-5, "dW_hh")
+
+
+def test_lstm_null_inputs():
+    T, B, H = 3, 8, 16
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    Q, W = rnd(B, 4 * H, seed=1), rnd(4 * H, H, seed=2, scale=0.2)
+    h1, c1, a1 = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
+    call("fhvae_lstm_fwd", None, ptr(Q), ptr(W), ptr(h1), ptr(c1), ptr(a1), T, B, H, 0)
+    P = Q.unsqueeze(0).expand(T, B, 4 * H).contiguous()
+    h2, c2, a2 = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
+    call("fhvae_lstm_fwd", ptr(P), None, ptr(W), ptr(h2), ptr(c2), ptr(a2), T, B, H, 0)
+    assert torch.equal(h1, h2) and torch.equal(c1, c2)
+    assert _lib.fn("fhvae_lstm_fwd")(None, None, ptr(W), ptr(h1), ptr(c1), ptr(a1), T, B, H, 0, None) == -1
+
+
+# ------------------------------------------------------------------------------- reparam / ELBO
+@pytest.mark.parametrize("B,T,F,Z", [(7, 4, 6, 16), (256, 20, 80, 32), (64, 20, 80, 16)])
+@pytest.mark.parametrize("layout", ["time_major", "simple"])
+def test_elbo_fwd_bwd(B, T, F, Z, layout):
+    g = torch.Generator().manual_seed(B + T)
+    x = torch.randn(B, T, F, generator=g)
+    xm = (torch.randn(B, T, F, generator=g) * 0.5).requires_grad_(True)
+    xl = (torch.randn(B, T, F, generator=g) * 0.3).requires_grad_(True)
+    z1h = (torch.randn(B, 2 * Z, generator=g) * 0.5).requires_grad_(True)
+    z2h = (torch.randn(B, 2 * Z, generator=g) * 0.5).requires_grad_(True)
+    mu2 = torch.randn(B, Z, generator=g).requires_grad_(True)
+    nsegs = torch.randint(1, 200, (B,), generator=g)
+    lb, lpx, nk1, nk2, lpm = O.elbo_terms(x, xm, xl, z1h[:, :Z], z1h[:, Z:], z2h[:, :Z], z2h[:, Z:], mu2, nsegs)
+    w = torch.randn(5, B, generator=g)
+    (w[0] * lb + w[1] * lpx + w[2] * nk1 + w[3] * nk2 + w[4] * lpm).sum().backward()
+    if layout == "time_major":      # (T,B,2F): [mu | logvar]
+        xhead = torch.cat([xm, xl], -1).permute(1, 0, 2).contiguous().detach().to(DEV)
+        xs_b, xs_t, lv_off = 2 * F, B * 2 * F, F
+        unpack = lambda d: (d.permute(1, 0, 2)[..., :F], d.permute(1, 0, 2)[..., F:])
+    else:                           # (B, 2TF): [mu(TF) | logvar(TF)]
+        xhead = torch.cat([xm.reshape(B, -1), xl.reshape(B, -1)], -1).contiguous().detach().to(DEV)
+        xs_b, xs_t, lv_off = 2 * T * F, F, T * F
+        unpack = lambda d: (d[:, :T * F].view(B, T, F), d[:, T * F:].view(B, T, F))
+    d = lambda t: t.detach().to(DEV).contiguous()
+    out5 = torch.zeros(5, B, device=DEV)
+    flag = torch.zeros(1, dtype=torch.int32, device=DEV)
+    call("fhvae_elbo_fwd", ptr(d(x)), ptr(xhead), xs_b, xs_t, lv_off, ptr(d(z1h)), ptr(d(z2h)), ptr(d(mu2)),
+         ptr(d(nsegs)), ptr(out5), ptr(flag), B, T, F, Z, Z)
+    for i, r in enumerate([lb, lpx, nk1, nk2, lpm]):
+        assert_close(out5[i], r, 1e-5, f"elbo out {i}")
+    assert int(flag) == 0
+    # coef as the host folds it: c_px = w_lb + w_px ... c_pm = w_lb/nsegs + w_pm
+    coef = torch.stack([w[0] + w[1], w[0] + w[2], w[0] + w[3], w[0] / nsegs + w[4]]).to(DEV).contiguous()
+    dxh = torch.zeros_like(xhead)
+    dz1, dz2, dmu2 = torch.zeros(B, 2 * Z, device=DEV), torch.zeros(B, 2 * Z, device=DEV), torch.zeros(B, Z, device=DEV)
+    call("fhvae_elbo_bwd", ptr(d(x)), ptr(xhead), xs_b, xs_t, lv_off, ptr(d(z1h)), ptr(d(z2h)), ptr(d(mu2)),
+         ptr(coef), ptr(dxh), ptr(dz1), ptr(dz2), ptr(dmu2), B, T, F, Z, Z)
+    dm, dl = unpack(dxh)
+    assert_close(dm, xm.grad, 1e-5, "d x_mu"); assert_close(dl, xl.grad, 1e-5, "d x_logvar")
+    assert_close(dz1, z1h.grad, 1e-5, "d z1head"); assert_close(dz2, z2h.grad, 1e-5, "d z2head")
+    assert_close(dmu2, mu2.grad, 1e-5, "d mu2")
+
+
+def test_elbo_nan_flag():
+    B, T, F, Z = 4, 2, 4, 8
+    z = lambda *s: torch.zeros(*s, device=DEV)
+    x = z(B, T, F); x[2, 0, 0] = float("nan")
+    out5, flag = z(5, B), torch.zeros(1, dtype=torch.int32, device=DEV)
+    call("fhvae_elbo_fwd", ptr(x), ptr(z(T, B, 2 * F)), 2 * F, B * 2 * F, F, ptr(z(B, 2 * Z)), ptr(z(B, 2 * Z)),
+         ptr(z(B, Z)), ptr(torch.ones(B, dtype=torch.int64, device=DEV)), ptr(out5), ptr(flag), B, T, F, Z, Z)
+    assert int(flag) == 1 and torch.isnan(out5[0, 2]) and not torch.isnan(out5[0, 0])
+
+
+def test_reparam_fwd_bwd():
+    B, Z = 33, 16
+    head, eps, ds = rnd(B, 2 * Z, seed=1), rnd(B, Z, seed=2), rnd(B, Z + 5, seed=3)
+    s = torch.zeros(B, Z + 3, device=DEV)
+    call("fhvae_reparam_fwd", ptr(head), 2 * Z, ptr(eps), ptr(s, 3), Z + 3, B, Z)
+    ref = head[:, :Z] + eps * torch.exp(0.5 * head[:, Z:])
+    assert_close(s[:, 3:], ref, 1e-6, "reparam")
+    dh = torch.ones(B, 2 * Z, device=DEV)
+    call("fhvae_reparam_bwd", ptr(head), 2 * Z, ptr(eps), ptr(ds, 5), Z + 5, ptr(dh), 2 * Z, 1, B, Z)
+    g = ds[:, 5:]
+    assert_close(dh[:, :Z], 1 + g, 1e-6, "dmu"); assert_close(dh[:, Z:], 1 + g * 0.5 * eps * torch.exp(0.5 * head[:, Z:]), 1e-6, "dlv")
+
+
+# ------------------------------------------------------------------------------- discriminative term
+@pytest.mark.parametrize("B,N,Z", [(5, 12, 16), (64, 1000, 16), (256, 5000, 32), (33, 129, 8)])
+def test_disc_fwd_bwd(B, N, Z):
+    g = torch.Generator().manual_seed(N)
+    table = torch.randn(N, Z, generator=g).double().requires_grad_(True)
+    idx = torch.randint(0, N, (B,), generator=g)
+    idx[0], idx[-1] = 0, N - 1
+    if B > 3:
+        idx[2] = idx[1]                                  # duplicate utterance in the batch
+    z2h = torch.randn(B, 2 * Z, generator=g).double()
+    z2h[:, :Z] = table.detach()[idx] + 0.5 * z2h[:, :Z]  # posterior means near their rows, as in training
+    z2h.requires_grad_(True)
+    lq = O.log_qy_per_segment(z2h[:, :Z], table, idx)
+    w = torch.randn(B, generator=g).double()
+    (w * lq).sum().backward()
+    d = lambda t: t.detach().float().to(DEV).contiguous()
+    zd, td, idd = d(z2h), d(table), idx.to(DEV)
+    ns = _lib.fn("fhvae_disc_nsplit")(B, N)
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    part, tgt, lqd, lse, mu2 = f(ns, B, 2), f(B), f(B), f(B), f(B, Z)
+    call("fhvae_mu2_gather", ptr(td), ptr(idd), ptr(mu2), B, Z, N)
+    assert torch.equal(mu2, td[idd])
+    call("fhvae_disc_fwd_partial", ptr(zd), 2 * Z, ptr(td), N, Z, ptr(part), ns, B)
+    call("fhvae_disc_target", ptr(zd), 2 * Z, ptr(mu2), ptr(tgt), B, Z)
+    call("fhvae_disc_combine", ptr(part), ns, ptr(tgt), ptr(lqd), ptr(lse), B)
+    assert_close(lqd, lq, 2e-5, "log_qy")
+    gq = d(w)
+    dtab, sumpm, dz, dmu2 = f(N, Z), f(ns, B, Z), f(B, 2 * Z), f(B, Z)
+    call("fhvae_disc_bwd_segs", ptr(zd), 2 * Z, ptr(td), N, Z, ptr(lse), ptr(sumpm), ns, B)
+    call("fhvae_disc_bwd_rows", ptr(zd), 2 * Z, ptr(td), N, Z, ptr(lse), ptr(gq), ptr(dtab), B)
+    call("fhvae_disc_bwd_finish", ptr(zd), 2 * Z, ptr(mu2), ptr(sumpm), ns, ptr(gq), ptr(dz), 2 * Z, ptr(dmu2), B, Z)
+    touched = torch.zeros(B, dtype=torch.int32, device=DEV)
+    call("fhvae_mu2_scatter_reduce", ptr(dmu2), ptr(idd), ptr(dtab), ptr(touched), B, Z, N)
+    assert_close(dz[:, :Z], z2h.grad[:, :Z], 5e-5, "d z2_mu")
+    assert float(dz[:, Z:].abs().max()) == 0.0
+    assert_close(dtab, table.grad, 5e-5, "d table")
+    # rows touched by the sparse part: exactly the distinct utterances, flagged at first occurrence
+    first = torch.zeros(B, dtype=torch.int32)
+    seen = set()
+    for b, r in enumerate(idx.tolist()):
+        if r not in seen:
+            first[b] = 1; seen.add(r)
+    assert torch.equal(touched.cpu(), first)
+
+
+def test_scatter_reduce_exact_and_deterministic():
+    B, Z, N = 512, 32, 40                                  # heavy duplication
+    g = torch.Generator().manual_seed(0)
+    idx = torch.randint(0, N, (B,), generator=g)
+    src = torch.randint(-8, 9, (B, Z), generator=g).float()   # small integers: float sums are exact
+    ref = torch.zeros(N, Z).index_add_(0, idx, src)
+    outs = []
+    for _ in range(2):
+        dst = torch.zeros(N, Z, device=DEV)
+        call("fhvae_mu2_scatter_reduce", ptr(src.to(DEV)), ptr(idx.to(DEV)), ptr(dst), None, B, Z, N)
+        outs.append(dst.cpu())
+    assert torch.equal(outs[0], ref) and torch.equal(outs[0], outs[1])
+
+
+def test_mu2_estimate_matches_reference_dict_loop():
+    B, Z, K = 300, 32, 17
+    g = torch.Generator().manual_seed(5)
+    z2h = torch.randn(B, 2 * Z, generator=g)
+    idx = torch.randint(0, K - 2, (B,), generator=g)       # rows K-2, K-1 never seen: stay untouched
+    d = O.estimate_mu2_dict([z2h[:100, :Z], z2h[100:, :Z]], [idx[:100], idx[100:]])
+    zsum, cnt = torch.zeros(K, Z, device=DEV), torch.zeros(K, device=DEV)
+    table = torch.full((K, Z), 7.0, device=DEV)
+    zd, idd = z2h.to(DEV), idx.to(DEV)
+    call("fhvae_mu2_accumulate", ptr(zd), 2 * Z, ptr(idd), ptr(zsum), ptr(cnt), 100, Z, K)
+    call("fhvae_mu2_accumulate", ptr(zd, 100 * 2 * Z), 2 * Z, ptr(idd, 100), ptr(zsum), ptr(cnt), B - 100, Z, K)
+    call("fhvae_mu2_estimate_finish", ptr(zsum), ptr(cnt), ptr(table), 0.25, K, Z)
+    for y, v in d.items():
+        assert_close(table[y], v, 1e-5, f"mu2[{y}]")
+    assert torch.equal(cnt.cpu().long(), torch.bincount(idx, minlength=K))
+    assert float((table[K - 2:] - 7.0).abs().max()) == 0.0
+
+
+def test_rows_copy_exact():
+    src = rnd(50, 16, seed=1)
+    dst = torch.zeros(20, 16, device=DEV)
+    s_rows = torch.tensor([49, 0, 7, 7], device=DEV)
+    d_rows = torch.tensor([0, 19, -1, 3], device=DEV)
+    call("fhvae_rows_copy", ptr(src), ptr(s_rows), ptr(dst), ptr(d_rows), 4, 16)
+    assert torch.equal(dst[0], src[49]) and torch.equal(dst[19], src[0]) and torch.equal(dst[3], src[7])
+    assert float(dst[1:3].abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------------------- Adam / helpers
+def test_adam_flat_matches_torch_adam():
+    n = 100003
+    p0, gs = rnd(n, seed=1), [rnd(n, seed=10 + i) for i in range(4)]
+    ref = torch.nn.Parameter(p0.clone().cpu())
+    opt = torch.optim.Adam([ref], lr=1e-3, betas=(0.95, 0.999))
+    p, m, v = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step = torch.zeros(1, dtype=torch.int32, device=DEV)
+    done = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for g in gs:
+        ref.grad = g.cpu().clone(); opt.step()
+        call("fhvae_adam_flat", ptr(p), ptr(g), ptr(m), ptr(v), n, 1e-3, 0.95, 0.999, 1e-8, 1.0, ptr(step), ptr(done))
+    assert int(step) == 4 and int(done) == 0
+    assert_close(p, ref.data, 1e-6, "adam params")
+    assert_close(m, opt.state[ref]["exp_avg"], 1e-6, "adam m")
+
+
+def test_transpose_colsum_add2_relu():
+    B, T, F = 9, 5, 12
+    x = rnd(B, T, F, seed=1)
+    y = torch.zeros(T, B, F, device=DEV)
+    call("fhvae_transpose_bt", ptr(x), ptr(y), B, T, F)
+    assert torch.equal(y, x.permute(1, 0, 2).contiguous())
+    a = rnd(777, 70, seed=2)
+    o1, o2 = torch.zeros(70, device=DEV), torch.zeros(70, device=DEV)
+    call("fhvae_colsum_batch", (ColsumProblem * 1)(ColsumProblem(ptr(a), ptr(o1), ptr(o2), 70, 777, 70)), 1)
+    assert_close(o1, a.double().sum(0), 1e-5, "colsum"); assert torch.equal(o1, o2)
+    s = torch.zeros(777 * 70, device=DEV)
+    call("fhvae_add2", ptr(s), ptr(a), ptr(a), 777 * 70)
+    assert torch.equal(s.view(777, 70), a + a)
+    d = torch.ones_like(a)
+    call("fhvae_relu_bwd", ptr(d), ptr(a), a.numel())
+    assert torch.equal(d, (a > 0).float())

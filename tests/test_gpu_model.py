@@ -1,0 +1,199 @@
+"""GPU: module-level parity of the CUDA path (through the nn.Module surface, i.e. through the C ABI)
+against (i) the golden vectors produced by the UNMODIFIED reference, (ii) the CPU oracle on the same
+seeded inputs -- forward values, gradients, Adam-updated parameters."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_scalablefhvae_b200 as P
+from oracle import fhvae_oracle as O
+from util import FP32_RTOL, assert_close, relerr, synth_batch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+NAMES = ["lower_bound", "log_qy", "log_px_z", "neg_kld_z1", "neg_kld_z2", "log_pmu2"]
+
+
+def _golden(golden_dir):
+    d = np.load(os.path.join(golden_dir, "simple_fhvae_tiny.npz"))
+    return {k: (torch.from_numpy(d[k]) if k != "meta" else d[k]) for k in d.files}
+
+
+def test_simple_tiny_matches_unmodified_reference(golden_dir):
+    """Forward values + as-is gradients of the reference itself (tests/golden, oracle/make_golden.py)."""
+    g = _golden(golden_dir)
+    T, F, B, N, Z, H = [int(v) for v in g["meta"]]
+    m = P.SimpleFHVAE(T * F, [H, H], [H, H], Z, Z, [H, H], num_seqs=N, detach_px=True, prior_grad=False,
+                      ref_log_qy=True)
+    sd = {k[2:]: v for k, v in g.items() if k.startswith("w:")}
+    sd["mu2_table"] = g["table"]
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV)
+    out = m(g["x"].to(DEV), g["idx"], N, g["nsegs"], eps={"z1": g["eps_z1"], "z2": g["eps_z2"]})
+    for n, o in zip(NAMES, out):
+        assert_close(o, g["out_" + n], FP32_RTOL, n)
+    loss = P.loss_function(out[0], out[1], 10.0)
+    assert_close(loss, g["loss"], FP32_RTOL, "loss")
+    loss.backward()
+    n_checked = 0
+    for k, p in m.named_parameters():
+        if k == "mu2_table":
+            assert_close(p.grad, g["grad_table"], FP32_RTOL, "grad table")
+        elif "g:" + k in g:
+            assert_close(p.grad, g["g:" + k], FP32_RTOL, "grad " + k)
+            n_checked += 1
+        else:
+            assert float(p.grad.abs().max()) == 0.0, k      # decoder: no gradient in the reference (F6)
+    assert n_checked == 16
+    # attribute surface read by utils.estimate_mu2_dict (utils.py:52,58)
+    assert m.qz2_x[0].shape == (B, Z) and float(m.pz2[1]) == pytest.approx(np.log(0.25))
+
+
+def _pair(kind, cfg, seed=0, **kw):
+    torch.manual_seed(seed)
+    if kind == "simple":
+        m = P.SimpleFHVAE(*cfg["args"], num_seqs=cfg["N"], **kw)
+        torch.manual_seed(seed)
+        o = O.SimpleFHVAEOracle(*cfg["args"], num_seqs=cfg["N"])
+    else:
+        m = P.FHVAE(*cfg["args"], seg_len=cfg["T"], num_seqs=cfg["N"], **kw)
+        torch.manual_seed(seed)
+        o = O.FHVAEOracle(*cfg["args"], seg_len=cfg["T"], num_seqs=cfg["N"])
+    o.load_state_dict(m.state_dict(), strict=True)
+    return m.to(DEV), o
+
+
+CFGS = {
+    "simple_c0": dict(kind="simple", B=64, T=20, F=80, N=1000, args=(1600, [128, 128], [128, 128], 16, 16, [128, 128])),
+    "simple_ragged": dict(kind="simple", B=7, T=3, F=8, N=9, args=(24, [24, 16], [8, 40], 8, 16, [16, 24])),
+    "fhvae_small": dict(kind="fhvae", B=10, T=6, F=8, N=13, args=(48, [32, 32], [32, 32], 8, 16, [32, 32])),
+    "fhvae_1layer_3layer": dict(kind="fhvae", B=5, T=4, F=12, N=6, args=(48, [16], [24, 24, 24], 16, 8, [40, 40])),
+    "fhvae_c1": dict(kind="fhvae", B=256, T=20, F=80, N=1000, args=(1600, [256, 256], [256, 256], 32, 32, [256, 256])),
+}
+
+
+def _eps(B, Z1, Z2, seed=2):
+    g = torch.Generator().manual_seed(seed)
+    return {"z2": torch.randn(B, Z2, generator=g), "z1": torch.randn(B, Z1, generator=g)}
+
+
+@pytest.mark.parametrize("name", list(CFGS))
+def test_forward_backward_matches_oracle(name):
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg)
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    eps = _eps(B, m.z1_dim, m.z2_dim)
+    out = m(x.to(DEV), idx, N, nsegs, eps=eps)
+    ref = o(x, idx, N, nsegs, eps=eps)
+    for n, a, b in zip(NAMES, out, ref):
+        assert_close(a, b, FP32_RTOL, f"{name}:{n}")
+    P.loss_function(out[0], out[1], 10.0).backward()
+    O.loss_function(ref[0], ref[1], 10.0).backward()
+    po = dict(o.named_parameters())
+    worst = 0.0
+    for k, p in m.named_parameters():
+        assert p.grad is not None, k
+        e = relerr(p.grad, po[k].grad)
+        worst = max(worst, e)
+        assert e <= FP32_RTOL, f"{name}: grad {k}: {e:.3e}"
+    print(f"{name}: worst gradient max-norm relative error {worst:.2e}")
+    # posteriors / px exposed as attributes
+    assert_close(m.qz2_x[0], o.qz2_x[0], FP32_RTOL, "qz2 mu"); assert_close(m.qz1_x[1], o.qz1_x[1], FP32_RTOL, "qz1 lv")
+    assert_close(m.px_z[0], o.px_z[0], FP32_RTOL, "px mu"); assert_close(m.z2_sample, o.z2_sample, FP32_RTOL, "z2 sample")
+
+
+@pytest.mark.parametrize("name", ["simple_ragged", "fhvae_small"])
+def test_flags_reproduce_reference_gradient_flow(name):
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg, detach_px=True, prior_grad=False)
+    o.detach_px, o.prior_grad = True, False
+    x, idx, nsegs = synth_batch(cfg["B"], cfg["T"], cfg["F"], cfg["N"])
+    eps = _eps(cfg["B"], m.z1_dim, m.z2_dim)
+    out = m(x.to(DEV), idx, cfg["N"], nsegs, eps=eps)
+    ref = o(x, idx, cfg["N"], nsegs, eps=eps)
+    P.loss_function(out[0], out[1]).backward(); O.loss_function(ref[0], ref[1]).backward()
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        if po[k].grad is None:
+            assert float(p.grad.abs().max()) == 0.0, k
+        else:
+            assert_close(p.grad, po[k].grad, FP32_RTOL, k)
+
+
+@pytest.mark.parametrize("name", ["simple_c0", "fhvae_small"])
+@pytest.mark.parametrize("graphs", [False, True])
+def test_train_steps_match_oracle_adam(name, graphs):
+    """Loop body of train_model.py:446-454, three steps; parameters after Adam must agree."""
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg, use_cuda_graphs=graphs)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    oopt = O.make_adam(o.parameters())
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    for step in range(3):
+        x, idx, nsegs = synth_batch(B, T, F, N, seed=100 + step)
+        eps = _eps(B, m.z1_dim, m.z2_dim, seed=step)
+        opt.zero_grad()
+        out = m(x.to(DEV), idx, N, nsegs, eps=eps)
+        loss = P.loss_function(out[0], out[1], 10.0)
+        loss.backward()
+        opt.step()
+        assert not torch.isnan(out[0]).any()                    # train_model.py:464
+        rl, _ = O.train_step(o, oopt, x, idx, N, nsegs, 10.0, eps=eps)
+        assert_close(loss, rl, FP32_RTOL, f"loss step {step}")
+    assert opt.steps_taken() == 3
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert_close(p, po[k], FP32_RTOL, f"param {k} after 3 Adam steps")
+
+
+def test_grad_accumulation_without_zero_grad():
+    cfg = CFGS["fhvae_small"]
+    m, o = _pair("fhvae", cfg)
+    x, idx, nsegs = synth_batch(cfg["B"], cfg["T"], cfg["F"], cfg["N"])
+    eps = _eps(cfg["B"], m.z1_dim, m.z2_dim)
+    for _ in range(2):
+        out = m(x.to(DEV), idx, cfg["N"], nsegs, eps=eps)
+        P.loss_function(out[0], out[1]).backward()
+        ref = o(x, idx, cfg["N"], nsegs, eps=eps)
+        O.loss_function(ref[0], ref[1]).backward()
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert_close(p.grad, po[k].grad, FP32_RTOL, k)
+
+
+def test_no_grad_forward_and_errors():
+    cfg = CFGS["fhvae_small"]
+    m, o = _pair("fhvae", cfg)
+    x, idx, nsegs = synth_batch(cfg["B"], cfg["T"], cfg["F"], cfg["N"])
+    with torch.no_grad():
+        out = m(x.to(DEV), idx, cfg["N"], nsegs, eps=_eps(cfg["B"], m.z1_dim, m.z2_dim))
+    assert not out[0].requires_grad
+    with pytest.raises(IndexError):
+        m(x.to(DEV), idx + cfg["N"], cfg["N"], nsegs)
+    with pytest.raises(ValueError):
+        m(x.to(DEV), idx, cfg["N"] + 1, nsegs)
+    # int num_segs (the signature's annotation) and device-resident idx are accepted
+    out2 = m(x.to(DEV), idx.to(DEV), cfg["N"], 3, eps=_eps(cfg["B"], m.z1_dim, m.z2_dim))
+    assert out2[0].shape == (cfg["B"],)
+
+
+def test_fullsize_properties_c1():
+    """Size-independent properties at BASELINE config-1 size: (i) segments are independent given the
+    parameters: permuting the batch permutes the per-segment outputs; (ii) the lower bound is the sum
+    of its terms; (iii) d loss / d table sums KL+prior rows exactly on the utterances in the batch."""
+    cfg = CFGS["fhvae_c1"]
+    m, _ = _pair("fhvae", cfg)
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    eps = _eps(B, 32, 32)
+    with torch.no_grad():
+        a = m(x.to(DEV), idx, N, nsegs, eps=eps)
+        perm = torch.randperm(B, generator=torch.Generator().manual_seed(0))
+        b = m(x[perm].to(DEV), idx[perm], N, nsegs[perm], eps={k: v[perm] for k, v in eps.items()})
+    for n, u, v in zip(NAMES, a, b):
+        assert_close(v, u[perm.to(DEV)], 1e-6, "perm " + n)
+    lb, _, px, k1, k2, pm = a
+    assert_close(lb, px + k1 + k2 + pm / nsegs.to(DEV), 1e-6, "lb = sum of terms")
