@@ -40,6 +40,8 @@ const char* fhvae_last_error_string(void);
 int fhvae_version(void);
 /* compile-time facts the host may assert on */
 int fhvae_built_for_sm(void);              /* 100 */
+/* kernels launched by this process through this library so far (bench.py `gpu_launches`) */
+unsigned long long fhvae_launch_count(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K1/K3/K5/K8 dense contractions.  Replaces nn.Linear addmm (simple_fhvae.py:130-134,208-212),

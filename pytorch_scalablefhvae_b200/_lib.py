@@ -66,8 +66,9 @@ PROTOTYPES = {
     "fhvae_axpy": [_p, _p, _f, _l, _p],
     "fhvae_version": [],
     "fhvae_built_for_sm": [],
+    "fhvae_launch_count": [],
 }
-NO_STATUS = {"fhvae_disc_nsplit", "fhvae_version", "fhvae_built_for_sm"}
+NO_STATUS = {"fhvae_disc_nsplit", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
 EXPORTS = sorted(list(PROTOTYPES) + ["fhvae_last_error_string"])
 
 _lib = None
@@ -105,7 +106,7 @@ def load():
     for name, args in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.argtypes = args
-        fn.restype = C.c_int
+        fn.restype = C.c_ulonglong if name == "fhvae_launch_count" else C.c_int
     _lib = lib
     return lib
 

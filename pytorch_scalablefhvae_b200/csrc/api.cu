@@ -1,10 +1,13 @@
 // C-ABI plumbing: error string, version, and the mode dispatch of the GEMM / LSTM entry points.
 #include <stdarg.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace fhvae {
 
 static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -27,6 +30,7 @@ using namespace fhvae;
 
 extern "C" const char* fhvae_last_error_string(void) { return g_err; }
 extern "C" int fhvae_version(void) { return 1; }
+extern "C" unsigned long long fhvae_launch_count(void) { return g_launches.load(); }
 extern "C" int fhvae_built_for_sm(void) { return 100; }
 
 extern "C" int fhvae_gemm_batch(const fhvae_gemm_problem* problems, int n_problems, int mode,

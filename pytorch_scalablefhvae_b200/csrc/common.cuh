@@ -13,6 +13,7 @@
 namespace fhvae {
 
 void set_error(const char* fmt, ...);
+void count_launches(int n);   // process-wide kernel-launch counter (bench.py gpu_launches)
 
 #define FHVAE_CHECK_ARG(cond, ...)                     \
     do {                                               \
@@ -34,6 +35,7 @@ void set_error(const char* fmt, ...);
 #define FHVAE_LAUNCH_CHECK(name)                                                        \
     do {                                                                                \
         cudaError_t e__ = cudaGetLastError();                                           \
+        ::fhvae::count_launches(1);                                                     \
         if (e__ != cudaSuccess) {                                                       \
             ::fhvae::set_error("%s: launch failed: %s", name, cudaGetErrorString(e__)); \
             return (int)e__;                                                            \

@@ -136,6 +136,7 @@ int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_al
             t ? h_all + (t - 1) * bh : nullptr, t ? c_all + (t - 1) * bh : nullptr,
             h_all + t * bh, c_all + t * bh, acts + t * 4 * bh, B, H);
     }
+    count_launches(T - 1);
     FHVAE_LAUNCH_CHECK("lstm_fwd_simt");
     return 0;
 }
@@ -152,6 +153,7 @@ int lstm_bwd_simt(const float* dh_all, const float* dh_last, const float* W_hh, 
             c_all + t * bh, t ? c_all + (t - 1) * bh : nullptr, acts + t * 4 * bh,
             dgates + t * 4 * bh, dgsum, dc, t == T - 1, B, H);
     }
+    count_launches(T - 1);
     FHVAE_LAUNCH_CHECK("lstm_bwd_simt");
     return 0;
 }

@@ -191,6 +191,18 @@ class _FHVAECore(nn.Module):
             log_qy = -log_qy.mean()
         return lb, log_qy, log_px_z, nk1, nk2, log_pmu2
 
+    def train_step(self, x, mu_idx, num_segs, optimizer, alpha: float = 10.0, eps=None, allreduce=None):
+        """Fused loop body of train_model.py:446-454: forward, loss = -mean(lb + alpha*log_qy)
+        (train_model.py:243-251), backward, Adam -- one replayed launch sequence (one CUDA graph when
+        ``use_cuda_graphs`` and no collective is interposed).  ``allreduce(flat_grads)`` is called
+        between backward and Adam for data-parallel training.  Returns the loss (device scalar)."""
+        if not x.is_cuda and not x.is_pinned():
+            raise RuntimeError("train_step takes a CUDA or pinned-host batch (no CPU path)")
+        B, T, F = x.shape
+        plan = self._plan(B, T, F)
+        plan.load_inputs(x, mu_idx, num_segs, eps)
+        return plan.run_train_step(optimizer, float(alpha), allreduce)
+
     def _publish(self, plan: "_Plan"):
         """Attributes the reference's callers read (utils.py:52,58)."""
         z1h, z2h = plan.z1head, plan.z2head
@@ -297,7 +309,62 @@ class _Plan:
             self.bwd[k].run(current_stream_ptr())
         return gflat
 
-    def _capture(self, f):
+    def run_train_step(self, optimizer, alpha, allreduce):
+        m = self.m
+        k = 0
+        gflat = m._grad_buffer(k)
+        if self.bwd[k] is None:
+            self.bwd[k] = self._build_bwd(gflat)
+        if not hasattr(self, "loss"):
+            self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        B = self.B
+
+        def fwd_bwd():
+            self.fwd.run(current_stream_ptr())
+            self.gout.zero_()
+            self.gout[0].fill_(-1.0 / B)              # d loss / d lower_bound
+            self.gout[5].fill_(-alpha / B)            # d loss / d log_qy
+            self.bwd[k].run(current_stream_ptr())
+            torch.sum(self.out[0] + alpha * self.out[5], dim=0, out=self.loss)
+            self.loss.mul_(-1.0 / B)
+
+        def adam():
+            optimizer.step_flat(m, gflat)
+
+        if not m.use_cuda_graphs:
+            fwd_bwd()
+            if allreduce is not None:
+                allreduce(gflat)
+            adam()
+        else:
+            key = ("train", alpha, id(optimizer), allreduce is None)
+            graphs = self.__dict__.setdefault("_train_graphs", {})
+            if key not in graphs:
+                optimizer._state_for(m)               # allocate Adam state outside capture
+                if allreduce is None:
+                    graphs[key] = (self._capture(lambda: (fwd_bwd(), adam()), restore=optimizer), None)
+                else:
+                    graphs[key] = (self._capture(fwd_bwd), self._capture(adam, restore=optimizer))
+            g1, g2 = graphs[key]
+            g1.replay()
+            if g2 is not None:
+                allreduce(gflat)
+                g2.replay()
+        return self.loss
+
+    def _capture(self, f, restore=None):
+        # the warm-up run below really executes f once: snapshot what an optimizer step would change
+        snap = None
+        if restore is not None:
+            st = restore._state_for(self.m)
+            snap = (self.m._flat.clone(), st["m"].clone(), st["v"].clone(), st["step"].clone())
+        g = self._capture_inner(f)
+        if snap is not None:
+            st = restore._state_for(self.m)
+            self.m._flat.copy_(snap[0]); st["m"].copy_(snap[1]); st["v"].copy_(snap[2]); st["step"].copy_(snap[3])
+        return g
+
+    def _capture_inner(self, f):
         # warm up on a side stream (lazy module loading must not happen inside capture), then capture
         s = torch.cuda.Stream()
         s.wait_stream(torch.cuda.current_stream())
