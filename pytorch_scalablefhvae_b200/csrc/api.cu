@@ -24,6 +24,10 @@ int lstm_bwd_simt(const float* dh_all, const float* dh_last, const float* W_hh, 
                   const float* acts, float* dgates, float* dgsum, float* dc, int T, int B, int H,
                   cudaStream_t st);
 
+bool lstm_cluster_supported(int B, int H);
+int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
+                     float* acts, int T, int B, int H, int mode, cudaStream_t st);
+
 }  // namespace fhvae
 
 using namespace fhvae;
@@ -55,6 +59,8 @@ extern "C" int fhvae_lstm_fwd(const float* P, const float* Q, const float* W_hh,
                               float* c_all, float* acts, int T, int B, int H, int mode, void* stream) {
     FHVAE_CHECK_ARG(W_hh && h_all && c_all && acts && (P || Q), "lstm_fwd: null pointer");
     FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_fwd: need T,B>0 and H %% 8 == 0");
+    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H))
+        return lstm_fwd_cluster(P, Q, W_hh, h_all, c_all, acts, T, B, H, mode, as_stream(stream));
     return lstm_fwd_simt(P, Q, W_hh, h_all, c_all, acts, T, B, H, as_stream(stream));
 }
 

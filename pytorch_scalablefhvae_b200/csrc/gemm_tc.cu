@@ -1,8 +1,303 @@
-// placeholder until gemm_tc.cu (tcgen05) lands: tensor-core modes fall through to an error
+// Grouped GEMM on the 5th-gen tensor cores (tcgen05.mma kind::f16, accumulators in TMEM).
+//
+//   C[m,n] = sum_k A(m,k) B(k,n) (+bias, +beta*C, ReLU)      fp32 in HBM on both sides.
+//
+// Operands stay fp32 in HBM (they are master weights / saved activations that the fp32-parity
+// contract needs); each CTA converts its tiles to bf16 on the way into shared memory:
+//   FHVAE_MODE_BF16    one pass      hi(A) * hi(B)
+//   FHVAE_MODE_BF16X3  three passes  lo*hi + hi*lo + hi*hi with x = hi + lo (+2^-18 x), fp32 accumulate
+//                      => ~1e-5 relative, the "fp32" tolerance of the north star, at 1/3 of the bf16 rate.
+// Shared-memory tiles use the canonical K-major no-swizzle UMMA layout (8x16B core matrices): element
+// (r,k) of a 128 x 64 tile at byte (k/8)*2048 + r*16 + (k%8)*2, i.e. LBO = 2048, SBO = 128.
+// 128x128 output tile per CTA, K stepped in blocks of 64 through a 2-stage ring: all 256 threads stage
+// (global fp32 -> bf16 hi/lo -> st.shared, fence.proxy.async), one thread issues the MMAs, tcgen05.commit
+// on an mbarrier releases the stage.  Long-K problems (weight gradients: K = T*B) are split along K
+// across CTAs and reduced with fp32 atomics into a pre-zeroed C.
+// Epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/beta/ReLU -> global.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace fhvae {
-int gemm_batch_tc(const fhvae_gemm_problem*, int, int mode, cudaStream_t) {
-    set_error("gemm_batch: tensor-core mode %d not built", mode);
-    return FHVAE_ENOSUP;
+
+using namespace tc;
+
+constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int TCT = 256;                        // threads per CTA
+constexpr int TILE_BYTES = BM * BK * 2;         // one bf16 operand tile: 16 KB
+constexpr uint32_t LBO = BM * 16, SBO = 128;
+
+struct TcProblem {
+    const float* A;
+    const float* B;
+    float* C;
+    const float* bias;
+    int M, N, K;
+    int relu;
+    long long a_rs, a_ks;       // A(m,k) = A[m*a_rs + k*a_ks]
+    long long b_rs, b_ks;       // B(k,n) = B[n*b_rs + k*b_ks]   (row = n)
+    long long ldc;
+    float beta;
+    int a_vec, b_vec, c_vec;    // 16-byte vector access allowed
+    int ksplit, kb_per_split;   // K blocks (of BK) per split
+    int tile_start, tiles_n, tiles_mn;
+};
+struct TcBatch {
+    TcProblem p[FHVAE_GEMM_MAX_BATCH];
+    int n;
+};
+
+// stage one 128 x 64 operand tile: thread -> (row = item & 127, k-chunk = item >> 7), 4 items / thread
+template <bool X3>
+__device__ __forceinline__ void stage_tile(const float* __restrict__ src, long long rs, long long ks, int vec,
+                                           int row0, int rows, int k0, int kend, uint8_t* s_hi, uint8_t* s_lo) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int item = threadIdx.x + i * TCT;
+        const int r = item & (BM - 1), kc = item >> 7;
+        const int gr = row0 + r, gk = k0 + kc * 8;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        if (gr < rows && gk < kend) {
+            if (ks == 1) {
+                const float* p = src + (long long)gr * rs + gk;
+                if (vec && gk + 8 <= kend) {
+                    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+                    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        if (gk + j < kend) v[j] = __ldg(p + j);
+                }
+            } else {   // rows contiguous: coalesced across the warp for every k
+                const float* p = src + (long long)gk * ks + gr;
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                    if (gk + j < kend) v[j] = __ldg(p + (long long)j * ks);
+            }
+        }
+        const uint32_t off = (uint32_t)(kc * BM + r) * 16;
+        if (X3) {
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + off) = hi;
+            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        } else {
+            *reinterpret_cast<uint4*>(s_hi + off) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+    }
 }
+
+template <bool X3>
+__global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__ TcBatch tb) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int OPS = X3 ? 4 : 2;                        // tiles per stage: A_hi [A_lo] B_hi [B_lo]
+    constexpr int STAGE_BYTES = OPS * TILE_BYTES;
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);   // [2]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+
+    int pi = 0;
+    while (pi + 1 < tb.n && (int)blockIdx.x >= tb.p[pi + 1].tile_start) ++pi;
+    const TcProblem& P = tb.p[pi];
+    int t = blockIdx.x - P.tile_start;
+    const int split = t / P.tiles_mn;
+    t -= split * P.tiles_mn;
+    const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
+    const int nkb_total = (P.K + BK - 1) / BK;
+    const int kb0 = split * P.kb_per_split;
+    const int kb1 = min(nkb_total, kb0 + P.kb_per_split);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    if (warp == 0) tmem_alloc<BN>(tmem_slot);
+    if (tid == 32) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        fence_mbar_init();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+
+    for (int kb = kb0; kb < kb1; ++kb) {
+        const int it = kb - kb0, s = it & 1;
+        uint8_t* st = smem + s * STAGE_BYTES;
+        if (it >= 2) mbar_wait(&mbar[s], ((it >> 1) - 1) & 1);     // MMAs that read this stage are done
+        const int k0 = kb * BK;
+        stage_tile<X3>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0, P.K, st, st + TILE_BYTES);
+        stage_tile<X3>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0, P.K, st + (X3 ? 2 : 1) * TILE_BYTES,
+                       st + 3 * TILE_BYTES);
+        fence_proxy_async();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES;
+            const uint32_t b_hi = a_hi + (X3 ? 2 : 1) * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+            const int kleft = min(BK, P.K - k0);
+            const int n16 = (kleft + 15) >> 4;
+            for (int j = 0; j < n16; ++j) {
+                const uint32_t ko = (uint32_t)j * 2 * LBO;
+                const uint64_t dah = make_smem_desc(a_hi + ko, LBO, SBO), dbh = make_smem_desc(b_hi + ko, LBO, SBO);
+                const uint32_t acc0 = (it > 0 || j > 0) ? 1u : 0u;
+                if (X3) {
+                    const uint64_t dal = make_smem_desc(a_lo + ko, LBO, SBO), dbl = make_smem_desc(b_lo + ko, LBO, SBO);
+                    umma_bf16(tmem_d, dal, dbh, idesc, acc0);
+                    umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                    umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                } else {
+                    umma_bf16(tmem_d, dah, dbh, idesc, acc0);
+                }
+            }
+            umma_commit(&mbar[s]);
+        }
+    }
+    // drain: the last commit covers every MMA issued before it
+    const int nit = kb1 - kb0;
+    if (nit > 0) {
+        const int last = nit - 1;
+        mbar_wait(&mbar[last & 1], (last >> 1) & 1);
+    }
+    tc_fence_after();
+
+    // epilogue: warp w reads TMEM lanes 32*(w&3).., columns 64*(w>>2)..+63
+    const int q = warp & 3, half = warp >> 2;
+    const int gm = m0 + q * 32 + lane;
+    const bool atomic = P.ksplit > 1;
+#pragma unroll
+    for (int cc = 0; cc < 2; ++cc) {
+        const int col0 = half * 64 + cc * 32;
+        float v[32];
+        if (nit > 0) {
+            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (gm < P.M) {
+            float* crow = P.C + (long long)gm * P.ldc + n0 + col0;
+            const int nvalid = min(32, P.N - n0 - col0);
+            if (atomic) {
+                for (int j = 0; j < nvalid; ++j) {
+                    float x = v[j];
+                    if (split == 0 && P.bias) x += __ldg(P.bias + n0 + col0 + j);
+                    atomicAdd(crow + j, x);
+                }
+            } else if (nvalid == 32 && P.c_vec) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    if (P.bias) {
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + col0 + j));
+                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    }
+                    if (P.beta != 0.f) {
+                        const float4 c = *reinterpret_cast<const float4*>(crow + j);
+                        o.x += P.beta * c.x; o.y += P.beta * c.y; o.z += P.beta * c.z; o.w += P.beta * c.w;
+                    }
+                    if (P.relu) {
+                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                    }
+                    *reinterpret_cast<float4*>(crow + j) = o;
+                }
+            } else {
+                for (int j = 0; j < nvalid; ++j) {
+                    float x = v[j];
+                    if (P.bias) x += __ldg(P.bias + n0 + col0 + j);
+                    if (P.beta != 0.f) x += P.beta * crow[j];
+                    if (P.relu) x = fmaxf(x, 0.f);
+                    crow[j] = x;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<BN>(tmem_d);
 }
+
+// zero the C tiles of split-K problems (beta == 0) before the atomics land
+__global__ void __launch_bounds__(256) gemm_tc_zero_kernel(const __grid_constant__ TcBatch tb) {
+    int pi = 0;
+    while (pi + 1 < tb.n && (int)blockIdx.x >= tb.p[pi + 1].tile_start) ++pi;
+    const TcProblem& P = tb.p[pi];
+    const int t = blockIdx.x - P.tile_start;
+    const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
+    for (int e = threadIdx.x; e < BM * BN; e += 256) {
+        const int m = m0 + e / BN, n = n0 + e % BN;
+        if (m < P.M && n < P.N) P.C[(long long)m * P.ldc + n] = 0.f;
+    }
+}
+
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+int gemm_batch_simt(const fhvae_gemm_problem* problems, int n, cudaStream_t st);
+
+int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStream_t st) {
+    static bool attr_set = false;
+    const bool x3 = (mode == FHVAE_MODE_BF16X3);
+    const int smem_x3 = 2 * 4 * TILE_BYTES + 64, smem_1 = 2 * 2 * TILE_BYTES + 64;
+    if (!attr_set) {
+        cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x3);
+        cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_1);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) {
+            set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+            return (int)(e1 != cudaSuccess ? e1 : e2);
+        }
+        attr_set = true;
+    }
+    TcBatch tb, zb;
+    memset(&tb, 0, sizeof(tb));
+    memset(&zb, 0, sizeof(zb));
+    fhvae_gemm_problem small[FHVAE_GEMM_MAX_BATCH];
+    int nsmall = 0, total = 0, ztotal = 0;
+    for (int i = 0; i < n; ++i) {
+        const fhvae_gemm_problem& p = problems[i];
+        if (p.M == 0 || p.N == 0) continue;
+        // tiny contractions (K < 16) gain nothing from the tensor pipe: exact fp32 path
+        if (p.K < 16) { small[nsmall++] = p; continue; }
+        TcProblem& q = tb.p[tb.n];
+        q.A = p.A; q.B = p.B; q.C = p.C; q.bias = p.bias;
+        q.M = p.M; q.N = p.N; q.K = p.K; q.relu = p.relu; q.beta = p.beta; q.ldc = p.ldc;
+        q.a_rs = p.sa_m; q.a_ks = p.sa_k; q.b_rs = p.sb_n; q.b_ks = p.sb_k;
+        q.a_vec = (p.sa_k == 1 && p.sa_m % 4 == 0 && aligned16(p.A));
+        q.b_vec = (p.sb_k == 1 && p.sb_n % 4 == 0 && aligned16(p.B));
+        q.c_vec = (p.ldc % 4 == 0 && aligned16(p.C) && (p.bias == nullptr || aligned16(p.bias)));
+        const int nkb = cdiv(p.K, BK);
+        int ks = 1;
+        if (nkb >= 16 && !p.relu) {
+            ks = (nkb + 5) / 10;
+            if (ks > 16) ks = 16;
+        }
+        q.kb_per_split = cdiv(nkb, ks);
+        q.ksplit = cdiv(nkb, q.kb_per_split);
+        q.tiles_n = cdiv(p.N, BN);
+        q.tiles_mn = cdiv(p.M, BM) * q.tiles_n;
+        q.tile_start = total;
+        total += q.tiles_mn * q.ksplit;
+        if (q.ksplit > 1 && p.beta == 0.f) {
+            TcProblem& z = zb.p[zb.n];
+            z = q;
+            z.tile_start = ztotal;
+            ztotal += q.tiles_mn;
+            ++zb.n;
+        }
+        ++tb.n;
+    }
+    if (ztotal > 0) {
+        gemm_tc_zero_kernel<<<ztotal, 256, 0, st>>>(zb);
+        FHVAE_LAUNCH_CHECK("gemm_tc_zero");
+    }
+    if (total > 0) {
+        if (x3) gemm_tc_kernel<true><<<total, TCT, smem_x3, st>>>(tb);
+        else    gemm_tc_kernel<false><<<total, TCT, smem_1, st>>>(tb);
+        FHVAE_LAUNCH_CHECK("gemm_tc");
+    }
+    if (nsmall > 0) return gemm_batch_simt(small, nsmall, st);
+    return 0;
+}
+
+}  // namespace fhvae

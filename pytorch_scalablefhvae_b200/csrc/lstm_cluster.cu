@@ -1,3 +1,265 @@
-// Persistent thread-block-cluster LSTM recurrence (W_hh resident in shared memory across the
-// cluster, tcgen05 MMA, gates fused in the epilogue).  Lands after the SIMT path is parity-green.
+// Persistent LSTM recurrence on thread-block clusters (H = 256).
+//
+// One cluster of 8 CTAs owns NB batch rows for all T steps of one layer.  CTA j of the cluster owns
+// hidden units [32j, 32j+32) = 128 gate columns (4 gates x 32 units); its W_hh slice (128 x 256) stays
+// resident in shared memory as bf16 hi/lo in the canonical K-major UMMA layout for the whole kernel.
+// Per time step each CTA issues   D[128 gate cols, NB] = W_slice (128 x 256) * h_{t-1}^T (NB x 256)
+// on tcgen05 (accumulator in TMEM), adds the precomputed input projection P[t] (+ time-invariant Q),
+// applies sigmoid/tanh, exchanges the four gates of a unit through shared memory, updates the cell
+// (c lives in registers across steps), and writes its 32-unit slice of h_t as bf16 hi/lo straight
+// into the h operand buffers of all 8 CTAs (DSMEM vector stores), double-buffered, one cluster
+// barrier per step.  h_t / c_t / gate activations also go to HBM in fp32 for BPTT.
+//
+// The backward kernel mirrors it: dgates_t is computed pointwise by the CTA that owns the units,
+// dh_{t-1} = dgates_t W_hh is a split-K contraction over the 8 CTAs' gate-column slices, reduced
+// through DSMEM (each CTA receives the 7 partial tiles of its own 32 units).
 #include "common.cuh"
+#include "tc_common.cuh"
+
+namespace fhvae {
+
+using namespace tc;
+
+constexpr int CH = 256;            // hidden size served by the cluster kernels
+constexpr int CL = 8;              // CTAs per cluster
+constexpr int UC = CH / CL;        // 32 units per CTA
+constexpr int NC = 4 * UC;         // 128 gate columns per CTA
+constexpr int KCH = CH / 8;        // 32 sixteen-byte K chunks
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_arrive() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cluster_wait() {
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_remote(uint32_t saddr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_remote_v4(uint32_t raddr, const uint4& v) {
+    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(raddr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+template <int NB>
+__device__ __forceinline__ void tmem_ld_nb(uint32_t taddr, float (&v)[NB]);
+template <>
+__device__ __forceinline__ void tmem_ld_nb<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
+template <>
+__device__ __forceinline__ void tmem_ld_nb<16>(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory map of the forward kernel (bytes)
+template <int NB, bool X3>
+struct FwdSmem {
+    static constexpr int W_PART = NC * CH * 2;                 // 64 KB per bf16 part
+    static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
+    static constexpr int H_PART = NB * CH * 2;                 // NB x 256 bf16
+    static constexpr int H_BUF = (X3 ? 2 : 1) * H_PART;        // hi [lo]
+    static constexpr int H_OFF = W_BYTES;
+    static constexpr int G_OFF = H_OFF + 2 * H_BUF;
+    static constexpr int G_BYTES = 4 * NB * (UC + 1) * 4;      // gates[4][NB][33] fp32
+    static constexpr int BAR_OFF = G_OFF + G_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 64;
+};
+
+template <int NB, bool X3>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1)
+lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q,
+                        const float* __restrict__ W_hh, float* __restrict__ h_all,
+                        float* __restrict__ c_all, float* __restrict__ acts, int T, int B) {
+    using S = FwdSmem<NB, X3>;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = smem + S::W_PART;
+    float (*gates)[NB][UC + 1] = reinterpret_cast<float (*)[NB][UC + 1]>(smem + S::G_OFF);
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int b0 = (blockIdx.x / CL) * NB;
+    constexpr int H4 = 4 * CH;
+
+    // ---- prologue: TMEM, barrier, resident W slice (row n = gate*32 + unit  <->  W_hh row gate*H + 32*rank + unit)
+    if (warp == 0) tmem_alloc<32>(tmem_slot);
+    if (tid == 32) { mbar_init(mma_bar, 1); fence_mbar_init(); }
+    for (int item = tid; item < NC * KCH; item += 128) {
+        const int n = item & (NC - 1), kc = item >> 7;
+        const int g = n >> 5, u = n & 31;
+        const float* src = W_hh + (size_t)(g * CH + rank * UC + u) * CH + kc * 8;
+        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
+        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        const uint32_t off = (uint32_t)(kc * NC + n) * 16;
+        if (X3) {
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            *reinterpret_cast<uint4*>(w_hi + off) = hi;
+            *reinterpret_cast<uint4*>(w_lo + off) = lo;
+        } else {
+            *reinterpret_cast<uint4*>(w_hi + off) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+    }
+    // time-invariant addend for this thread's (gate = warp, unit = lane) column, all NB rows
+    const int col = warp * CH + rank * UC + lane;
+    float qv[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) qv[b] = Q ? __ldg(Q + (size_t)(b0 + b) * H4 + col) : 0.f;
+    float creg[NB / 4];
+#pragma unroll
+    for (int i = 0; i < NB / 4; ++i) creg[i] = 0.f;
+
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    constexpr uint32_t idesc = make_idesc_bf16(NC, NB);
+    constexpr uint32_t W_LBO = NC * 16, H_LBO = NB * 16, SBO_ = 128;
+    cluster_arrive();          // pairs with the wait at the top of step 0 (barriers initialised cluster-wide)
+
+    for (int t = 0; t < T; ++t) {
+        // prefetch this step's input projection
+        float pv[NB];
+        const float* Pt = P ? P + ((size_t)t * B + b0) * H4 + col : nullptr;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+
+        cluster_wait();        // h_{t-1} slices of all 8 CTAs have landed in hbuf[t&1]
+        float acc[NB];
+        if (t > 0) {
+            if (tid == 0) {
+                fence_proxy_async_all();
+                tc_fence_after();
+                const uint32_t hb = smem_u32(smem + S::H_OFF + (t & 1) * S::H_BUF);
+                const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo);
+#pragma unroll 1
+                for (int s = 0; s < CH / 16; ++s) {
+                    const uint64_t dwh = make_smem_desc(whi + s * 2 * W_LBO, W_LBO, SBO_);
+                    const uint64_t dhh = make_smem_desc(hb + s * 2 * H_LBO, H_LBO, SBO_);
+                    if (X3) {
+                        const uint64_t dwl = make_smem_desc(wlo + s * 2 * W_LBO, W_LBO, SBO_);
+                        const uint64_t dhl = make_smem_desc(hb + S::H_PART + s * 2 * H_LBO, H_LBO, SBO_);
+                        umma_bf16(tmem_d, dwl, dhh, idesc, s > 0 ? 1u : 0u);
+                        umma_bf16(tmem_d, dwh, dhl, idesc, 1u);
+                        umma_bf16(tmem_d, dwh, dhh, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_d, dwh, dhh, idesc, s > 0 ? 1u : 0u);
+                    }
+                }
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, (t - 1) & 1);
+            tc_fence_after();
+            tmem_ld_nb<NB>(tmem_d + ((uint32_t)(warp * 32) << 16), acc);
+        } else {
+#pragma unroll
+            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+        }
+        // gate activation: warp = gate (0:i 1:f 2:g 3:o), lane = unit, registers = batch rows
+        float* At = acts + ((size_t)t * B + b0) * H4 + col;
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            const float pre = acc[b] + pv[b] + qv[b];
+            const float a = (warp == 2) ? tanhf(pre) : sigmoidf_acc(pre);
+            At[(size_t)b * H4] = a;
+            gates[warp][b][lane] = a;
+        }
+        tc_fence_before();
+        __syncthreads();
+        // cell update: thread = (unit = lane, rows warp*NB/4 ..)
+        uint8_t* hnext = smem + S::H_OFF + ((t + 1) & 1) * S::H_BUF;
+        const int kglob = rank * UC + lane;                    // this unit's K index in the h operand
+        const uint32_t hoff_k = (uint32_t)(kglob >> 3) * H_LBO + (uint32_t)(kglob & 7) * 2;
+#pragma unroll
+        for (int i = 0; i < NB / 4; ++i) {
+            const int b = warp * (NB / 4) + i;
+            const float ig = gates[0][b][lane], fg = gates[1][b][lane], gg = gates[2][b][lane],
+                        og = gates[3][b][lane];
+            const float c = fmaf(fg, creg[i], ig * gg);
+            creg[i] = c;
+            const float h = og * tanhf(c);
+            const size_t o = ((size_t)t * B + b0 + b) * CH + kglob;
+            h_all[o] = h;
+            c_all[o] = c;
+            const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+            *reinterpret_cast<__nv_bfloat16*>(hnext + hoff_k + b * 16) = hh;
+            if (X3)
+                *reinterpret_cast<__nv_bfloat16*>(hnext + S::H_PART + hoff_k + b * 16) =
+                    __float2bfloat16_rn(h - __bfloat162float(hh));
+        }
+        __syncthreads();
+        // broadcast this CTA's slice (4 K-chunks x NB rows x 16 B per part) to the 7 peers
+        if (t + 1 < T) {
+            constexpr int VEC_PER_PART = 4 * NB;
+            constexpr int NVEC = (X3 ? 2 : 1) * VEC_PER_PART;
+            for (int v = tid; v < NVEC; v += 128) {
+                const int part = v / VEC_PER_PART, rem = v % VEC_PER_PART;
+                const int kcl = rem / NB, row = rem % NB;
+                uint8_t* src = hnext + part * S::H_PART + (uint32_t)(rank * 4 + kcl) * H_LBO + row * 16;
+                const uint4 val = *reinterpret_cast<const uint4*>(src);
+                const uint32_t laddr = smem_u32(src);
+#pragma unroll
+                for (uint32_t d = 0; d < CL; ++d)
+                    if (d != rank) st_remote_v4(map_remote(laddr, d), val);
+            }
+        }
+        cluster_arrive();
+    }
+    cluster_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<32>(tmem_d);
+}
+
+int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
+                  float* acts, int T, int B, int H, cudaStream_t st);
+
+template <int NB, bool X3>
+static int launch_fwd(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
+                      float* acts, int T, int B, cudaStream_t st) {
+    using S = FwdSmem<NB, X3>;
+    static bool attr = false;
+    auto kern = lstm_fwd_cluster_kernel<NB, X3>;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("lstm_fwd_cluster: cudaFuncSetAttribute(%d B): %s", S::TOTAL, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr = true;
+    }
+    kern<<<(B / NB) * CL, 128, S::TOTAL, st>>>(P, Q, W_hh, h_all, c_all, acts, T, B);
+    FHVAE_LAUNCH_CHECK("lstm_fwd_cluster");
+    return 0;
+}
+
+bool lstm_cluster_supported(int B, int H) { return H == CH && B % 32 == 0; }
+
+int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
+                     float* acts, int T, int B, int H, int mode, cudaStream_t st) {
+    if (mode == FHVAE_MODE_BF16X3) return launch_fwd<32, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
+    return launch_fwd<32, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
+}
+
+}  // namespace fhvae

@@ -60,6 +60,55 @@ def test_gemm_grouped_launch():
         assert_close(outs[3 * i], refs[i], 1e-5, f"group {i}")
 
 
+TC_TOL = {1: 2e-5, 2: 1e-2}     # bf16x3 split (fp32-parity mode) / single bf16 pass
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (5120, 1024, 80), (5120, 1024, 256), (37, 129, 53),
+                                   (256, 64, 512), (300, 160, 16), (256, 1024, 32)])
+def test_gemm_tc_nt(M, N, K, mode):
+    A, W, b = rnd(M, K, seed=1), rnd(N, K, seed=2), rnd(N, seed=3)
+    Cc = torch.full((M, N), 3.0, device=DEV)
+    gemm(A, W, Cc, M, N, K, (K, 1), (1, K), N, bias=b, relu=1, mode=mode)
+    ref = torch.relu(A.double() @ W.double().t() + b.double())
+    assert_close(Cc, ref, TC_TOL[mode], f"gemm_tc nt mode {mode}")
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_gemm_tc_dgrad_wgrad_splitk(mode):
+    # dgrad (NN), K = 1024 -> split-K with atomics, beta = 0 and beta = 1
+    M, N, K = 5120, 256, 1024
+    G, W = rnd(M, K, seed=4), rnd(K, N, seed=5, scale=0.1)
+    Cc = torch.full((M, N), 7.0, device=DEV)
+    gemm(G, W, Cc, M, N, K, (K, 1), (N, 1), N, mode=mode)
+    ref = G.double() @ W.double()
+    assert_close(Cc, ref, TC_TOL[mode], "dgrad")
+    C1 = torch.ones(M, N, device=DEV)
+    gemm(G, W, C1, M, N, K, (K, 1), (N, 1), N, beta=1.0, mode=mode)
+    assert_close(C1, ref + 1.0, TC_TOL[mode], "dgrad beta=1")
+    # wgrad (TN): dW[1024,256] = dY[4864,1024]^T X[4864,256], into a strided sub-block
+    R, Nn, K2 = 4864, 1024, 256
+    dY, X = rnd(R, Nn, seed=7, scale=0.1), rnd(R, K2, seed=8)
+    dW = torch.full((Nn, K2 + 32), 5.0, device=DEV)
+    p = GemmProblem(ptr(dY), ptr(X), ptr(dW, 16), None, Nn, K2, R, 0, 1, Nn, K2, 1, K2 + 32, 0.0, 0)
+    call("fhvae_gemm_batch", (GemmProblem * 1)(p), 1, mode)
+    assert_close(dW[:, 16:16 + K2], dY.double().t() @ X.double(), TC_TOL[mode], "wgrad")
+    assert float((dW[:, :16] - 5.0).abs().max()) == 0.0 and float((dW[:, 16 + K2:] - 5.0).abs().max()) == 0.0
+
+
+def test_gemm_tc_grouped_mixed():
+    shapes = [(100, 64, 32), (5, 200, 77), (300, 16, 8), (640, 256, 1280)]
+    probs, keep, refs = [], [], []
+    for i, (M, N, K) in enumerate(shapes):
+        A, W = rnd(M, K, seed=10 + i), rnd(N, K, seed=20 + i)
+        Cc = torch.zeros(M, N, device=DEV)
+        probs.append(GemmProblem(ptr(A), ptr(W), ptr(Cc), None, M, N, K, 0, K, 1, 1, K, N, 0.0, 0))
+        keep += [A, W, Cc]; refs.append(A.double() @ W.double().t())
+    call("fhvae_gemm_batch", (GemmProblem * 4)(*probs), 4, 1)
+    for i in range(4):
+        assert_close(keep[3 * i + 2], refs[i], 2e-5, f"group {i}")
+
+
 # ------------------------------------------------------------------------------- LSTM
 def _lstm_ref(P, Q, W, R_all, R_last):
     """fp64 autograd statement of the recurrence used for both fwd and bwd checks."""
@@ -106,6 +155,24 @@ def test_lstm_fwd_bwd_vs_fp64(T, B, H):
     dW = f(4 * H, H)
     gemm(dg[1:], h_all, dW, 4 * H, H, (T - 1) * B, (1, 4 * H), (H, 1), H)
     assert_close(dW, W.grad, 5e-5, "dW_hh")
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("T,B", [(1, 32), (3, 64), (20, 256)])
+def test_lstm_cluster_fwd_matches_simt(T, B, mode):
+    """Persistent cluster/tcgen05 recurrence (H=256) against the exact fp32 per-step kernels."""
+    H = 256
+    P = rnd(T, B, 4 * H, seed=1, scale=0.7)
+    Q = rnd(B, 4 * H, seed=2, scale=0.3)
+    W = rnd(4 * H, H, seed=3, scale=1.0 / 16)
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    ref = [f(T, B, H), f(T, B, H), f(T, B, 4 * H)]
+    out = [f(T, B, H), f(T, B, H), f(T, B, 4 * H)]
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(ref[0]), ptr(ref[1]), ptr(ref[2]), T, B, H, 0)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(out[0]), ptr(out[1]), ptr(out[2]), T, B, H, mode)
+    torch.cuda.synchronize()
+    for a, b, n in zip(out, ref, ["h_all", "c_all", "acts"]):
+        assert_close(a, b, TC_TOL[mode], f"{n} mode {mode}")
 
 
 def test_lstm_null_inputs():

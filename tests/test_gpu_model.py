@@ -105,6 +105,29 @@ def test_forward_backward_matches_oracle(name):
     assert_close(m.px_z[0], o.px_z[0], FP32_RTOL, "px mu"); assert_close(m.z2_sample, o.z2_sample, FP32_RTOL, "z2 sample")
 
 
+@pytest.mark.parametrize("name", ["simple_c0", "fhvae_small", "fhvae_c1"])
+@pytest.mark.parametrize("mode,rtol", [(P.MODE_BF16X3, FP32_RTOL), (P.MODE_BF16, 2e-2)])
+def test_tensor_core_modes_match_oracle(name, mode, rtol):
+    """north_star tolerances: fp32-parity mode (bf16 hi/lo split x3 on tcgen05) within 1e-4 relative;
+    bf16 input-GEMM mode within 2e-2, stated separately."""
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg, gemm_mode=mode)
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    eps = _eps(B, m.z1_dim, m.z2_dim)
+    out = m(x.to(DEV), idx, N, nsegs, eps=eps)
+    ref = o(x, idx, N, nsegs, eps=eps)
+    for n, a, b in zip(NAMES, out, ref):
+        assert_close(a, b, rtol, f"{name}:{n}")
+    P.loss_function(out[0], out[1], 10.0).backward()
+    O.loss_function(ref[0], ref[1], 10.0).backward()
+    po = dict(o.named_parameters())
+    worst = max(relerr(p.grad, po[k].grad) for k, p in m.named_parameters())
+    print(f"{name} mode {mode}: worst gradient max-norm relative error {worst:.2e}")
+    for k, p in m.named_parameters():
+        assert_close(p.grad, po[k].grad, rtol, f"{name}: grad {k}")
+
+
 @pytest.mark.parametrize("name", ["simple_ragged", "fhvae_small"])
 def test_flags_reproduce_reference_gradient_flow(name):
     cfg = CFGS[name]
