@@ -151,7 +151,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("FHVAE_MODE", "f32"), choices=["f32", "bf16x3", "bf16"])
+    ap.add_argument("--mode", default=os.environ.get("FHVAE_MODE", "bf16x3"), choices=["f32", "bf16x3", "bf16"])
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time split to stderr")

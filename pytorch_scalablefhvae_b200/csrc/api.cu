@@ -28,6 +28,10 @@ bool lstm_cluster_supported(int B, int H);
 int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
                      float* acts, int T, int B, int H, int mode, cudaStream_t st);
 
+int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
+                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
+                     cudaStream_t st);
+
 }  // namespace fhvae
 
 using namespace fhvae;
@@ -69,6 +73,9 @@ extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const f
                               float* dh_rec, float* dc, int T, int B, int H, int mode, void* stream) {
     FHVAE_CHECK_ARG(W_hh && c_all && acts && dgates && dc && (dh_all || dh_last), "lstm_bwd: null pointer");
     FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_bwd: need T,B>0 and H %% 8 == 0");
+    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H))
+        return lstm_bwd_cluster(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, H, mode,
+                                as_stream(stream));
     return lstm_bwd_simt(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dc, T, B, H,
                          as_stream(stream));
 }

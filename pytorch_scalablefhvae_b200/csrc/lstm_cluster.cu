@@ -232,6 +232,226 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
     if (warp == 0) tmem_dealloc<32>(tmem_d);
 }
 
+
+// ================================================================================================
+// BPTT
+// ================================================================================================
+template <int NB, bool X3>
+struct BwdSmem {
+    static constexpr int W_HALF = 128 * NC * 2;                // 128 units x 128 gate cols bf16 = 32 KB
+    static constexpr int W_PART = 2 * W_HALF;                  // 256 units: 64 KB
+    static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
+    static constexpr int G_PART = NB * NC * 2;                 // dgates operand, NB x 128 bf16
+    static constexpr int G_OFF = W_BYTES;
+    static constexpr int G_BYTES = (X3 ? 2 : 1) * G_PART;
+    static constexpr int RSTRIDE = NB + 4;                     // floats per (src, unit) row of the receive buffer
+    static constexpr int R_OFF = G_OFF + G_BYTES;
+    static constexpr int R_BYTES = CL * UC * RSTRIDE * 4;
+    static constexpr int BAR_OFF = R_OFF + R_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 64;
+};
+
+template <int NB, bool X3>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1)
+lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restrict__ dh_last,
+                        const float* __restrict__ W_hh, const float* __restrict__ c_all,
+                        const float* __restrict__ acts, float* __restrict__ dgates,
+                        float* __restrict__ dgsum, int T, int B) {
+    using S = BwdSmem<NB, X3>;
+    constexpr int RPT = NB / 4;                                // batch rows per thread
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* w_hi = smem;
+    uint8_t* w_lo = smem + S::W_PART;
+    uint8_t* g_hi = smem + S::G_OFF;
+    uint8_t* g_lo = g_hi + S::G_PART;
+    float* recv = reinterpret_cast<float*>(smem + S::R_OFF);   // [src][unit][RSTRIDE]
+    uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int b0 = (blockIdx.x / CL) * NB;
+    constexpr int H4 = 4 * CH;
+
+    if (warp == 0) tmem_alloc<2 * NB>(tmem_slot);
+    if (tid == 32) { mbar_init(mma_bar, 1); fence_mbar_init(); }
+    // resident A operand: A[n][k] = W_hh[(g*H + 32*rank + u) * H + n],  k = g*32 + u, n = output unit
+    for (int item = tid; item < CH * (NC / 8); item += 128) {
+        const int n = item & (CH - 1), kc = item >> 8;         // lanes <-> consecutive n: coalesced
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = kc * 8 + j, g = k >> 5, u = k & 31;
+            v[j] = __ldg(W_hh + (size_t)(g * CH + rank * UC + u) * CH + n);
+        }
+        const uint32_t off = (uint32_t)(n >> 7) * S::W_HALF + (uint32_t)(kc * 128 + (n & 127)) * 16;
+        if (X3) {
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            *reinterpret_cast<uint4*>(w_hi + off) = hi;
+            *reinterpret_cast<uint4*>(w_lo + off) = lo;
+        } else {
+            *reinterpret_cast<uint4*>(w_hi + off) =
+                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        }
+    }
+    float dcreg[RPT], gsum[4][RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) {
+        dcreg[i] = 0.f;
+        gsum[0][i] = gsum[1][i] = gsum[2][i] = gsum[3][i] = 0.f;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_d = *tmem_slot;
+    constexpr uint32_t idesc = make_idesc_bf16(128, NB);
+    constexpr uint32_t W_LBO = 128 * 16, G_LBO = NB * 16, SBO_ = 128;
+    const int ucol = rank * UC + lane;                         // this thread's hidden unit
+    cluster_arrive();
+
+    for (int t = T - 1; t >= 0; --t) {
+        // ---- prefetch everything the pointwise step needs (thread = unit `lane`, rows warp*RPT + i)
+        float a_i[RPT], a_f[RPT], a_g[RPT], a_o[RPT], c_t[RPT], c_p[RPT], dh[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int b = b0 + warp * RPT + i;
+            const size_t r4 = ((size_t)t * B + b) * H4, r1 = ((size_t)t * B + b) * CH;
+            a_i[i] = __ldg(acts + r4 + ucol);
+            a_f[i] = __ldg(acts + r4 + CH + ucol);
+            a_g[i] = __ldg(acts + r4 + 2 * CH + ucol);
+            a_o[i] = __ldg(acts + r4 + 3 * CH + ucol);
+            c_t[i] = __ldg(c_all + r1 + ucol);
+            c_p[i] = t ? __ldg(c_all + r1 - (size_t)B * CH + ucol) : 0.f;
+            float d = dh_all ? __ldg(dh_all + r1 + ucol) : 0.f;
+            if (t == T - 1 && dh_last) d += __ldg(dh_last + (size_t)b * CH + ucol);
+            dh[i] = d;
+        }
+        cluster_wait();        // the 8 partial dh tiles for this step have landed in recv
+        if (t < T - 1) {
+#pragma unroll
+            for (int src = 0; src < CL; ++src) {
+                const float* rp = recv + (src * UC + lane) * S::RSTRIDE + warp * RPT;
+#pragma unroll
+                for (int i = 0; i < RPT; i += 4) {
+                    const float4 p = *reinterpret_cast<const float4*>(rp + i);
+                    dh[i] += p.x; dh[i + 1] += p.y; dh[i + 2] += p.z; dh[i + 3] += p.w;
+                }
+            }
+        }
+        // ---- pointwise BPTT; dgates -> HBM, running sum, bf16 operand in smem
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const int bl = warp * RPT + i;
+            const float tc = tanhf(c_t[i]);
+            const float dc = dcreg[i] + dh[i] * a_o[i] * (1.f - tc * tc);
+            dcreg[i] = dc * a_f[i];
+            float gq[4];
+            gq[0] = dc * a_g[i] * a_i[i] * (1.f - a_i[i]);
+            gq[1] = dc * c_p[i] * a_f[i] * (1.f - a_f[i]);
+            gq[2] = dc * a_i[i] * (1.f - a_g[i] * a_g[i]);
+            gq[3] = dh[i] * tc * a_o[i] * (1.f - a_o[i]);
+            float* dg = dgates + ((size_t)t * B + b0 + bl) * H4 + ucol;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                dg[g * CH] = gq[g];
+                gsum[g][i] += gq[g];
+                const int k = g * 32 + lane;
+                const uint32_t off = (uint32_t)(k >> 3) * G_LBO + (uint32_t)bl * 16 + (uint32_t)(k & 7) * 2;
+                const __nv_bfloat16 hh = __float2bfloat16_rn(gq[g]);
+                *reinterpret_cast<__nv_bfloat16*>(g_hi + off) = hh;
+                if (X3) *reinterpret_cast<__nv_bfloat16*>(g_lo + off) = __float2bfloat16_rn(gq[g] - __bfloat162float(hh));
+            }
+        }
+        if (t > 0) {
+            fence_proxy_async();
+            __syncthreads();
+            // ---- partial dh_{t-1}[unit, b] = sum over this CTA's 128 gate columns
+            if (tid == 0) {
+                tc_fence_after();
+                const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo), ghi = smem_u32(g_hi), glo = smem_u32(g_lo);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 1
+                    for (int s = 0; s < NC / 16; ++s) {
+                        const uint32_t wo = hf * S::W_HALF + s * 2 * W_LBO, go = s * 2 * G_LBO;
+                        const uint64_t dwh = make_smem_desc(whi + wo, W_LBO, SBO_);
+                        const uint64_t dgh = make_smem_desc(ghi + go, G_LBO, SBO_);
+                        const uint32_t td = tmem_d + hf * NB;
+                        if (X3) {
+                            const uint64_t dwl = make_smem_desc(wlo + wo, W_LBO, SBO_);
+                            const uint64_t dgl = make_smem_desc(glo + go, G_LBO, SBO_);
+                            umma_bf16(td, dwl, dgh, idesc, s > 0 ? 1u : 0u);
+                            umma_bf16(td, dwh, dgl, idesc, 1u);
+                            umma_bf16(td, dwh, dgh, idesc, 1u);
+                        } else {
+                            umma_bf16(td, dwh, dgh, idesc, s > 0 ? 1u : 0u);
+                        }
+                    }
+                }
+                umma_commit(mma_bar);
+            }
+            mbar_wait(mma_bar, (T - 1 - t) & 1);
+            tc_fence_after();
+            // ---- reduce-scatter: TMEM lane = unit; warp q holds units 32q.. (-> CTA q) and 128+32q.. (-> CTA 4+q)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                float pv[NB];
+                tmem_ld_nb<NB>(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(hf * NB), pv);
+                const uint32_t dst = hf * 4 + warp;
+                const uint32_t laddr = smem_u32(recv + (rank * UC + lane) * S::RSTRIDE);
+                const uint32_t raddr = map_remote(laddr, dst);
+#pragma unroll
+                for (int i = 0; i < NB; i += 4)
+                    st_remote_v4(raddr + i * 4, make_uint4(__float_as_uint(pv[i]), __float_as_uint(pv[i + 1]),
+                                                           __float_as_uint(pv[i + 2]), __float_as_uint(pv[i + 3])));
+            }
+            tc_fence_before();
+        }
+        cluster_arrive();
+    }
+    cluster_wait();
+    if (dgsum) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            float* o = dgsum + (size_t)(b0 + warp * RPT + i) * H4 + ucol;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) o[g * CH] = gsum[g][i];
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<2 * NB>(tmem_d);
+}
+
+template <int NB, bool X3>
+static int launch_bwd(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
+                      const float* acts, float* dgates, float* dgsum, int T, int B, cudaStream_t st) {
+    using S = BwdSmem<NB, X3>;
+    static bool attr = false;
+    auto kern = lstm_bwd_cluster_kernel<NB, X3>;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+        if (e != cudaSuccess) {
+            set_error("lstm_bwd_cluster: cudaFuncSetAttribute(%d B): %s", S::TOTAL, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr = true;
+    }
+    kern<<<(B / NB) * CL, 128, S::TOTAL, st>>>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B);
+    FHVAE_LAUNCH_CHECK("lstm_bwd_cluster");
+    return 0;
+}
+
+int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
+                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
+                     cudaStream_t st) {
+    if (mode == FHVAE_MODE_BF16X3)
+        return launch_bwd<32, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
+    return launch_bwd<32, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
+}
+
 int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
                   float* acts, int T, int B, int H, cudaStream_t st);
 

@@ -175,6 +175,28 @@ def test_lstm_cluster_fwd_matches_simt(T, B, mode):
         assert_close(a, b, TC_TOL[mode], f"{n} mode {mode}")
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("T,B,use_all,use_last", [(1, 32, True, True), (4, 64, False, True), (20, 256, True, False),
+                                                  (20, 256, True, True)])
+def test_lstm_cluster_bwd_matches_simt(T, B, use_all, use_last, mode):
+    H = 256
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    P, Q = rnd(T, B, 4 * H, seed=1, scale=0.7), rnd(B, 4 * H, seed=2, scale=0.3)
+    W = rnd(4 * H, H, seed=3, scale=1.0 / 16)
+    h_all, c_all, acts = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(h_all), ptr(c_all), ptr(acts), T, B, H, 0)
+    dh_all, dh_last = rnd(T, B, H, seed=4), rnd(B, H, seed=5)
+    res = []
+    for md in (0, mode):
+        dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(2, B, H), f(B, H)
+        call("fhvae_lstm_bwd", ptr(dh_all) if use_all else None, ptr(dh_last) if use_last else None, ptr(W),
+             ptr(c_all), ptr(acts), ptr(dg), ptr(dgsum), ptr(dh_rec), ptr(dc), T, B, H, md)
+        torch.cuda.synchronize()
+        res.append((dg, dgsum))
+    assert_close(res[1][0], res[0][0], TC_TOL[mode], f"dgates mode {mode}")
+    assert_close(res[1][1], res[0][1], TC_TOL[mode], f"dgsum mode {mode}")
+
+
 def test_lstm_null_inputs():
     T, B, H = 3, 8, 16
     f = lambda *s: torch.zeros(*s, device=DEV)

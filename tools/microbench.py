@@ -1,0 +1,70 @@
+"""Per-kernel micro-timings on one B200 (CUDA events, L2 flushed between reps): LSTM recurrence
+kernels vs T, and every GEMM shape of the config-1 step.  Development aid; numbers quoted in
+profiles/ come from here."""
+import os, sys, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import pytorch_scalablefhvae_b200 as P
+from pytorch_scalablefhvae_b200 import _lib
+from pytorch_scalablefhvae_b200._lib import GemmProblem
+from pytorch_scalablefhvae_b200.plan import ptr
+
+dev = "cuda"
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+
+def timeit(f, reps=10):
+    f(); torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(); f(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2] * 1e3   # us
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def lstm(mode, T, B=256, H=256):
+    z = lambda *s: torch.randn(*s, device=dev) * 0.3
+    Pp, Q, W = z(T, B, 4 * H), z(B, 4 * H), z(4 * H, H) / 16
+    h, c, a = z(T, B, H), z(T, B, H), z(T, B, 4 * H)
+    dg, dgs, dhr, dc, dh = z(T, B, 4 * H), z(B, 4 * H), z(2, B, H), z(B, H), z(T, B, H)
+    fw = lambda: _lib.check(_lib.fn("fhvae_lstm_fwd")(ptr(Pp), ptr(Q), ptr(W), ptr(h), ptr(c), ptr(a), T, B, H, mode, st()))
+    bw = lambda: _lib.check(_lib.fn("fhvae_lstm_bwd")(ptr(dh), None, ptr(W), ptr(c), ptr(a), ptr(dg), ptr(dgs), ptr(dhr), ptr(dc), T, B, H, mode, st()))
+    return timeit(fw), timeit(bw)
+
+
+def gemm(mode, M, N, K, kind):
+    A = torch.randn(M, K, device=dev); Bm = torch.randn(N, K, device=dev); C = torch.zeros(M, N, device=dev)
+    if kind == "nt":
+        p = GemmProblem(ptr(A), ptr(Bm), ptr(C), None, M, N, K, 0, K, 1, 1, K, N, 0.0, 0)
+    elif kind == "nn":
+        Bm = torch.randn(K, N, device=dev)
+        p = GemmProblem(ptr(A), ptr(Bm), ptr(C), None, M, N, K, 0, K, 1, N, 1, N, 0.0, 0)
+    else:  # tn: C[M,N] = G[K,M]^T X[K,N]
+        A = torch.randn(K, M, device=dev); Bm = torch.randn(K, N, device=dev)
+        p = GemmProblem(ptr(A), ptr(Bm), ptr(C), None, M, N, K, 0, 1, M, N, 1, N, 0.0, 0)
+    arr = (GemmProblem * 1)(p)
+    us = timeit(lambda: _lib.check(_lib.fn("fhvae_gemm_batch")(arr, 1, mode, st())))
+    return us, 2.0 * M * N * K / us / 1e6   # TFLOP/s
+
+
+if __name__ == "__main__":
+    out = {}
+    for mode in (1, 2):
+        for T in (1, 2, 5, 20):
+            out[f"lstm mode{mode} T{T} fwd/bwd us"] = lstm(mode, T)
+    shapes = [("nt", 5120, 1024, 80), ("nt", 5120, 1024, 256), ("nt", 5120, 160, 256), ("nt", 256, 1024, 64),
+              ("nt", 256, 64, 256), ("nn", 5120, 256, 1024), ("nn", 5120, 256, 160), ("nn", 256, 64, 1024),
+              ("tn", 1024, 256, 4864), ("tn", 1024, 256, 5120), ("tn", 1024, 80, 5120), ("tn", 160, 256, 5120),
+              ("tn", 1024, 64, 256), ("tn", 64, 256, 256)]
+    for mode in (1, 2):
+        for kind, M, N, K in shapes:
+            out[f"gemm mode{mode} {kind} {M}x{N}x{K} us,TF"] = gemm(mode, M, N, K, kind)
+    for k, v in out.items():
+        print(k, [round(x, 2) for x in v])
