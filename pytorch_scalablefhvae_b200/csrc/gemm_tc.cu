@@ -9,8 +9,9 @@
 //                      => ~1e-5 relative, the "fp32" tolerance of the north star, at 1/3 of the bf16 rate.
 // Shared-memory tiles use the canonical K-major no-swizzle UMMA layout (8x16B core matrices): element
 // (r,k) of a 128 x 64 tile at byte (k/8)*2048 + r*16 + (k%8)*2, i.e. LBO = 2048, SBO = 128.
-// 128x128 output tile per CTA, K stepped in blocks of 64 through a 2-stage ring: all 256 threads stage
-// (global fp32 -> bf16 hi/lo -> st.shared, fence.proxy.async), one thread issues the MMAs, tcgen05.commit
+// 128x128 output tile per CTA, K stepped in blocks of BK (64 bf16 / 32 bf16x3: 64 KB of smem either way,
+// two CTAs per SM) through a 2-stage ring: all 256 threads stage (global fp32 -> registers, prefetched one
+// block ahead -> bf16 hi/lo -> st.shared, fence.proxy.async), one thread issues the MMAs, tcgen05.commit
 // on an mbarrier releases the stage.  Long-K problems (weight gradients: K = T*B) are split along K
 // across CTAs and reduced with fp32 atomics into a pre-zeroed C.
 // Epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/beta/ReLU -> global.
@@ -21,10 +22,18 @@ namespace fhvae {
 
 using namespace tc;
 
-constexpr int BM = 128, BN = 128, BK = 64;
+constexpr int BM = 128, BN = 128;
 constexpr int TCT = 256;                        // threads per CTA
-constexpr int TILE_BYTES = BM * BK * 2;         // one bf16 operand tile: 16 KB
 constexpr uint32_t LBO = BM * 16, SBO = 128;
+template <bool X3>
+struct Cfg {
+    static constexpr int BK = X3 ? 32 : 64;
+    static constexpr int TILE_BYTES = BM * BK * 2;          // one bf16 operand tile
+    static constexpr int OPS = X3 ? 4 : 2;                  // A_hi [A_lo] B_hi [B_lo]
+    static constexpr int STAGE_BYTES = OPS * TILE_BYTES;    // 32 KB
+    static constexpr int IT = BM * (BK / 8) / TCT;          // (row, k-chunk) items per thread per operand
+    static constexpr int SMEM = 2 * STAGE_BYTES + 64;
+};
 
 struct TcProblem {
     const float* A;
@@ -46,56 +55,64 @@ struct TcBatch {
     int n;
 };
 
-// stage one 128 x 64 operand tile: thread -> (row = item & 127, k-chunk = item >> 7), 4 items / thread
-template <bool X3>
-__device__ __forceinline__ void stage_tile(const float* __restrict__ src, long long rs, long long ks, int vec,
-                                           int row0, int rows, int k0, int kend, uint8_t* s_hi, uint8_t* s_lo) {
+// One operand tile = 128 rows x BK: thread -> items (row = item & 127, k-chunk = item >> 7).
+// load_tile: global fp32 -> registers (issued one k-block ahead);  store_tile: registers -> bf16 smem.
+template <int IT>
+__device__ __forceinline__ void load_tile(const float* __restrict__ src, long long rs, long long ks, int vec,
+                                          int row0, int rows, int k0, int kend, float (&v)[IT][8]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < IT; ++i) {
         const int item = threadIdx.x + i * TCT;
         const int r = item & (BM - 1), kc = item >> 7;
         const int gr = row0 + r, gk = k0 + kc * 8;
-        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = 0.f;
+        for (int j = 0; j < 8; ++j) v[i][j] = 0.f;
         if (gr < rows && gk < kend) {
             if (ks == 1) {
                 const float* p = src + (long long)gr * rs + gk;
                 if (vec && gk + 8 <= kend) {
                     const float4 a = __ldg(reinterpret_cast<const float4*>(p));
                     const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-                    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                    v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                    v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+                    v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (gk + j < kend) v[j] = __ldg(p + j);
+                        if (gk + j < kend) v[i][j] = __ldg(p + j);
                 }
             } else {   // rows contiguous: coalesced across the warp for every k
                 const float* p = src + (long long)gk * ks + gr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (gk + j < kend) v[j] = __ldg(p + (long long)j * ks);
+                    if (gk + j < kend) v[i][j] = __ldg(p + (long long)j * ks);
             }
         }
+    }
+}
+template <bool X3, int IT>
+__device__ __forceinline__ void store_tile(const float (&v)[IT][8], uint8_t* s_hi, uint8_t* s_lo) {
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+        const int item = threadIdx.x + i * TCT;
+        const int r = item & (BM - 1), kc = item >> 7;
         const uint32_t off = (uint32_t)(kc * BM + r) * 16;
         if (X3) {
             uint4 hi, lo;
-            split_bf16(v, hi, lo);
+            split_bf16(v[i], hi, lo);
             *reinterpret_cast<uint4*>(s_hi + off) = hi;
             *reinterpret_cast<uint4*>(s_lo + off) = lo;
         } else {
-            *reinterpret_cast<uint4*>(s_hi + off) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            *reinterpret_cast<uint4*>(s_hi + off) = make_uint4(pack_bf16(v[i][0], v[i][1]), pack_bf16(v[i][2], v[i][3]),
+                                                               pack_bf16(v[i][4], v[i][5]), pack_bf16(v[i][6], v[i][7]));
         }
     }
 }
 
 template <bool X3>
-__global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__ TcBatch tb) {
+__global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(const __grid_constant__ TcBatch tb) {
     extern __shared__ __align__(1024) uint8_t smem[];
-    constexpr int OPS = X3 ? 4 : 2;                        // tiles per stage: A_hi [A_lo] B_hi [B_lo]
-    constexpr int STAGE_BYTES = OPS * TILE_BYTES;
+    using C = Cfg<X3>;
+    constexpr int BK = C::BK, TILE_BYTES = C::TILE_BYTES, STAGE_BYTES = C::STAGE_BYTES, IT = C::IT;
     uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);   // [2]
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
 
@@ -106,7 +123,7 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__
     const int split = t / P.tiles_mn;
     t -= split * P.tiles_mn;
     const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
-    const int nkb_total = (P.K + BK - 1) / BK;
+    const int nkb_total = (P.K + Cfg<X3>::BK - 1) / Cfg<X3>::BK;
     const int kb0 = split * P.kb_per_split;
     const int kb1 = min(nkb_total, kb0 + P.kb_per_split);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -123,14 +140,22 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__
     const uint32_t tmem_d = *tmem_slot;
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
 
+    float va[IT][8], vb[IT][8];
+    if (kb0 < kb1) {
+        load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, kb0 * BK, P.K, va);
+        load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, kb0 * BK, P.K, vb);
+    }
     for (int kb = kb0; kb < kb1; ++kb) {
         const int it = kb - kb0, s = it & 1;
         uint8_t* st = smem + s * STAGE_BYTES;
         if (it >= 2) mbar_wait(&mbar[s], ((it >> 1) - 1) & 1);     // MMAs that read this stage are done
         const int k0 = kb * BK;
-        stage_tile<X3>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0, P.K, st, st + TILE_BYTES);
-        stage_tile<X3>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0, P.K, st + (X3 ? 2 : 1) * TILE_BYTES,
-                       st + 3 * TILE_BYTES);
+        store_tile<X3, IT>(va, st, st + TILE_BYTES);
+        store_tile<X3, IT>(vb, st + (X3 ? 2 : 1) * TILE_BYTES, st + 3 * TILE_BYTES);
+        if (kb + 1 < kb1) {                                        // next block's loads fly during sync + MMA
+            load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0 + BK, P.K, va);
+            load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0 + BK, P.K, vb);
+        }
         fence_proxy_async();
         __syncthreads();
         if (tid == 0) {
@@ -163,13 +188,15 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__
     }
     tc_fence_after();
 
-    // epilogue: warp w reads TMEM lanes 32*(w&3).., columns 64*(w>>2)..+63
+    // epilogue: warp w reads TMEM lanes 32*(w&3).., columns 64*(w>>2)..+63 (thread = row), transposes each
+    // 32x32 block through shared memory (the operand stages are free now) and writes full 128-byte lines
     const int q = warp & 3, half = warp >> 2;
-    const int gm = m0 + q * 32 + lane;
+    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
     const bool atomic = P.ksplit > 1;
-#pragma unroll
+#pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
         const int col0 = half * 64 + cc * 32;
+        if (n0 + col0 >= P.N) break;
         float v[32];
         if (nit > 0) {
             tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
@@ -177,39 +204,25 @@ __global__ void __launch_bounds__(TCT, 1) gemm_tc_kernel(const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.f;
         }
-        if (gm < P.M) {
-            float* crow = P.C + (long long)gm * P.ldc + n0 + col0;
-            const int nvalid = min(32, P.N - n0 - col0);
-            if (atomic) {
-                for (int j = 0; j < nvalid; ++j) {
-                    float x = v[j];
-                    if (split == 0 && P.bias) x += __ldg(P.bias + n0 + col0 + j);
-                    atomicAdd(crow + j, x);
-                }
-            } else if (nvalid == 32 && P.c_vec) {
+        __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    if (P.bias) {
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(P.bias + n0 + col0 + j));
-                        o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-                    }
-                    if (P.beta != 0.f) {
-                        const float4 c = *reinterpret_cast<const float4*>(crow + j);
-                        o.x += P.beta * c.x; o.y += P.beta * c.y; o.z += P.beta * c.z; o.w += P.beta * c.w;
-                    }
-                    if (P.relu) {
-                        o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
-                    }
-                    *reinterpret_cast<float4*>(crow + j) = o;
-                }
+        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+        __syncwarp();
+        const int gn = n0 + col0 + lane;                      // lane = column now
+        const bool nok = gn < P.N;
+        const float bv = (nok && P.bias && (!atomic || split == 0)) ? __ldg(P.bias + gn) : 0.f;
+        const int mrow0 = m0 + q * 32;
+        const int rmax = min(32, P.M - mrow0);
+        if (nok) {
+            float* cp = P.C + (long long)mrow0 * P.ldc + gn;
+            if (atomic) {
+                for (int r = 0; r < rmax; ++r) atomicAdd(cp + (long long)r * P.ldc, tr[r * 33 + lane] + bv);
             } else {
-                for (int j = 0; j < nvalid; ++j) {
-                    float x = v[j];
-                    if (P.bias) x += __ldg(P.bias + n0 + col0 + j);
-                    if (P.beta != 0.f) x += P.beta * crow[j];
+                for (int r = 0; r < rmax; ++r) {
+                    float x = tr[r * 33 + lane] + bv;
+                    if (P.beta != 0.f) x += P.beta * cp[(long long)r * P.ldc];
                     if (P.relu) x = fmaxf(x, 0.f);
-                    crow[j] = x;
+                    cp[(long long)r * P.ldc] = x;
                 }
             }
         }
@@ -239,21 +252,26 @@ int gemm_batch_simt(const fhvae_gemm_problem* problems, int n, cudaStream_t st);
 int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStream_t st) {
     static bool attr_set = false;
     const bool x3 = (mode == FHVAE_MODE_BF16X3);
-    const int smem_x3 = 2 * 4 * TILE_BYTES + 64, smem_1 = 2 * 2 * TILE_BYTES + 64;
     if (!attr_set) {
-        cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_x3);
-        cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_1);
+        cudaError_t e1 = cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<true>::SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg<false>::SMEM);
         if (e1 != cudaSuccess || e2 != cudaSuccess) {
             set_error("gemm_tc: cudaFuncSetAttribute failed: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
             return (int)(e1 != cudaSuccess ? e1 : e2);
         }
         attr_set = true;
     }
+    const int bk = x3 ? Cfg<true>::BK : Cfg<false>::BK;
     TcBatch tb, zb;
     memset(&tb, 0, sizeof(tb));
     memset(&zb, 0, sizeof(zb));
     fhvae_gemm_problem small[FHVAE_GEMM_MAX_BATCH];
-    int nsmall = 0, total = 0, ztotal = 0;
+    int nsmall = 0, total = 0, ztotal = 0, unsplit_tiles = 0;
+    for (int i = 0; i < n; ++i)
+        if (problems[i].M > 0 && problems[i].N > 0 && problems[i].K >= 16)
+            unsplit_tiles += cdiv(problems[i].M, BM) * cdiv(problems[i].N, BN);
+    // split K so that the launch offers ~2 CTAs per SM, never below 128 of K per split
+    const int want_split = unsplit_tiles > 0 ? cdiv(2 * kNumSM, unsplit_tiles) : 1;
     for (int i = 0; i < n; ++i) {
         const fhvae_gemm_problem& p = problems[i];
         if (p.M == 0 || p.N == 0) continue;
@@ -266,11 +284,13 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         q.a_vec = (p.sa_k == 1 && p.sa_m % 4 == 0 && aligned16(p.A));
         q.b_vec = (p.sb_k == 1 && p.sb_n % 4 == 0 && aligned16(p.B));
         q.c_vec = (p.ldc % 4 == 0 && aligned16(p.C) && (p.bias == nullptr || aligned16(p.bias)));
-        const int nkb = cdiv(p.K, BK);
+        const int nkb = cdiv(p.K, bk);
         int ks = 1;
-        if (nkb >= 16 && !p.relu) {
-            ks = (nkb + 5) / 10;
-            if (ks > 16) ks = 16;
+        if (!p.relu && (p.beta == 0.f || p.beta == 1.f)) {
+            const int max_split = p.K / 128;                 // >= 128 of K per split
+            ks = want_split < max_split ? want_split : max_split;
+            if (ks > 32) ks = 32;
+            if (ks < 1) ks = 1;
         }
         q.kb_per_split = cdiv(nkb, ks);
         q.ksplit = cdiv(nkb, q.kb_per_split);
@@ -292,8 +312,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         FHVAE_LAUNCH_CHECK("gemm_tc_zero");
     }
     if (total > 0) {
-        if (x3) gemm_tc_kernel<true><<<total, TCT, smem_x3, st>>>(tb);
-        else    gemm_tc_kernel<false><<<total, TCT, smem_1, st>>>(tb);
+        if (x3) gemm_tc_kernel<true><<<total, TCT, Cfg<true>::SMEM, st>>>(tb);
+        else    gemm_tc_kernel<false><<<total, TCT, Cfg<false>::SMEM, st>>>(tb);
         FHVAE_LAUNCH_CHECK("gemm_tc");
     }
     if (nsmall > 0) return gemm_batch_simt(small, nsmall, st);

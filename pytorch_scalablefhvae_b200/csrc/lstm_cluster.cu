@@ -13,6 +13,7 @@
 // The backward kernel mirrors it: dgates_t is computed pointwise by the CTA that owns the units,
 // dh_{t-1} = dgates_t W_hh is a split-K contraction over the 8 CTAs' gate-column slices, reduced
 // through DSMEM (each CTA receives the 7 partial tiles of its own 32 units).
+#include <stdlib.h>
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -25,6 +26,7 @@ constexpr int CL = 8;              // CTAs per cluster
 constexpr int UC = CH / CL;        // 32 units per CTA
 constexpr int NC = 4 * UC;         // 128 gate columns per CTA
 constexpr int KCH = CH / 8;        // 32 sixteen-byte K chunks
+constexpr int CNT = 512;           // threads per CTA: 4 TMEM lane quarters x 4 column groups
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
     uint32_t r;
@@ -48,8 +50,16 @@ __device__ __forceinline__ void st_remote_v4(uint32_t raddr, const uint4& v) {
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-template <int NB>
-__device__ __forceinline__ void tmem_ld_nb(uint32_t taddr, float (&v)[NB]);
+// Development aid (tools/timeline.py builds with -DFHVAE_TIMELINE): SM-clock stamps of CTA 0 / thread 0.
+#ifdef FHVAE_TIMELINE
+__device__ long long g_timeline[2][32][12];
+#define TL(k, step, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (step) < 32) g_timeline[k][step][slot] = clock64(); } while (0)
+#else
+#define TL(k, step, slot) do { } while (0)
+#endif
+
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_nb(uint32_t taddr, float (&v)[NCOL]);
 template <>
 __device__ __forceinline__ void tmem_ld_nb<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
 template <>
@@ -66,6 +76,28 @@ __device__ __forceinline__ void tmem_ld_nb<16>(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+template <>
+__device__ __forceinline__ void tmem_ld_nb<4>(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <>
+__device__ __forceinline__ void tmem_ld_nb<8>(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
 
 // shared-memory map of the forward kernel (bytes)
 template <int NB, bool X3>
@@ -81,12 +113,16 @@ struct FwdSmem {
     static constexpr int TOTAL = BAR_OFF + 64;
 };
 
-template <int NB, bool X3>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1)
+template <int NB, bool X3, int NT>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q,
                         const float* __restrict__ W_hh, float* __restrict__ h_all,
                         float* __restrict__ c_all, float* __restrict__ acts, int T, int B) {
     using S = FwdSmem<NB, X3>;
+    constexpr int NCG = NT / 128;              // column groups: warps sharing one TMEM lane quarter
+    constexpr int CPW = NB / NCG;              // batch rows (TMEM columns) per thread in the gate phase
+    constexpr int RPT = NB * 32 / NT;          // batch rows per thread in the cell phase
+    constexpr int WIT = NC * KCH / NT;         // resident-W items per thread
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_hi = smem;
     uint8_t* w_lo = smem + S::W_PART;
@@ -95,39 +131,51 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;    // gate (= TMEM lane quarter), column group
     const uint32_t rank = cluster_ctarank();
     const int b0 = (blockIdx.x / CL) * NB;
     constexpr int H4 = 4 * CH;
 
     // ---- prologue: TMEM, barrier, resident W slice (row n = gate*32 + unit  <->  W_hh row gate*H + 32*rank + unit)
-    if (warp == 0) tmem_alloc<32>(tmem_slot);
+    constexpr int NACC = 4;                    // independent TMEM accumulators (k-steps round-robin)
+    constexpr int TCOLS = NACC * NB < 32 ? 32 : NACC * NB;
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) { mbar_init(mma_bar, 1); fence_mbar_init(); }
-    for (int item = tid; item < NC * KCH; item += 128) {
-        const int n = item & (NC - 1), kc = item >> 7;
-        const int g = n >> 5, u = n & 31;
-        const float* src = W_hh + (size_t)(g * CH + rank * UC + u) * CH + kc * 8;
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        const float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-        const uint32_t off = (uint32_t)(kc * NC + n) * 16;
-        if (X3) {
-            uint4 hi, lo;
-            split_bf16(v, hi, lo);
-            *reinterpret_cast<uint4*>(w_hi + off) = hi;
-            *reinterpret_cast<uint4*>(w_lo + off) = lo;
-        } else {
-            *reinterpret_cast<uint4*>(w_hi + off) =
-                make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+    {
+        float4 wa[WIT], wb[WIT];
+#pragma unroll
+        for (int i = 0; i < WIT; ++i) {        // all loads in flight first
+            const int item = tid + i * NT;
+            const int n = item & (NC - 1), kc = item >> 7;
+            const float* src = W_hh + (size_t)((n >> 5) * CH + rank * UC + (n & 31)) * CH + kc * 8;
+            wa[i] = __ldg(reinterpret_cast<const float4*>(src));
+            wb[i] = __ldg(reinterpret_cast<const float4*>(src) + 1);
+        }
+#pragma unroll
+        for (int i = 0; i < WIT; ++i) {
+            const int item = tid + i * NT;
+            const int n = item & (NC - 1), kc = item >> 7;
+            const float v[8] = {wa[i].x, wa[i].y, wa[i].z, wa[i].w, wb[i].x, wb[i].y, wb[i].z, wb[i].w};
+            const uint32_t off = (uint32_t)(kc * NC + n) * 16;
+            if (X3) {
+                uint4 hi, lo;
+                split_bf16(v, hi, lo);
+                *reinterpret_cast<uint4*>(w_hi + off) = hi;
+                *reinterpret_cast<uint4*>(w_lo + off) = lo;
+            } else {
+                *reinterpret_cast<uint4*>(w_hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
+                                                                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+            }
         }
     }
-    // time-invariant addend for this thread's (gate = warp, unit = lane) column, all NB rows
-    const int col = warp * CH + rank * UC + lane;
-    float qv[NB];
+    // time-invariant addend for this thread's (gate q, unit lane) column, rows cg*CPW ..
+    const int col = q * CH + rank * UC + lane;
+    float qv[CPW];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) qv[b] = Q ? __ldg(Q + (size_t)(b0 + b) * H4 + col) : 0.f;
-    float creg[NB / 4];
+    for (int b = 0; b < CPW; ++b) qv[b] = Q ? __ldg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f;
+    float creg[RPT];
 #pragma unroll
-    for (int i = 0; i < NB / 4; ++i) creg[i] = 0.f;
+    for (int i = 0; i < RPT; ++i) creg[i] = 0.f;
 
     fence_proxy_async();
     tc_fence_before();
@@ -140,80 +188,98 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
 
     for (int t = 0; t < T; ++t) {
         // prefetch this step's input projection
-        float pv[NB];
-        const float* Pt = P ? P + ((size_t)t * B + b0) * H4 + col : nullptr;
+        float pv[CPW];
+        const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
 #pragma unroll
-        for (int b = 0; b < NB; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+        for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
 
+        TL(0, t, 0);
         cluster_wait();        // h_{t-1} slices of all 8 CTAs have landed in hbuf[t&1]
-        float acc[NB];
+        TL(0, t, 1);
+        float acc[CPW];
         if (t > 0) {
             if (tid == 0) {
                 fence_proxy_async_all();
                 tc_fence_after();
                 const uint32_t hb = smem_u32(smem + S::H_OFF + (t & 1) * S::H_BUF);
-                const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo);
-#pragma unroll 1
+                // descriptors differ only in the 16-byte-granular start address: base + constant
+                const uint64_t dwh0 = make_smem_desc(smem_u32(w_hi), W_LBO, SBO_);
+                const uint64_t dwl0 = make_smem_desc(smem_u32(w_lo), W_LBO, SBO_);
+                const uint64_t dhh0 = make_smem_desc(hb, H_LBO, SBO_);
+                const uint64_t dhl0 = make_smem_desc(hb + S::H_PART, H_LBO, SBO_);
+#pragma unroll
                 for (int s = 0; s < CH / 16; ++s) {
-                    const uint64_t dwh = make_smem_desc(whi + s * 2 * W_LBO, W_LBO, SBO_);
-                    const uint64_t dhh = make_smem_desc(hb + s * 2 * H_LBO, H_LBO, SBO_);
+                    const uint64_t iw = (uint64_t)((s * 2 * W_LBO) >> 4), ih = (uint64_t)((s * 2 * H_LBO) >> 4);
+                    const uint32_t td = tmem_d + (uint32_t)((s % NACC) * NB);
+                    const uint32_t first = s >= NACC ? 1u : 0u;
                     if (X3) {
-                        const uint64_t dwl = make_smem_desc(wlo + s * 2 * W_LBO, W_LBO, SBO_);
-                        const uint64_t dhl = make_smem_desc(hb + S::H_PART + s * 2 * H_LBO, H_LBO, SBO_);
-                        umma_bf16(tmem_d, dwl, dhh, idesc, s > 0 ? 1u : 0u);
-                        umma_bf16(tmem_d, dwh, dhl, idesc, 1u);
-                        umma_bf16(tmem_d, dwh, dhh, idesc, 1u);
+                        umma_bf16(td, dwl0 + iw, dhh0 + ih, idesc, first);
+                        umma_bf16(td, dwh0 + iw, dhl0 + ih, idesc, 1u);
+                        umma_bf16(td, dwh0 + iw, dhh0 + ih, idesc, 1u);
                     } else {
-                        umma_bf16(tmem_d, dwh, dhh, idesc, s > 0 ? 1u : 0u);
+                        umma_bf16(td, dwh0 + iw, dhh0 + ih, idesc, first);
                     }
                 }
                 umma_commit(mma_bar);
+                TL(0, t, 2);
             }
             mbar_wait(mma_bar, (t - 1) & 1);
+            TL(0, t, 3);
             tc_fence_after();
-            tmem_ld_nb<NB>(tmem_d + ((uint32_t)(warp * 32) << 16), acc);
+            tmem_ld_nb<CPW>(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CPW), acc);
+#pragma unroll
+            for (int a = 1; a < NACC; ++a) {
+                float part[CPW];
+                tmem_ld_nb<CPW>(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * NB + cg * CPW), part);
+#pragma unroll
+                for (int b = 0; b < CPW; ++b) acc[b] += part[b];
+            }
+            TL(0, t, 4);
         } else {
 #pragma unroll
-            for (int b = 0; b < NB; ++b) acc[b] = 0.f;
+            for (int b = 0; b < CPW; ++b) acc[b] = 0.f;
         }
-        // gate activation: warp = gate (0:i 1:f 2:g 3:o), lane = unit, registers = batch rows
-        float* At = acts + ((size_t)t * B + b0) * H4 + col;
+        // gate activation: q = gate (0:i 1:f 2:g 3:o), lane = unit, registers = batch rows
+        // (HBM stores are deferred past the cluster arrive: its release fence would otherwise wait for them)
+        float aval[CPW];
 #pragma unroll
-        for (int b = 0; b < NB; ++b) {
+        for (int b = 0; b < CPW; ++b) {
             const float pre = acc[b] + pv[b] + qv[b];
-            const float a = (warp == 2) ? tanhf(pre) : sigmoidf_acc(pre);
-            At[(size_t)b * H4] = a;
-            gates[warp][b][lane] = a;
+            aval[b] = (q == 2) ? tanhf_fast(pre) : sigmoidf_fast(pre);
+            gates[q][cg * CPW + b][lane] = aval[b];
         }
+        TL(0, t, 5);
         tc_fence_before();
         __syncthreads();
-        // cell update: thread = (unit = lane, rows warp*NB/4 ..)
+        TL(0, t, 6);
+        // cell update: thread = (unit = lane, rows warp*RPT ..)
         uint8_t* hnext = smem + S::H_OFF + ((t + 1) & 1) * S::H_BUF;
         const int kglob = rank * UC + lane;                    // this unit's K index in the h operand
+        float hreg[RPT];
         const uint32_t hoff_k = (uint32_t)(kglob >> 3) * H_LBO + (uint32_t)(kglob & 7) * 2;
 #pragma unroll
-        for (int i = 0; i < NB / 4; ++i) {
-            const int b = warp * (NB / 4) + i;
+        for (int i = 0; i < RPT; ++i) {
+            const int b = warp * RPT + i;
             const float ig = gates[0][b][lane], fg = gates[1][b][lane], gg = gates[2][b][lane],
                         og = gates[3][b][lane];
             const float c = fmaf(fg, creg[i], ig * gg);
             creg[i] = c;
-            const float h = og * tanhf(c);
-            const size_t o = ((size_t)t * B + b0 + b) * CH + kglob;
-            h_all[o] = h;
-            c_all[o] = c;
+            const float h = og * tanhf_fast(c);
+            hreg[i] = h;
             const __nv_bfloat16 hh = __float2bfloat16_rn(h);
             *reinterpret_cast<__nv_bfloat16*>(hnext + hoff_k + b * 16) = hh;
             if (X3)
                 *reinterpret_cast<__nv_bfloat16*>(hnext + S::H_PART + hoff_k + b * 16) =
                     __float2bfloat16_rn(h - __bfloat162float(hh));
         }
+        TL(0, t, 7);
         __syncthreads();
+        TL(0, t, 8);
         // broadcast this CTA's slice (4 K-chunks x NB rows x 16 B per part) to the 7 peers
         if (t + 1 < T) {
             constexpr int VEC_PER_PART = 4 * NB;
             constexpr int NVEC = (X3 ? 2 : 1) * VEC_PER_PART;
-            for (int v = tid; v < NVEC; v += 128) {
+            for (int v = tid; v < NVEC; v += NT) {
                 const int part = v / VEC_PER_PART, rem = v % VEC_PER_PART;
                 const int kcl = rem / NB, row = rem % NB;
                 uint8_t* src = hnext + part * S::H_PART + (uint32_t)(rank * 4 + kcl) * H_LBO + row * 16;
@@ -224,14 +290,26 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
                     if (d != rank) st_remote_v4(map_remote(laddr, d), val);
             }
         }
+        TL(0, t, 9);
         cluster_arrive();
+        TL(0, t, 10);
+        // saved-for-backward state -> HBM, off the critical path
+        float* At = acts + ((size_t)t * B + b0 + cg * CPW) * H4 + col;
+#pragma unroll
+        for (int b = 0; b < CPW; ++b) At[(size_t)b * H4] = aval[b];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            const size_t o = ((size_t)t * B + b0 + warp * RPT + i) * CH + kglob;
+            h_all[o] = hreg[i];
+            c_all[o] = creg[i];
+        }
+        TL(0, t, 11);
     }
     cluster_wait();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<32>(tmem_d);
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem_d);
 }
-
 
 // ================================================================================================
 // BPTT
@@ -251,14 +329,18 @@ struct BwdSmem {
     static constexpr int TOTAL = BAR_OFF + 64;
 };
 
-template <int NB, bool X3>
-__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(128, 1)
+template <int NB, bool X3, int NT>
+__global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restrict__ dh_last,
                         const float* __restrict__ W_hh, const float* __restrict__ c_all,
                         const float* __restrict__ acts, float* __restrict__ dgates,
                         float* __restrict__ dgsum, int T, int B) {
     using S = BwdSmem<NB, X3>;
-    constexpr int RPT = NB / 4;                                // batch rows per thread
+    constexpr int NCG = NT / 128;                              // column groups per TMEM lane quarter
+    constexpr int CPW = NB / NCG;                              // TMEM columns per thread in the scatter phase
+    constexpr int RPT = NB * 32 / NT;                          // batch rows per thread in the pointwise phase
+    constexpr int WIT = CH * (NC / 8) / NT;                    // resident-W items per thread
+    static_assert(RPT == 1 || RPT == 2 || RPT % 4 == 0, "receive-buffer reads are scalar / float2 / float4");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint8_t* w_hi = smem;
     uint8_t* w_lo = smem + S::W_PART;
@@ -269,14 +351,19 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = warp >> 2;
     const uint32_t rank = cluster_ctarank();
     const int b0 = (blockIdx.x / CL) * NB;
     constexpr int H4 = 4 * CH;
 
-    if (warp == 0) tmem_alloc<2 * NB>(tmem_slot);
+    constexpr int NACC = 2;                                    // independent accumulators per unit half
+    constexpr int TCOLS = 2 * NACC * NB < 32 ? 32 : 2 * NACC * NB;
+    if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) { mbar_init(mma_bar, 1); fence_mbar_init(); }
     // resident A operand: A[n][k] = W_hh[(g*H + 32*rank + u) * H + n],  k = g*32 + u, n = output unit
-    for (int item = tid; item < CH * (NC / 8); item += 128) {
+#pragma unroll 2
+    for (int i = 0; i < WIT; ++i) {
+        const int item = tid + i * NT;
         const int n = item & (CH - 1), kc = item >> 8;         // lanes <-> consecutive n: coalesced
         float v[8];
 #pragma unroll
@@ -333,18 +420,26 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
 #pragma unroll
             for (int src = 0; src < CL; ++src) {
                 const float* rp = recv + (src * UC + lane) * S::RSTRIDE + warp * RPT;
+                if (RPT == 1) {
+                    dh[0] += rp[0];
+                } else if (RPT == 2) {
+                    const float2 p = *reinterpret_cast<const float2*>(rp);
+                    dh[0] += p.x; dh[RPT - 1] += p.y;
+                } else {
 #pragma unroll
-                for (int i = 0; i < RPT; i += 4) {
-                    const float4 p = *reinterpret_cast<const float4*>(rp + i);
-                    dh[i] += p.x; dh[i + 1] += p.y; dh[i + 2] += p.z; dh[i + 3] += p.w;
+                    for (int i = 0; i + 3 < RPT; i += 4) {
+                        const float4 p = *reinterpret_cast<const float4*>(rp + i);
+                        dh[i] += p.x; dh[i + 1] += p.y; dh[i + 2] += p.z; dh[i + 3] += p.w;
+                    }
                 }
             }
         }
-        // ---- pointwise BPTT; dgates -> HBM, running sum, bf16 operand in smem
+        // ---- pointwise BPTT; running sum, bf16 operand in smem (HBM store deferred)
+        float gkeep[4][RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             const int bl = warp * RPT + i;
-            const float tc = tanhf(c_t[i]);
+            const float tc = tanhf_fast(c_t[i]);
             const float dc = dcreg[i] + dh[i] * a_o[i] * (1.f - tc * tc);
             dcreg[i] = dc * a_f[i];
             float gq[4];
@@ -352,10 +447,9 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
             gq[1] = dc * c_p[i] * a_f[i] * (1.f - a_f[i]);
             gq[2] = dc * a_i[i] * (1.f - a_g[i] * a_g[i]);
             gq[3] = dh[i] * tc * a_o[i] * (1.f - a_o[i]);
-            float* dg = dgates + ((size_t)t * B + b0 + bl) * H4 + ucol;
 #pragma unroll
             for (int g = 0; g < 4; ++g) {
-                dg[g * CH] = gq[g];
+                gkeep[g][i] = gq[g];
                 gsum[g][i] += gq[g];
                 const int k = g * 32 + lane;
                 const uint32_t off = (uint32_t)(k >> 3) * G_LBO + (uint32_t)bl * 16 + (uint32_t)(k & 7) * 2;
@@ -370,23 +464,24 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
             // ---- partial dh_{t-1}[unit, b] = sum over this CTA's 128 gate columns
             if (tid == 0) {
                 tc_fence_after();
-                const uint32_t whi = smem_u32(w_hi), wlo = smem_u32(w_lo), ghi = smem_u32(g_hi), glo = smem_u32(g_lo);
-#pragma unroll 1
+                const uint64_t dwh0 = make_smem_desc(smem_u32(w_hi), W_LBO, SBO_);
+                const uint64_t dwl0 = make_smem_desc(smem_u32(w_lo), W_LBO, SBO_);
+                const uint64_t dgh0 = make_smem_desc(smem_u32(g_hi), G_LBO, SBO_);
+                const uint64_t dgl0 = make_smem_desc(smem_u32(g_lo), G_LBO, SBO_);
+#pragma unroll
                 for (int hf = 0; hf < 2; ++hf) {
-#pragma unroll 1
+#pragma unroll
                     for (int s = 0; s < NC / 16; ++s) {
-                        const uint32_t wo = hf * S::W_HALF + s * 2 * W_LBO, go = s * 2 * G_LBO;
-                        const uint64_t dwh = make_smem_desc(whi + wo, W_LBO, SBO_);
-                        const uint64_t dgh = make_smem_desc(ghi + go, G_LBO, SBO_);
-                        const uint32_t td = tmem_d + hf * NB;
+                        const uint64_t iw = (uint64_t)((hf * S::W_HALF + s * 2 * W_LBO) >> 4);
+                        const uint64_t ig = (uint64_t)((s * 2 * G_LBO) >> 4);
+                        const uint32_t td = tmem_d + (uint32_t)((hf * NACC + (s % NACC)) * NB);
+                        const uint32_t first = s >= NACC ? 1u : 0u;
                         if (X3) {
-                            const uint64_t dwl = make_smem_desc(wlo + wo, W_LBO, SBO_);
-                            const uint64_t dgl = make_smem_desc(glo + go, G_LBO, SBO_);
-                            umma_bf16(td, dwl, dgh, idesc, s > 0 ? 1u : 0u);
-                            umma_bf16(td, dwh, dgl, idesc, 1u);
-                            umma_bf16(td, dwh, dgh, idesc, 1u);
+                            umma_bf16(td, dwl0 + iw, dgh0 + ig, idesc, first);
+                            umma_bf16(td, dwh0 + iw, dgl0 + ig, idesc, 1u);
+                            umma_bf16(td, dwh0 + iw, dgh0 + ig, idesc, 1u);
                         } else {
-                            umma_bf16(td, dwh, dgh, idesc, s > 0 ? 1u : 0u);
+                            umma_bf16(td, dwh0 + iw, dgh0 + ig, idesc, first);
                         }
                     }
                 }
@@ -394,22 +489,35 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
             }
             mbar_wait(mma_bar, (T - 1 - t) & 1);
             tc_fence_after();
-            // ---- reduce-scatter: TMEM lane = unit; warp q holds units 32q.. (-> CTA q) and 128+32q.. (-> CTA 4+q)
+            // ---- reduce-scatter: TMEM lane = unit; quarter q holds units 32q.. (-> CTA q) and 128+32q.. (-> CTA 4+q)
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
-                float pv[NB];
-                tmem_ld_nb<NB>(tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(hf * NB), pv);
-                const uint32_t dst = hf * 4 + warp;
-                const uint32_t laddr = smem_u32(recv + (rank * UC + lane) * S::RSTRIDE);
+                float pv[CPW];
+                tmem_ld_nb<CPW>(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * NACC * NB + cg * CPW), pv);
+#pragma unroll
+                for (int a = 1; a < NACC; ++a) {
+                    float part[CPW];
+                    tmem_ld_nb<CPW>(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((hf * NACC + a) * NB + cg * CPW), part);
+#pragma unroll
+                    for (int b = 0; b < CPW; ++b) pv[b] += part[b];
+                }
+                const uint32_t dst = hf * 4 + q;
+                const uint32_t laddr = smem_u32(recv + (rank * UC + lane) * S::RSTRIDE + cg * CPW);
                 const uint32_t raddr = map_remote(laddr, dst);
 #pragma unroll
-                for (int i = 0; i < NB; i += 4)
+                for (int i = 0; i < CPW; i += 4)
                     st_remote_v4(raddr + i * 4, make_uint4(__float_as_uint(pv[i]), __float_as_uint(pv[i + 1]),
                                                            __float_as_uint(pv[i + 2]), __float_as_uint(pv[i + 3])));
             }
             tc_fence_before();
         }
         cluster_arrive();
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            float* dg = dgates + ((size_t)t * B + b0 + warp * RPT + i) * H4 + ucol;
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dg[g * CH] = gkeep[g][i];
+        }
     }
     cluster_wait();
     if (dgsum) {
@@ -422,7 +530,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<2 * NB>(tmem_d);
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem_d);
 }
 
 template <int NB, bool X3>
@@ -430,7 +538,7 @@ static int launch_bwd(const float* dh_all, const float* dh_last, const float* W_
                       const float* acts, float* dgates, float* dgsum, int T, int B, cudaStream_t st) {
     using S = BwdSmem<NB, X3>;
     static bool attr = false;
-    auto kern = lstm_bwd_cluster_kernel<NB, X3>;
+    auto kern = lstm_bwd_cluster_kernel<NB, X3, CNT>;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) {
@@ -439,17 +547,9 @@ static int launch_bwd(const float* dh_all, const float* dh_last, const float* W_
         }
         attr = true;
     }
-    kern<<<(B / NB) * CL, 128, S::TOTAL, st>>>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B);
+    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B);
     FHVAE_LAUNCH_CHECK("lstm_bwd_cluster");
     return 0;
-}
-
-int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
-                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
-                     cudaStream_t st) {
-    if (mode == FHVAE_MODE_BF16X3)
-        return launch_bwd<32, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
-    return launch_bwd<32, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
 }
 
 int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
@@ -460,7 +560,7 @@ static int launch_fwd(const float* P, const float* Q, const float* W_hh, float* 
                       float* acts, int T, int B, cudaStream_t st) {
     using S = FwdSmem<NB, X3>;
     static bool attr = false;
-    auto kern = lstm_fwd_cluster_kernel<NB, X3>;
+    auto kern = lstm_fwd_cluster_kernel<NB, X3, CNT>;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
         if (e != cudaSuccess) {
@@ -469,17 +569,71 @@ static int launch_fwd(const float* P, const float* Q, const float* W_hh, float* 
         }
         attr = true;
     }
-    kern<<<(B / NB) * CL, 128, S::TOTAL, st>>>(P, Q, W_hh, h_all, c_all, acts, T, B);
+    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(P, Q, W_hh, h_all, c_all, acts, T, B);
     FHVAE_LAUNCH_CHECK("lstm_fwd_cluster");
     return 0;
 }
 
 bool lstm_cluster_supported(int B, int H) { return H == CH && B % 32 == 0; }
 
+// NB = 16 spreads the batch over twice as many clusters (halves the per-SM pointwise + DSMEM work);
+// worth it only if all B/16 clusters of 8 CTAs are co-resident (16 clusters for B = 256).
+template <int NB, bool X3>
+static int max_clusters_fwd() {
+    using S = FwdSmem<NB, X3>;
+    auto kern = lstm_fwd_cluster_kernel<NB, X3, CNT>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(CL * 32);
+    cfg.blockDim = dim3(CNT);
+    cfg.dynamicSmemBytes = S::TOTAL;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CL; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+static int pick_nb(int B) {
+    static int max16 = -1;
+    if (max16 < 0) {
+        max16 = max_clusters_fwd<16, true>();
+        const char* e = getenv("FHVAE_LSTM_NB");
+        if (getenv("FHVAE_VERBOSE"))
+            fprintf(stderr, "[fhvae] max co-resident clusters of %d CTAs (NB=16, bf16x3 fwd): %d; NB=32: %d\n", CL, max16,
+                    max_clusters_fwd<32, true>());
+        if (e && atoi(e) == 32) max16 = 0;
+        if (e && atoi(e) == 16) max16 = 1 << 20;
+    }
+    return (B % 16 == 0 && B / 16 <= max16) ? 16 : 32;
+}
+
 int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
                      float* acts, int T, int B, int H, int mode, cudaStream_t st) {
-    if (mode == FHVAE_MODE_BF16X3) return launch_fwd<32, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
-    return launch_fwd<32, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
+    const bool x3 = (mode == FHVAE_MODE_BF16X3);
+    if (pick_nb(B) == 16)
+        return x3 ? launch_fwd<16, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st)
+                  : launch_fwd<16, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
+    return x3 ? launch_fwd<32, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st)
+              : launch_fwd<32, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
 }
+
+int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
+                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
+                     cudaStream_t st) {
+    const bool x3 = (mode == FHVAE_MODE_BF16X3);
+    if (pick_nb(B) == 16)
+        return x3 ? launch_bwd<16, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st)
+                  : launch_bwd<16, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
+    return x3 ? launch_bwd<32, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st)
+              : launch_bwd<32, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
+}
+
+#ifdef FHVAE_TIMELINE
+extern "C" int fhvae_debug_timeline(long long* out) {
+    return (int)cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+}
+#endif
 
 }  // namespace fhvae

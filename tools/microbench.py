@@ -13,14 +13,25 @@ dev = "cuda"
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 
-def timeit(f, reps=10):
+COLD = bool(int(os.environ.get("COLD", "0")))
+
+
+def timeit(f, reps=5, inner=20):
+    """Median device time of one call: `inner` back-to-back launches are captured in a CUDA graph so
+    that host launch latency (ctypes + cudaLaunch, ~10-20 us) is not what gets measured."""
     f(); torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(inner):
+            f()
+    g.replay(); torch.cuda.synchronize()
     ts = []
     for _ in range(reps):
-        flush.zero_()
+        if COLD:
+            flush.zero_()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(); f(); e.record(); torch.cuda.synchronize()
-        ts.append(s.elapsed_time(e))
+        s.record(); g.replay(); e.record(); torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e) / inner)
     ts.sort()
     return ts[len(ts) // 2] * 1e3   # us
 
