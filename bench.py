@@ -183,8 +183,9 @@ def main():
     xh, idh, nsh = x.pin_memory(), idx.pin_memory(), nsegs.pin_memory()
     allreduce = None
     if world > 1:
-        def allreduce(g):
-            dist.all_reduce(g)                     # sum; FusedAdam applies grad_scale = 1/world
+        from pytorch_scalablefhvae_b200.parallel import DataParallel
+        dp = DataParallel(m, opt)                  # broadcasts rank 0's parameters, grad_scale = 1/world
+        allreduce = dp.allreduce_                  # ONE NCCL all-reduce of the flat gradient buffer per step
 
     def barrier():
         if world > 1:
@@ -227,7 +228,7 @@ def main():
         if allreduce is not None:
             allreduce(m.packed_grads())
         opt.step()
-        return float(lss)                                                  # D2H (train_model.py:453)
+        return float(lss.detach())                                         # D2H (train_model.py:453)
 
     for _ in range(args.warmup):
         e2e_step()

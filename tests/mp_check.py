@@ -1,0 +1,56 @@
+"""Run under torchrun on N GPUs: N-rank data-parallel training must equal single-GPU training on the
+concatenated batch (same parameters after two Adam steps).  Exit code 0 = pass."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import torch
+import torch.distributed as dist
+
+import pytorch_scalablefhvae_b200 as P
+from pytorch_scalablefhvae_b200.parallel import DataParallel
+from util import synth_batch
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    Bl, T, F, N, H, Z = 64, 20, 80, 200, 256, 32
+    mode = P.MODE_BF16X3
+    args = (T * F, [H, H], [H, H], Z, Z, [H, H])
+    torch.manual_seed(0)
+    m = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode).to(dev)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    dp = DataParallel(m, opt)
+    torch.manual_seed(0)
+    ref = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode).to(dev)
+    ropt = P.FusedAdam(ref.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    worst = 0.0
+    for step in range(2):
+        x, idx, nsegs = synth_batch(Bl * world, T, F, N, seed=50 + step)
+        g = torch.Generator().manual_seed(step)
+        eps = {"z1": torch.randn(Bl * world, Z, generator=g), "z2": torch.randn(Bl * world, Z, generator=g)}
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        l_dp = dp.train_step(x[sl].to(dev), idx[sl], nsegs[sl], 10.0, eps={k: v[sl] for k, v in eps.items()})
+        l_ref = ref.train_step(x.to(dev), idx, nsegs, ropt, 10.0, eps=eps)
+        worst = max(worst, abs(float(dp.global_mean(l_dp)) - float(l_ref)) / abs(float(l_ref)))
+    for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
+        d = float((p - q).abs().max())
+        assert d <= 2 * 2 * 1e-3, (k, d)                                       # bounded (Adam sign-like at |g|~0)
+        frac = float(((p - q).abs() <= 1e-4 * float(q.abs().max())).float().mean())
+        assert frac >= 0.999, (k, frac)
+    assert worst < 1e-4, worst
+    # replicas stay bit-identical across ranks
+    flat = m._flat.clone()
+    dist.broadcast(flat, src=0)
+    assert torch.equal(flat, m._flat)
+    if rank == 0:
+        print(f"mp_check ok: world {world}, loss rel err {worst:.2e}")
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -235,3 +235,17 @@ def test_fullsize_properties_c1():
         assert_close(v, u[perm.to(DEV)], 1e-6, "perm " + n)
     lb, _, px, k1, k2, pm = a
     assert_close(lb, px + k1 + k2 + pm / nsegs.to(DEV), 1e-6, "lb = sum of terms")
+
+
+def test_multi_gpu_data_parallel_equals_single_gpu():
+    """N-rank DP (NCCL all-reduce of the flat gradient buffer) == 1-GPU step on the concatenated batch."""
+    import subprocess, sys
+    n = torch.cuda.device_count()
+    if n < 2:
+        pytest.skip("needs >= 2 GPUs (gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={min(n, 2)}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29611", os.path.join(root, "tests", "mp_check.py")],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "mp_check ok" in r.stdout
