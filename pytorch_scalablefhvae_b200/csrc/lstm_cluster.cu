@@ -25,7 +25,6 @@ constexpr int CH = 256;            // hidden size served by the cluster kernels
 constexpr int CL = 8;              // CTAs per cluster
 constexpr int UC = CH / CL;        // 32 units per CTA
 constexpr int NC = 4 * UC;         // 128 gate columns per CTA
-constexpr int KCH = CH / 8;        // 32 sixteen-byte K chunks
 constexpr int CNT = 512;           // threads per CTA: 4 TMEM lane quarters x 4 column groups
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -52,7 +51,7 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 
 // Development aid (tools/timeline.py builds with -DFHVAE_TIMELINE): SM-clock stamps of CTA 0 / thread 0.
 #ifdef FHVAE_TIMELINE
-__device__ long long g_timeline[2][32][12];
+__device__ long long g_timeline[2][32][16];
 #define TL(k, step, slot) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (step) < 32) g_timeline[k][step][slot] = clock64(); } while (0)
 #else
 #define TL(k, step, slot) do { } while (0)
@@ -102,8 +101,7 @@ __device__ __forceinline__ void tmem_ld_nb<8>(uint32_t taddr, float (&v)[8]) {
 // shared-memory map of the forward kernel (bytes)
 template <int NB, bool X3>
 struct FwdSmem {
-    static constexpr int W_PART = NC * CH * 2;                 // 64 KB per bf16 part
-    static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
+    static constexpr int W_PART = 0, W_BYTES = 0;              // W_hh slice lives in TMEM (A operand)
     static constexpr int H_PART = NB * CH * 2;                 // NB x 256 bf16
     static constexpr int H_BUF = (X3 ? 2 : 1) * H_PART;        // hi [lo]
     static constexpr int H_OFF = W_BYTES;
@@ -122,10 +120,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
     constexpr int NCG = NT / 128;              // column groups: warps sharing one TMEM lane quarter
     constexpr int CPW = NB / NCG;              // batch rows (TMEM columns) per thread in the gate phase
     constexpr int RPT = NB * 32 / NT;          // batch rows per thread in the cell phase
-    constexpr int WIT = NC * KCH / NT;         // resident-W items per thread
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint8_t* w_hi = smem;
-    uint8_t* w_lo = smem + S::W_PART;
     float (*gates)[NB][UC + 1] = reinterpret_cast<float (*)[NB][UC + 1]>(smem + S::G_OFF);
     uint64_t* mma_bar = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mma_bar + 1);
@@ -136,37 +131,44 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
     const int b0 = (blockIdx.x / CL) * NB;
     constexpr int H4 = 4 * CH;
 
-    // ---- prologue: TMEM, barrier, resident W slice (row n = gate*32 + unit  <->  W_hh row gate*H + 32*rank + unit)
-    constexpr int NACC = 4;                    // independent TMEM accumulators (k-steps round-robin)
-    constexpr int TCOLS = NACC * NB < 32 ? 32 : NACC * NB;
+    // ---- prologue: TMEM, barrier, resident W slice as the TMEM A operand:
+    //      lane n = gate*32 + unit  <->  W_hh row gate*H + 32*rank + unit;  column k/2 holds (k, k+1) as bf16
+    constexpr int NACC = 2;                    // independent TMEM accumulators (k-steps round-robin)
+    constexpr int WCOLS = CH / 2;              // 128 columns per bf16 part
+    constexpr int ACOL = (X3 ? 2 : 1) * WCOLS; // accumulators start after the W part(s)
+    constexpr int TCOLS = (ACOL + NACC * NB) <= 256 ? 256 : 512;
     if (warp == 0) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) { mbar_init(mma_bar, 1); fence_mbar_init(); }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
     {
-        float4 wa[WIT], wb[WIT];
+        // thread (q, lane) owns TMEM lane 32q+lane = W row; column group cg covers k in [64cg, 64cg+64)
+        static_assert(NT == 512, "W staging assumes 4 column groups");
+        const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+        float4 wv[16];
 #pragma unroll
-        for (int i = 0; i < WIT; ++i) {        // all loads in flight first
-            const int item = tid + i * NT;
-            const int n = item & (NC - 1), kc = item >> 7;
-            const float* src = W_hh + (size_t)((n >> 5) * CH + rank * UC + (n & 31)) * CH + kc * 8;
-            wa[i] = __ldg(reinterpret_cast<const float4*>(src));
-            wb[i] = __ldg(reinterpret_cast<const float4*>(src) + 1);
-        }
+        for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
 #pragma unroll
-        for (int i = 0; i < WIT; ++i) {
-            const int item = tid + i * NT;
-            const int n = item & (NC - 1), kc = item >> 7;
-            const float v[8] = {wa[i].x, wa[i].y, wa[i].z, wa[i].w, wb[i].x, wb[i].y, wb[i].z, wb[i].w};
-            const uint32_t off = (uint32_t)(kc * NC + n) * 16;
-            if (X3) {
-                uint4 hi, lo;
-                split_bf16(v, hi, lo);
-                *reinterpret_cast<uint4*>(w_hi + off) = hi;
-                *reinterpret_cast<uint4*>(w_lo + off) = lo;
-            } else {
-                *reinterpret_cast<uint4*>(w_hi + off) = make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]),
-                                                                   pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+        for (int hf = 0; hf < 2; ++hf) {       // two 16-column halves keep the register footprint small
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float4 w4 = wv[hf * 8 + i];
+                const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    const __nv_bfloat16 a = __float2bfloat16_rn(v[2 * j]), b = __float2bfloat16_rn(v[2 * j + 1]);
+                    hi[2 * i + j] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+                    lo[2 * i + j] = pack_bf16(v[2 * j] - __bfloat162float(a), v[2 * j + 1] - __bfloat162float(b));
+                }
             }
+            tmem_st16(ta + hf * 16, hi);
+            if (X3) tmem_st16(ta + WCOLS + hf * 16, lo);
         }
+        tmem_wait_st();
     }
     // time-invariant addend for this thread's (gate q, unit lane) column, rows cg*CPW ..
     const int col = q * CH + rank * UC + lane;
@@ -177,13 +179,12 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
 #pragma unroll
     for (int i = 0; i < RPT; ++i) creg[i] = 0.f;
 
-    fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem_d = *tmem_slot;
+    const uint32_t tmem_d = tmem_base + ACOL;
     constexpr uint32_t idesc = make_idesc_bf16(NC, NB);
-    constexpr uint32_t W_LBO = NC * 16, H_LBO = NB * 16, SBO_ = 128;
+    constexpr uint32_t H_LBO = NB * 16, SBO_ = 128;
     cluster_arrive();          // pairs with the wait at the top of step 0 (barriers initialised cluster-wide)
 
     for (int t = 0; t < T; ++t) {
@@ -199,25 +200,26 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
         float acc[CPW];
         if (t > 0) {
             if (tid == 0) {
-                fence_proxy_async_all();
+                fence_proxy_async();           // .shared::cta: peers' generic-proxy h stores -> tensor-core reads
                 tc_fence_after();
+                TL(0, t, 12);
                 const uint32_t hb = smem_u32(smem + S::H_OFF + (t & 1) * S::H_BUF);
-                // descriptors differ only in the 16-byte-granular start address: base + constant
-                const uint64_t dwh0 = make_smem_desc(smem_u32(w_hi), W_LBO, SBO_);
-                const uint64_t dwl0 = make_smem_desc(smem_u32(w_lo), W_LBO, SBO_);
+                // B descriptors differ only in the 16-byte-granular start address: base + constant;
+                // A (W_hh slice) comes from TMEM: 8 columns per K=16 step
                 const uint64_t dhh0 = make_smem_desc(hb, H_LBO, SBO_);
                 const uint64_t dhl0 = make_smem_desc(hb + S::H_PART, H_LBO, SBO_);
 #pragma unroll
                 for (int s = 0; s < CH / 16; ++s) {
-                    const uint64_t iw = (uint64_t)((s * 2 * W_LBO) >> 4), ih = (uint64_t)((s * 2 * H_LBO) >> 4);
+                    const uint64_t ih = (uint64_t)((s * 2 * H_LBO) >> 4);
+                    const uint32_t awh = tmem_base + (uint32_t)(s * 8), awl = awh + WCOLS;
                     const uint32_t td = tmem_d + (uint32_t)((s % NACC) * NB);
                     const uint32_t first = s >= NACC ? 1u : 0u;
                     if (X3) {
-                        umma_bf16(td, dwl0 + iw, dhh0 + ih, idesc, first);
-                        umma_bf16(td, dwh0 + iw, dhl0 + ih, idesc, 1u);
-                        umma_bf16(td, dwh0 + iw, dhh0 + ih, idesc, 1u);
+                        umma_bf16_ts(td, awl, dhh0 + ih, idesc, first);
+                        umma_bf16_ts(td, awh, dhl0 + ih, idesc, 1u);
+                        umma_bf16_ts(td, awh, dhh0 + ih, idesc, 1u);
                     } else {
-                        umma_bf16(td, dwh0 + iw, dhh0 + ih, idesc, first);
+                        umma_bf16_ts(td, awh, dhh0 + ih, idesc, first);
                     }
                 }
                 umma_commit(mma_bar);
@@ -308,7 +310,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
     cluster_wait();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<TCOLS>(tmem_d);
+    if (warp == 0) tmem_dealloc<TCOLS>(tmem_base);
 }
 
 // ================================================================================================

@@ -20,10 +20,10 @@ for mode in (1, 2):
         lib.fhvae_lstm_fwd(ctypes.c_void_p(ptr(P)), ctypes.c_void_p(ptr(Q)), ctypes.c_void_p(ptr(W)), ctypes.c_void_p(ptr(h)),
                            ctypes.c_void_p(ptr(c)), ctypes.c_void_p(ptr(a)), T, B, H, mode, None)
     torch.cuda.synchronize()
-    buf = (ctypes.c_longlong * (2 * 32 * 12))()
+    buf = (ctypes.c_longlong * (2 * 32 * 16))()
     lib.fhvae_debug_timeline(buf)
-    tl = [[buf[(0 * 32 + t) * 12 + k] for k in range(12)] for t in range(T)]
+    tl = [[buf[(0 * 32 + t) * 16 + k] for k in range(16)] for t in range(T)]
     print(f"mode {mode}: cycles per phase (steps 5..9), step period:")
     for t in range(5, 10):
         d = [tl[t][k] - tl[t][k - 1] for k in range(1, 12)]
-        print(t, dict(zip(names[1:], d)), "period", tl[t][0] - tl[t - 1][0])
+        print(t, dict(zip(names[1:], d)), "fence", tl[t][12] - tl[t][1], "period", tl[t][0] - tl[t - 1][0])
