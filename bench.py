@@ -296,7 +296,7 @@ def dominant_kernel_roofline(m, P, xd, idd, nsd, opt, args):
 
     def timed_run(cl):
         evs = []
-        for f, name, a in cl.calls:
+        for f, name, a, _side in cl.calls:
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record()
             if f is None:

@@ -365,14 +365,16 @@ class _Plan:
         return g
 
     def _capture_inner(self, f):
-        # warm up on a side stream (lazy module loading must not happen inside capture), then capture
-        s = torch.cuda.Stream()
+        # warm up on a side stream (lazy module loading must not happen inside capture), then capture.
+        # The capture stream has HIGH priority: the critical-path kernels (cluster recurrence) then win
+        # the SMs over the weight-gradient GEMMs that CallList forks onto its default-priority stream.
+        s = torch.cuda.Stream(priority=-1)
         s.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(s):
             f()
         torch.cuda.current_stream().wait_stream(s)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        with torch.cuda.graph(g, stream=s):
             f()
         return g
 
@@ -552,8 +554,14 @@ class _FHVAEPlan(_Plan):
             self.dzcat = f(B, Z1 + Z2)
             self.dh_rec, self.dc = f(2, B, Hmax), f(B, Hmax)
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
-        wg: List = []          # deferred weight-gradient GEMMs (one grouped launch at the end)
-        cs: List = []          # deferred bias column sums
+        cs: List = []          # bias column sums (one grouped side launch at the end)
+
+        class _Side(list):     # weight-gradient GEMMs: flushed to the side stream right behind their inputs
+            def flush(self_):
+                if self_:
+                    c.gemm(list(self_), mode, side=True)
+                    self_.clear()
+        wg = _Side()
 
         def stack_bwd(k, dh_all_top, dh_last_of):
             """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum."""
@@ -577,6 +585,7 @@ class _FHVAEPlan(_Plan):
                     nxt = self.dhA if dh_all != ptr(self.dhA) else self.dhB
                     c.gemm([gemm_nn(ptr(self.dg[k, l]), 4 * H, m.poff(wih), H, ptr(nxt), H, TB, H, 4 * H)], mode)
                     dh_all = ptr(nxt)
+                wg.flush()
 
         def head_bwd(k, dhead, Z, wname, bname):
             """dW/db of a Gaussian head on the final hidden states + the dh_last they receive."""
@@ -632,9 +641,9 @@ class _FHVAEPlan(_Plan):
         stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]))
         wih_z2 = _lstm_names(pre["z2"], 0)[0]
         wg.append(gemm_tn(ptr(self.dg["z2", 0]), 4 * Hz2, ptr(self.x_tm), F, g(wih_z2), F, 4 * Hz2, F, TB))
-        # ---------------- deferred weight / bias gradients
-        c.gemm(wg, mode)
-        c.colsum(cs)
+        # ---------------- remaining weight gradients + bias gradients (side stream, joined by run())
+        wg.flush()
+        c.colsum(cs, side=True)
         return c
 
 

@@ -34,40 +34,70 @@ def gemm_tn(G, ldg, X, ldx, Cp, ldc, M, N, K, beta=0.0) -> GemmProblem:
     return GemmProblem(G, X, Cp, None, M, N, K, 0, 1, ldg, ldx, 1, ldc, beta, 0)
 
 
+_SIDE_STREAMS = {}
+
+
+def _side_stream(device) -> "torch.cuda.Stream":
+    key = torch.cuda.current_device() if device is None else device
+    if key not in _SIDE_STREAMS:
+        _SIDE_STREAMS[key] = torch.cuda.Stream()
+    return _SIDE_STREAMS[key]
+
+
 class CallList:
+    """Ordered kernel launches.  Calls tagged ``side=True`` are off the critical path (weight / bias
+    gradients): they are forked onto a second stream behind an event recorded at their position in the
+    main sequence and joined back at the end, so they fill the SMs the 64-CTA cluster recurrence leaves
+    idle.  Works identically eagerly and under CUDA-graph capture (fork/join become graph branches)."""
+
     def __init__(self):
-        self.calls = []      # (cfunc, name, args)
+        self.calls = []      # (cfunc, name, args, side)
         self.keep = []       # ctypes arrays / tensors that must outlive the list
 
-    def add(self, name: str, *args):
-        self.calls.append((_lib.fn(name), name, args))
+    def add(self, name: str, *args, side: bool = False):
+        self.calls.append((_lib.fn(name), name, args, side))
 
-    def gemm(self, problems: List[GemmProblem], mode: int):
+    def gemm(self, problems: List[GemmProblem], mode: int, side: bool = False):
         for i in range(0, len(problems), _lib.GEMM_MAX_BATCH):
             chunk = problems[i:i + _lib.GEMM_MAX_BATCH]
             arr = (GemmProblem * len(chunk))(*chunk)
             self.keep.append(arr)
-            self.add("fhvae_gemm_batch", arr, len(chunk), mode)
+            self.add("fhvae_gemm_batch", arr, len(chunk), mode, side=side)
 
-    def colsum(self, problems: List[ColsumProblem]):
+    def colsum(self, problems: List[ColsumProblem], side: bool = False):
         for i in range(0, len(problems), _lib.COLSUM_MAX_BATCH):
             chunk = problems[i:i + _lib.COLSUM_MAX_BATCH]
             arr = (ColsumProblem * len(chunk))(*chunk)
             self.keep.append(arr)
-            self.add("fhvae_colsum_batch", arr, len(chunk))
+            self.add("fhvae_colsum_batch", arr, len(chunk), side=side)
 
     def torch_op(self, f):
         """A host callable (tiny torch ops on static buffers; still graph-capturable)."""
-        self.calls.append((None, "torch", f))
+        self.calls.append((None, "torch", f, False))
 
-    def run(self, stream: int):
-        for f, name, args in self.calls:
+    def run(self, stream: int = 0, overlap: bool = True):
+        main = torch.cuda.current_stream()
+        mptr = main.cuda_stream
+        side = None
+        for f, name, args, on_side in self.calls:
             if f is None:
                 args()
                 continue
-            st = f(*args, stream)
+            if on_side and overlap:
+                if side is None:
+                    side = _side_stream(None)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                st = f(*args, side.cuda_stream)
+            else:
+                st = f(*args, mptr)
             if st:
                 _lib.check(st, name)
+        if side is not None:
+            ev = torch.cuda.Event()
+            ev.record(side)
+            main.wait_event(ev)
 
     def __len__(self):
         return len(self.calls)
