@@ -9,10 +9,13 @@
 //                      => ~1e-5 relative, the "fp32" tolerance of the north star, at 1/3 of the bf16 rate.
 // Shared-memory tiles use the canonical K-major no-swizzle UMMA layout (8x16B core matrices): element
 // (r,k) of a 128 x 64 tile at byte (k/8)*2048 + r*16 + (k%8)*2, i.e. LBO = 2048, SBO = 128.
-// 128x128 output tile per CTA, K stepped in blocks of BK (64 bf16 / 32 bf16x3: 64 KB of smem either way,
-// two CTAs per SM) through a 2-stage ring: all 256 threads stage (global fp32 -> registers, prefetched one
-// block ahead -> bf16 hi/lo -> st.shared, fence.proxy.async), one thread issues the MMAs, tcgen05.commit
-// on an mbarrier releases the stage.  Long-K problems (weight gradients: K = T*B) are split along K
+// 128x128 output tile per CTA, K stepped in blocks of BK (64 bf16 / 32 bf16x3 = 32 KB per stage) through a
+// 3-stage mbarrier ring (96 KB, two CTAs per SM), warp-specialised: 8 producer warps stage the operands
+// (global fp32 -> a register ring that keeps DEPTH K-blocks of loads in flight per thread -> bf16 hi/lo ->
+// st.shared, fence.proxy.async, one arrive per warp on full[s]); a 9th warp's elected lane waits full[s],
+// issues the MMAs and tcgen05.commit's onto empty[s]; no CTA-wide barrier inside the K loop.  The producers
+// then run the epilogue.  (Measured: with one K-block in flight per thread a stage took 2500-5000 cycles =
+// one exposed L2/HBM round trip; tools/gemm_timeline.py.)  Long-K problems (weight gradients: K = T*B) are split along K
 // across CTAs and reduced with fp32 atomics into a pre-zeroed C.
 // Epilogue: tcgen05.ld 32x32b.x32 -> registers -> bias/beta/ReLU -> global.
 #include "common.cuh"
@@ -23,7 +26,9 @@ namespace fhvae {
 using namespace tc;
 
 constexpr int BM = 128, BN = 128;
-constexpr int TCT = 256;                        // threads per CTA
+constexpr int TCT = 256;                        // producer / epilogue threads per CTA
+constexpr int TCT_ALL = TCT + 32;               // + the MMA-issuing warp
+constexpr int NSTAGE = 3;                       // 96 KB: two CTAs per SM (296 slots for the 320-tile projections)
 constexpr uint32_t LBO = BM * 16, SBO = 128;
 template <bool X3>
 struct Cfg {
@@ -32,7 +37,8 @@ struct Cfg {
     static constexpr int OPS = X3 ? 4 : 2;                  // A_hi [A_lo] B_hi [B_lo]
     static constexpr int STAGE_BYTES = OPS * TILE_BYTES;    // 32 KB
     static constexpr int IT = BM * (BK / 8) / TCT;          // (row, k-chunk) items per thread per operand
-    static constexpr int SMEM = 2 * STAGE_BYTES + 64;
+    static constexpr int DEPTH = X3 ? 2 : 1;                // K-blocks of global loads in flight per thread
+    static constexpr int SMEM = NSTAGE * STAGE_BYTES + 128;
 };
 
 struct TcProblem {
@@ -108,13 +114,25 @@ __device__ __forceinline__ void store_tile(const float (&v)[IT][8], uint8_t* s_h
     }
 }
 
+#ifdef FHVAE_TIMELINE
+__device__ long long g_gemm_tl[64];
+#define GTL(slot) do { if (blockIdx.x == 0 && (threadIdx.x == 0)) g_gemm_tl[slot] = clock64(); } while (0)
+#define GTLM(slot) do { if (blockIdx.x == 0) g_gemm_tl[slot] = clock64(); } while (0)
+extern "C" int fhvae_debug_gemm_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_gemm_tl, sizeof(g_gemm_tl)); }
+#else
+#define GTL(slot) do { } while (0)
+#define GTLM(slot) do { } while (0)
+#endif
+
 template <bool X3>
-__global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(const __grid_constant__ TcBatch tb) {
+__global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_constant__ TcBatch tb) {
     extern __shared__ __align__(1024) uint8_t smem[];
     using C = Cfg<X3>;
     constexpr int BK = C::BK, TILE_BYTES = C::TILE_BYTES, STAGE_BYTES = C::STAGE_BYTES, IT = C::IT;
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(smem + 2 * STAGE_BYTES);   // [2]
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NSTAGE * STAGE_BYTES);   // [NSTAGE] producers -> MMA
+    uint64_t* empty = full + NSTAGE;                                             // [NSTAGE] MMA done -> producers
+    uint64_t* accd = empty + NSTAGE;                                             // accumulator complete
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accd + 1);
 
     int pi = 0;
     while (pi + 1 < tb.n && (int)blockIdx.x >= tb.p[pi + 1].tile_start) ++pi;
@@ -123,15 +141,17 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(const __grid_constant__
     const int split = t / P.tiles_mn;
     t -= split * P.tiles_mn;
     const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
-    const int nkb_total = (P.K + Cfg<X3>::BK - 1) / Cfg<X3>::BK;
+    const int nkb_total = (P.K + BK - 1) / BK;
     const int kb0 = split * P.kb_per_split;
     const int kb1 = min(nkb_total, kb0 + P.kb_per_split);
+    const int nit = kb1 - kb0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    GTL(0);
 
-    if (warp == 0) tmem_alloc<BN>(tmem_slot);
-    if (tid == 32) {
-        mbar_init(&mbar[0], 1);
-        mbar_init(&mbar[1], 1);
+    if (warp == TCT / 32) tmem_alloc<BN>(tmem_slot);
+    if (tid == 0) {
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(&full[i], TCT / 32); mbar_init(&empty[i], 1); }
+        mbar_init(accd, 1);
         fence_mbar_init();
     }
     tc_fence_before();
@@ -139,97 +159,127 @@ __global__ void __launch_bounds__(TCT, 2) gemm_tc_kernel(const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    GTL(1);
 
-    float va[IT][8], vb[IT][8];
-    if (kb0 < kb1) {
-        load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, kb0 * BK, P.K, va);
-        load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, kb0 * BK, P.K, vb);
-    }
-    for (int kb = kb0; kb < kb1; ++kb) {
-        const int it = kb - kb0, s = it & 1;
-        uint8_t* st = smem + s * STAGE_BYTES;
-        if (it >= 2) mbar_wait(&mbar[s], ((it >> 1) - 1) & 1);     // MMAs that read this stage are done
-        const int k0 = kb * BK;
-        store_tile<X3, IT>(va, st, st + TILE_BYTES);
-        store_tile<X3, IT>(vb, st + (X3 ? 2 : 1) * TILE_BYTES, st + 3 * TILE_BYTES);
-        if (kb + 1 < kb1) {                                        // next block's loads fly during sync + MMA
-            load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0 + BK, P.K, va);
-            load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0 + BK, P.K, vb);
+    if (warp == TCT / 32) {
+        // ================= MMA issuer: one elected lane =================
+        if (lane == 0) {
+            for (int it = 0; it < nit; ++it) {
+                const int s = it % NSTAGE;
+                mbar_wait(&full[s], (it / NSTAGE) & 1);
+                if (it < 12) GTLM(32 + 2 * it);
+                tc_fence_after();
+                const uint32_t a_hi = smem_u32(smem + s * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+                const uint32_t b_hi = a_hi + (X3 ? 2 : 1) * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
+                const int kleft = min(BK, P.K - (kb0 + it) * BK);
+                const int n16 = (kleft + 15) >> 4;
+                for (int j = 0; j < n16; ++j) {
+                    const uint32_t ko = (uint32_t)j * 2 * LBO;
+                    const uint64_t dah = make_smem_desc(a_hi + ko, LBO, SBO), dbh = make_smem_desc(b_hi + ko, LBO, SBO);
+                    const uint32_t acc0 = (it > 0 || j > 0) ? 1u : 0u;
+                    if (X3) {
+                        const uint64_t dal = make_smem_desc(a_lo + ko, LBO, SBO), dbl = make_smem_desc(b_lo + ko, LBO, SBO);
+                        umma_bf16(tmem_d, dal, dbh, idesc, acc0);
+                        umma_bf16(tmem_d, dah, dbl, idesc, 1u);
+                        umma_bf16(tmem_d, dah, dbh, idesc, 1u);
+                    } else {
+                        umma_bf16(tmem_d, dah, dbh, idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);            // stage s reusable once these MMAs have read it
+                if (it < 12) GTLM(33 + 2 * it);
+            }
+            umma_commit(accd);                     // covers every MMA issued above
         }
-        fence_proxy_async();
-        __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            const uint32_t a_hi = smem_u32(st), a_lo = a_hi + TILE_BYTES;
-            const uint32_t b_hi = a_hi + (X3 ? 2 : 1) * TILE_BYTES, b_lo = a_hi + 3 * TILE_BYTES;
-            const int kleft = min(BK, P.K - k0);
-            const int n16 = (kleft + 15) >> 4;
-            for (int j = 0; j < n16; ++j) {
-                const uint32_t ko = (uint32_t)j * 2 * LBO;
-                const uint64_t dah = make_smem_desc(a_hi + ko, LBO, SBO), dbh = make_smem_desc(b_hi + ko, LBO, SBO);
-                const uint32_t acc0 = (it > 0 || j > 0) ? 1u : 0u;
-                if (X3) {
-                    const uint64_t dal = make_smem_desc(a_lo + ko, LBO, SBO), dbl = make_smem_desc(b_lo + ko, LBO, SBO);
-                    umma_bf16(tmem_d, dal, dbh, idesc, acc0);
-                    umma_bf16(tmem_d, dah, dbl, idesc, 1u);
-                    umma_bf16(tmem_d, dah, dbh, idesc, 1u);
-                } else {
-                    umma_bf16(tmem_d, dah, dbh, idesc, acc0);
+        __syncwarp();
+    } else {
+        // ================= producers (8 warps), then epilogue =================
+        constexpr int DEPTH = C::DEPTH;
+        float va[DEPTH][IT][8], vb[DEPTH][IT][8];
+#pragma unroll
+        for (int d = 0; d < DEPTH; ++d)
+            if (d < nit) {
+                load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, (kb0 + d) * BK, P.K, va[d]);
+                load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, (kb0 + d) * BK, P.K, vb[d]);
+            }
+        for (int it0 = 0; it0 < nit; it0 += DEPTH) {
+#pragma unroll
+            for (int d = 0; d < DEPTH; ++d) {
+                const int it = it0 + d;
+                if (it < nit) {
+                    const int s = it % NSTAGE;
+                    uint8_t* st = smem + s * STAGE_BYTES;
+                    if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
+                    store_tile<X3, IT>(va[d], st, st + TILE_BYTES);
+                    store_tile<X3, IT>(vb[d], st + (X3 ? 2 : 1) * TILE_BYTES, st + 3 * TILE_BYTES);
+                    if (it + DEPTH < nit) {        // refill this ring slot: DEPTH K-blocks stay in flight
+                        const int k0 = (kb0 + it + DEPTH) * BK;
+                        load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0, P.K, va[d]);
+                        load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0, P.K, vb[d]);
+                    }
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full[s]);
+                    if (it < 12) GTL(2 + it);
                 }
             }
-            umma_commit(&mbar[s]);
         }
-    }
-    // drain: the last commit covers every MMA issued before it
-    const int nit = kb1 - kb0;
-    if (nit > 0) {
-        const int last = nit - 1;
-        mbar_wait(&mbar[last & 1], (last >> 1) & 1);
-    }
-    tc_fence_after();
+        if (nit > 0) mbar_wait(accd, 0);
+        tc_fence_after();
+        GTL(20);
 
-    // epilogue: warp w reads TMEM lanes 32*(w&3).., columns 64*(w>>2)..+63 (thread = row), transposes each
-    // 32x32 block through shared memory (the operand stages are free now) and writes full 128-byte lines
-    const int q = warp & 3, half = warp >> 2;
-    float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
-    const bool atomic = P.ksplit > 1;
+        // epilogue: warp w owns the 32x32 block (TMEM lanes 32*(w&3).., columns 32*(w>>2)..): thread = row,
+        // transposed through shared memory (the operand stages are free now) into full 128-byte line stores
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-        const int col0 = half * 64 + cc * 32;
-        if (n0 + col0 >= P.N) break;
-        float v[32];
-        if (nit > 0) {
-            tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
-        } else {
+        for (int cb = warp >> 2; cb < BN / 32; cb += TCT / 128) {
+            const int q = warp & 3, col0 = cb * 32;
+            float* tr = reinterpret_cast<float*>(smem) + warp * (32 * 33);
+            const bool atomic = P.ksplit > 1;
+            __syncwarp();
+            if (n0 + col0 < P.N) {
+                float v[32];
+                if (nit > 0) {
+                    tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)col0, v);
+                } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.f;
-        }
-        __syncwarp();
+                    for (int j = 0; j < 32; ++j) v[j] = 0.f;
+                }
 #pragma unroll
-        for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
-        __syncwarp();
-        const int gn = n0 + col0 + lane;                      // lane = column now
-        const bool nok = gn < P.N;
-        const float bv = (nok && P.bias && (!atomic || split == 0)) ? __ldg(P.bias + gn) : 0.f;
-        const int mrow0 = m0 + q * 32;
-        const int rmax = min(32, P.M - mrow0);
-        if (nok) {
-            float* cp = P.C + (long long)mrow0 * P.ldc + gn;
-            if (atomic) {
-                for (int r = 0; r < rmax; ++r) atomicAdd(cp + (long long)r * P.ldc, tr[r * 33 + lane] + bv);
-            } else {
-                for (int r = 0; r < rmax; ++r) {
-                    float x = tr[r * 33 + lane] + bv;
-                    if (P.beta != 0.f) x += P.beta * cp[(long long)r * P.ldc];
-                    if (P.relu) x = fmaxf(x, 0.f);
-                    cp[(long long)r * P.ldc] = x;
+                for (int j = 0; j < 32; ++j) tr[lane * 33 + j] = v[j];
+                __syncwarp();
+                const int gn = n0 + col0 + lane;                  // lane = column now
+                const bool nok = gn < P.N;
+                const float bv = (nok && P.bias && (!atomic || split == 0)) ? __ldg(P.bias + gn) : 0.f;
+                const int mrow0 = m0 + q * 32;
+                const int rmax = min(32, P.M - mrow0);
+                if (nok) {
+                    float* cp = P.C + (long long)mrow0 * P.ldc + gn;
+                    if (atomic) {
+#pragma unroll 8
+                        for (int r = 0; r < rmax; ++r) atomicAdd(cp + (long long)r * P.ldc, tr[r * 33 + lane] + bv);
+                    } else if (P.beta == 0.f) {
+#pragma unroll 8
+                        for (int r = 0; r < rmax; ++r) {
+                            float x = tr[r * 33 + lane] + bv;
+                            if (P.relu) x = fmaxf(x, 0.f);
+                            cp[(long long)r * P.ldc] = x;
+                        }
+                    } else {
+#pragma unroll 8
+                        for (int r = 0; r < rmax; ++r) {
+                            float x = tr[r * 33 + lane] + bv + P.beta * cp[(long long)r * P.ldc];
+                            if (P.relu) x = fmaxf(x, 0.f);
+                            cp[(long long)r * P.ldc] = x;
+                        }
+                    }
                 }
             }
         }
-    }
+    GTL(21);
+    }   // producers / epilogue
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<BN>(tmem_d);
+    if (warp == TCT / 32) tmem_dealloc<BN>(tmem_d);
 }
 
 // zero the C tiles of split-K problems (beta == 0) before the atomics land
@@ -312,8 +362,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         FHVAE_LAUNCH_CHECK("gemm_tc_zero");
     }
     if (total > 0) {
-        if (x3) gemm_tc_kernel<true><<<total, TCT, Cfg<true>::SMEM, st>>>(tb);
-        else    gemm_tc_kernel<false><<<total, TCT, Cfg<false>::SMEM, st>>>(tb);
+        if (x3) gemm_tc_kernel<true><<<total, TCT_ALL, Cfg<true>::SMEM, st>>>(tb);
+        else    gemm_tc_kernel<false><<<total, TCT_ALL, Cfg<false>::SMEM, st>>>(tb);
         FHVAE_LAUNCH_CHECK("gemm_tc");
     }
     if (nsmall > 0) return gemm_batch_simt(small, nsmall, st);

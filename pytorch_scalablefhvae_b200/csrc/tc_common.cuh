@@ -162,22 +162,24 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // ---- fp32 -> bf16 hi/lo split -----------------------------------------------------------------
 // x = hi + lo + e, |e| <= 2^-18 |x|:  hi = bf16(x), lo = bf16(x - hi)
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&h);
+// one cvt.rn.bf16x2.f32 packs two floats (first operand -> upper half)
+__device__ __forceinline__ uint32_t pack_bf16(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
 }
 __device__ __forceinline__ void split_bf16(const float (&v)[8], uint4& hi, uint4& lo) {
-    float r[8];
-    uint32_t h[4];
+    uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 a = __float2bfloat16_rn(v[2 * i]), b = __float2bfloat16_rn(v[2 * i + 1]);
-        r[2 * i] = v[2 * i] - __bfloat162float(a);
-        r[2 * i + 1] = v[2 * i + 1] - __bfloat162float(b);
-        h[i] = (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+        h[i] = pack_bf16(v[2 * i], v[2 * i + 1]);
+        // bf16 -> fp32 is a 16-bit shift: residuals without cvt instructions
+        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xffff0000u);
+        l[i] = pack_bf16(r0, r1);
     }
     hi = make_uint4(h[0], h[1], h[2], h[3]);
-    lo = make_uint4(pack_bf16(r[0], r[1]), pack_bf16(r[2], r[3]), pack_bf16(r[4], r[5]), pack_bf16(r[6], r[7]));
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 }  // namespace tc
