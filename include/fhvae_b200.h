@@ -176,6 +176,11 @@ int fhvae_adam_flat(float* p, const float* g, float* m, float* v, int64_t n,
 /* ---------------------------------------------------------------------------------------------
  * small data-movement helpers
  * ------------------------------------------------------------------------------------------- */
+/* Device-side segment feeder (datasets.py:214-223 + :100-105 without the per-item file open / H2D copy):
+ * feats (R,F) = all utterances packed row-wise in HBM; seg b = rows [start[b], start[b]+T);
+ * out[b,t,f] = (feats[(start[b]+t)*F + f] - mean[f]) * inv_std[f]   (mean / inv_std may be NULL: no MVN). */
+int fhvae_gather_segments(const float* feats, const int64_t* start, const float* mean, const float* inv_std,
+                          float* out, int B, int T, int F, int64_t R, void* stream);
 /* (B,T,F) -> (T,B,F) */
 int fhvae_transpose_bt(const float* src, float* dst, int B, int T, int F, void* stream);
 /* out[c] = sum_r in[r*ld + c]  (r < R); deterministic.  out2 (may be NULL) receives a second copy

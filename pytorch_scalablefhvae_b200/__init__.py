@@ -4,6 +4,10 @@ from . import _lib
 from ._lib import MODE_BF16, MODE_BF16X3, MODE_F32_SIMT, build
 from .model import FHVAE, SimpleFHVAE, loss_function
 from .optim import FusedAdam
+from .inference import extract_posteriors, segment_table
+from .hierarchical import ShardedMu2Table, sample_sequences
+from .checkpoint import load_checkpoint_file, save_checkpoint
 
 __all__ = ["FHVAE", "SimpleFHVAE", "FusedAdam", "loss_function", "build", "MODE_F32_SIMT", "MODE_BF16X3",
-           "MODE_BF16"]
+           "MODE_BF16", "extract_posteriors", "segment_table", "ShardedMu2Table", "sample_sequences",
+           "load_checkpoint_file", "save_checkpoint"]

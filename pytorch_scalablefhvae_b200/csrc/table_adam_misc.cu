@@ -133,6 +133,20 @@ __global__ void transpose_bt_kernel(const float* __restrict__ src, float* __rest
     dst[i] = __ldg(src + ((int64_t)b * T + t) * F + f);
 }
 
+__global__ void gather_segments_kernel(const float* __restrict__ feats, const int64_t* __restrict__ start,
+                                       const float* __restrict__ mean, const float* __restrict__ inv_std,
+                                       float* __restrict__ out, int B, int T, int F, int64_t R) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)B * T * F) return;
+    const int f = (int)(i % F);
+    const int64_t bt = i / F;
+    const int t = (int)(bt % T), b = (int)(bt / T);
+    const int64_t row = start[b] + t;
+    float v = (row >= 0 && row < R) ? __ldg(feats + row * F + f) : 0.f;
+    if (mean) v = (v - __ldg(mean + f)) * __ldg(inv_std + f);
+    out[i] = v;
+}
+
 // 32 columns per CTA, 32 warps stride over rows, fixed-order reduction over warps; grouped launch
 struct ColsumBatch {
     fhvae_colsum_problem p[FHVAE_COLSUM_MAX_BATCH];
@@ -236,6 +250,17 @@ extern "C" int fhvae_adam_flat(float* p, const float* g, float* m, float* v, int
     adam_flat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
                                                             grad_scale, step, done_counter);
     FHVAE_LAUNCH_CHECK("adam_flat");
+    return 0;
+}
+
+extern "C" int fhvae_gather_segments(const float* feats, const int64_t* start, const float* mean,
+                                     const float* inv_std, float* out, int B, int T, int F, int64_t R,
+                                     void* stream) {
+    FHVAE_CHECK_ARG(feats && start && out && B > 0 && T > 0 && F > 0 && R > 0, "gather_segments: bad argument");
+    FHVAE_CHECK_ARG((mean == nullptr) == (inv_std == nullptr), "gather_segments: mean and inv_std go together");
+    gather_segments_kernel<<<cdiv((int64_t)B * T * F, 256), 256, 0, as_stream(stream)>>>(feats, start, mean,
+                                                                                          inv_std, out, B, T, F, R);
+    FHVAE_LAUNCH_CHECK("gather_segments");
     return 0;
 }
 

@@ -63,6 +63,11 @@ class _FHVAECore(nn.Module):
             self._shape[name] = tuple(shape)
             off += (_prod(shape) + 3) // 4 * 4          # 16-byte aligned slots
         self._n_flat = off
+        # registration order = the reference's construction order (the insertion order of `init`), so that
+        # named_parameters() / optimizer.state_dict() indices line up with the reference's modules; the
+        # flat-buffer LAYOUT (specs order) is independent of it
+        order = {n: i for i, n in enumerate(init.keys())}
+        specs = sorted(specs, key=lambda ns: order[ns[0]])
         self._names = [n for n, _ in specs]
         flat = torch.zeros(off, dtype=torch.float32)
         self._plist: List[nn.Parameter] = []
@@ -203,6 +208,25 @@ class _FHVAECore(nn.Module):
         plan.load_inputs(x, mu_idx, num_segs, eps)
         return plan.run_train_step(optimizer, float(alpha), allreduce)
 
+    @torch.no_grad()
+    def encode(self, x: torch.Tensor, eps=None):
+        """Forward-only posterior extraction (what eval_model.py:55-59 leaves as TODO): runs only the two
+        encoders.  With ``eps=None`` the z2 *mean* conditions the z1 encoder (eps = 0).  Returns views of
+        the plan's buffers: dict(z1_mu, z1_logvar, z2_mu, z2_logvar), valid until the next call."""
+        if not x.is_cuda:
+            raise RuntimeError("pytorch_scalablefhvae_b200 has no CPU path")
+        B, T, F = x.shape
+        plan = self._plan(B, T, F)
+        plan.x.copy_(x, non_blocking=True)
+        if eps is None:
+            plan.eps1.zero_(); plan.eps2.zero_()
+        else:
+            plan.eps1.copy_(eps["z1"].reshape(plan.eps1.shape)); plan.eps2.copy_(eps["z2"].reshape(plan.eps2.shape))
+        plan.run_encode()
+        Z1, Z2 = self.z1_dim, self.z2_dim
+        return {"z1_mu": plan.z1head[:, :Z1], "z1_logvar": plan.z1head[:, Z1:],
+                "z2_mu": plan.z2head[:, :Z2], "z2_logvar": plan.z2head[:, Z2:]}
+
     def _publish(self, plan: "_Plan"):
         """Attributes the reference's callers read (utils.py:52,58)."""
         z1h, z2h = plan.z1head, plan.z2head
@@ -295,6 +319,21 @@ class _Plan:
             self._graph_fwd.replay()
         else:
             self.fwd.run(current_stream_ptr())
+
+    def run_encode(self):
+        """Replay only the encoder prefix of the forward list (marked by ``n_encode_calls``)."""
+        enc = self.__dict__.get("_enc")
+        if enc is None:
+            enc = CallList()
+            enc.calls = self.fwd.calls[:self.n_encode_calls]
+            enc.keep = self.fwd.keep
+            self._enc = enc
+        if self.m.use_cuda_graphs:
+            if self.__dict__.get("_graph_enc") is None:
+                self._graph_enc = self._capture(lambda: enc.run(current_stream_ptr()))
+            self._graph_enc.replay()
+        else:
+            enc.run(current_stream_ptr())
 
     def run_backward(self, gout, k: int) -> torch.Tensor:
         gflat = self.m._grad_buffer(k)
@@ -524,6 +563,7 @@ class _FHVAEPlan(_Plan):
         self._head_fwd(c, final_h("z1"), "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias",
                        self.z1head, Z1)
         c.add("fhvae_reparam_fwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.zcat), Z1 + Z2, B, Z1)
+        self.n_encode_calls = len(c.calls)
         # decoder: the whole layer-0 input is time-invariant
         wih_d, _, _, _ = _lstm_names(pre["dec"], 0)
         c.gemm([gemm_nt(ptr(self.zcat), Z1 + Z2, m.poff(wih_d), Z1 + Z2, ptr(self.Q["dec"]), 4 * Hd, B,
@@ -690,6 +730,7 @@ class _SimplePlan(_Plan):
         self._head_fwd(c, [(ptr(self.a["z1", 1]), h1, h1)], "z1_gauss_layer.mulayer.weight",
                        "z1_gauss_layer.mulayer.bias", self.z1head, Z1)
         c.add("fhvae_reparam_fwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.zcat), Z1 + Z2, B, Z1)
+        self.n_encode_calls = len(c.calls)
         h0, h1 = m.x_hus
         c.gemm([gemm_nt(ptr(self.zcat), Z1 + Z2, w("pre_decoder.fc1"), Z1 + Z2, ptr(self.a["dec", 0]), h0, B,
                         h0, Z1 + Z2, bias=bia("pre_decoder.fc1"), relu=1)], mode)

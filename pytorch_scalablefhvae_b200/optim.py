@@ -68,6 +68,42 @@ class FusedAdam(torch.optim.Optimizer):
                                         current_stream_ptr())
         _lib.check(rc, "fhvae_adam_flat")
 
+    # ---- torch.optim.Adam-compatible state (utils.py:142 saves optimizer.state_dict())
+    def state_dict(self):
+        state, idx = {}, 0
+        groups = []
+        for g in self.param_groups:
+            ids = []
+            for p in g["params"]:
+                mod, name = p._fhvae[0](), p._fhvae[1]
+                st = self._flat_state.get(id(mod))
+                if st is not None:
+                    o, n = mod._off[name], p.numel()
+                    state[idx] = {"step": st["step"].float().cpu().reshape(()),
+                                  "exp_avg": st["m"][o:o + n].view_as(p).clone(),
+                                  "exp_avg_sq": st["v"][o:o + n].view_as(p).clone()}
+                ids.append(idx)
+                idx += 1
+            groups.append({**{k: v for k, v in g.items() if k != "params"}, "params": ids})
+        return {"state": state, "param_groups": groups}
+
+    def load_state_dict(self, sd):
+        idx = 0
+        for g, sg in zip(self.param_groups, sd["param_groups"]):
+            for k, v in sg.items():
+                if k != "params":
+                    g[k] = v
+            for p in g["params"]:
+                mod, name = p._fhvae[0](), p._fhvae[1]
+                st = self._state_for(mod)
+                ps = sd["state"].get(idx)
+                if ps is not None:
+                    o, n = mod._off[name], p.numel()
+                    st["m"][o:o + n].view_as(p).copy_(ps["exp_avg"])
+                    st["v"][o:o + n].view_as(p).copy_(ps["exp_avg_sq"])
+                    st["step"].fill_(int(ps["step"]))
+                idx += 1
+
     def steps_taken(self, mod=None) -> int:
         mod = mod or self._modules[0]
         return int(self._state_for(mod)["step"].item())

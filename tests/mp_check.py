@@ -47,6 +47,22 @@ def main():
     flat = m._flat.clone()
     dist.broadcast(flat, src=0)
     assert torch.equal(flat, m._flat)
+    # ---- sharded master table: rows routed to / fetched from their owner (utt mod world), exact
+    from pytorch_scalablefhvae_b200.parallel import shard_rows
+    Nm, K = 1003, 64
+    table = P.ShardedMu2Table(Nm, Z, dev, seed=3)
+    full = torch.zeros(Nm, Z)
+    for r in range(world):                       # what every rank's shard holds, regenerated from the seeds
+        g = torch.Generator().manual_seed(3 + r)
+        full[r::world] = torch.randn(max(shard_rows(Nm, r, world), 1), Z, generator=g)[:shard_rows(Nm, r, world)]
+    utts = torch.from_numpy(__import__("numpy").random.RandomState(11).permutation(Nm)[:K].astype("int64"))
+    cache = table.fetch(utts)
+    assert torch.equal(cache.cpu(), full[utts]), "fetch must return the owners' rows exactly"
+    table.write_back(utts, cache * 2.0)
+    again = table.fetch(utts)
+    assert torch.equal(again.cpu(), full[utts] * 2.0)
+    other = torch.tensor([u for u in range(Nm) if u not in set(utts.tolist())][:50])
+    assert torch.equal(table.fetch(other).cpu(), full[other]), "rows outside the sample stay untouched"
     if rank == 0:
         print(f"mp_check ok: world {world}, loss rel err {worst:.2e}")
     dist.destroy_process_group()

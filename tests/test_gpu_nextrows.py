@@ -1,0 +1,150 @@
+"""GPU: the rows either side of the hot path: posterior extraction over whole utterances
+(config 4), hierarchical-sampling table (config 3), checkpoint interop."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_scalablefhvae_b200 as P
+from oracle import fhvae_oracle as O
+from util import FP32_RTOL, assert_close
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def _model_pair(N=9, mode=P.MODE_F32_SIMT, H=32, F=8, T=6, Z1=8, Z2=16):
+    torch.manual_seed(0)
+    args = (T * F, [H, H], [H, H], Z1, Z2, [H, H])
+    m = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode)
+    o = O.FHVAEOracle(*args, seg_len=T, num_seqs=N)
+    o.load_state_dict(m.state_dict())
+    return m.to(DEV), o
+
+
+@pytest.mark.parametrize("bs", [7, 64])
+def test_extract_posteriors_matches_oracle(bs):
+    T, F, shift = 6, 8, 2
+    m, o = _model_pair()
+    rng = np.random.default_rng(0)
+    lengths = [int(v) for v in rng.integers(3, 40, size=11)]          # includes utterances shorter than seg_len
+    lengths[3] = 5
+    feats = torch.randn(sum(lengths), F, generator=torch.Generator().manual_seed(1))
+    out = P.extract_posteriors(m, feats.to(DEV), lengths, seg_shift=shift, batch_size=bs)
+    # reference segmenting (datasets.py:176-181) + encoders with eps = 0 + utils.estimate_mu2_dict
+    segs, utt = [], []
+    off = 0
+    for u, l in enumerate(lengths):
+        for s in O.segment_starts(l, T, shift):
+            segs.append(feats[off + s: off + s + T]); utt.append(u)
+        off += l
+    x = torch.stack(segs)
+    utt = torch.tensor(utt)
+    assert torch.equal(out["seg_utt"].cpu(), utt)                       # bit-exact indices
+    assert out["nsegs"].tolist() == [max((l - T) // shift + 1, 0) for l in lengths]
+    zero = {"z1": torch.zeros(len(x), 8), "z2": torch.zeros(len(x), 16)}
+    with torch.no_grad():
+        o(x, torch.zeros(len(x), dtype=torch.long), 9, torch.ones(len(x), dtype=torch.long), eps=zero)
+    assert_close(out["z2_mu"], o.qz2_x[0], FP32_RTOL, "z2_mu")
+    assert_close(out["z1_mu"], o.qz1_x[0], FP32_RTOL, "z1_mu")
+    d = O.estimate_mu2_dict([o.qz2_x[0]], [utt])
+    for u in range(len(lengths)):
+        ref = d[u] if u in d else torch.zeros(16)
+        assert_close(out["mu2"][u], ref, FP32_RTOL, f"mu2[{u}]") if u in d else None
+        if u not in d:
+            assert float(out["mu2"][u].abs().max()) == 0.0
+
+
+def test_gather_segments_mvn_exact():
+    from pytorch_scalablefhvae_b200 import _lib
+    from pytorch_scalablefhvae_b200.plan import ptr
+    R, F, T = 50, 12, 5
+    feats = torch.randn(R, F, device=DEV)
+    start = torch.tensor([0, 45, 7, 7], device=DEV)
+    mean, std = torch.randn(F, device=DEV), torch.rand(F, device=DEV) + 0.5
+    inv = 1.0 / std
+    out = torch.empty(4, T, F, device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(_lib.fn("fhvae_gather_segments")(ptr(feats), ptr(start), None, None, ptr(out), 4, T, F, R, st))
+    ref = torch.stack([feats[s:s + T] for s in start.tolist()])
+    assert torch.equal(out, ref)
+    _lib.check(_lib.fn("fhvae_gather_segments")(ptr(feats), ptr(start), ptr(mean), ptr(inv), ptr(out), 4, T, F, R, st))
+    assert_close(out, (ref - mean) * inv, 1e-6, "mvn")
+
+
+def test_hierarchical_table_roundtrip_and_refresh(golden_dir):
+    h = json.load(open(os.path.join(golden_dir, "hier_sample.json")))
+    seqlist = [f"utt{i:05d}" for i in range(h["n"])]
+    assert P.sample_sequences(seqlist, h["k"], h["seed"]).tolist() == h["sampled"]       # train_model.py:426-428
+    N, K, Z = 1000, 50, 16
+    table = P.ShardedMu2Table(N, Z, DEV, seed=3)
+    master0 = table.shard.clone()
+    utts = torch.from_numpy(np.random.RandomState(5).permutation(N)[:K].astype(np.int64))
+    cache = table.fetch(utts)
+    assert torch.equal(cache, master0[utts.to(DEV)])                                       # exact rows (world 1)
+    new = cache + 1.0
+    table.write_back(utts, new)
+    touched = torch.zeros(N, dtype=torch.bool); touched[utts] = True
+    assert torch.equal(table.shard[touched.to(DEV)], (master0 + 1.0)[touched.to(DEV)])
+    assert torch.equal(table.shard[~touched.to(DEV)], master0[~touched.to(DEV)])          # untouched rows intact
+    # cache refresh with the current encoder == utils.estimate_mu2_dict on the oracle
+    m, o = _model_pair(N=K)
+    g = torch.Generator().manual_seed(7)
+    xs = [torch.randn(20, 6, 8, generator=g) for _ in range(3)]
+    labs = [torch.randint(0, K - 5, (20,), generator=g) for _ in range(3)]
+    before = m.mu2_table.detach().clone()
+    t = table.refresh(m, [x.to(DEV) for x in xs], labs)
+    zero = {"z1": torch.zeros(20, 8), "z2": torch.zeros(20, 16)}
+    z2s = []
+    with torch.no_grad():
+        for x in xs:
+            o(x, torch.zeros(20, dtype=torch.long), K, torch.ones(20, dtype=torch.long), eps=zero)
+            z2s.append(o.qz2_x[0].clone())
+    d = O.estimate_mu2_dict(z2s, labs)
+    for y in range(K):
+        if y in d:
+            assert_close(t[y], d[y], FP32_RTOL, f"mu2[{y}]")
+        else:
+            assert torch.equal(t[y], before[y])                                            # never-seen rows keep their value
+
+
+def test_checkpoint_interop_with_reference_layout(tmp_path):
+    m, o = _model_pair()
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    x = torch.randn(5, 6, 8); idx = torch.tensor([0, 8, 3, 3, 1]); ns = torch.tensor([2, 3, 4, 4, 9])
+    out = m(x.to(DEV), idx, 9, ns); P.loss_function(out[0], out[1]).backward(); opt.step()
+    path = P.save_checkpoint(m, opt, [], {"a": 1}, "run", epoch=3, best_epoch=3, val_lower_bound=-1.0,
+                             best_val_lb=-1.0, checkpoint_dir=str(tmp_path))
+    assert path.name == "fhvae_run_e3.tar" and (tmp_path / "best_model_fhvae_run_e3.tar").exists()
+    ck = torch.load(path, weights_only=False)
+    assert set(ck) >= {"best_val_lb", "best_epoch", "epoch", "model_type", "model_params", "optimizer", "state_dict",
+                       "summary_vals", "values"}                                            # utils.py:126-145
+    assert ck["model_params"] == ([32, 32], [32, 32], 8, 16, [32, 32])
+    m2, values, optim_state, start_epoch, best, summ = P.load_checkpoint_file(path, finetune=False)
+    assert start_epoch == 5 and values == {"a": 1}                                          # utils.py:89-92 (+2)
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a.cpu(), b.cpu()), k
+    # optimizer state is torch.optim.Adam-shaped: it loads into the reference's optimizer and back
+    ref_opt = torch.optim.Adam(o.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    names_m = [n for n, _ in m.named_parameters()]
+    names_o = [n for n, _ in o.named_parameters()]
+    assert names_m == names_o
+    sd = optim_state
+    ref_opt.load_state_dict({"state": {i: {k: (v.cpu() if torch.is_tensor(v) else v) for k, v in st.items()}
+                                       for i, st in sd["state"].items()}, "param_groups": sd["param_groups"]})
+    m2.to(DEV)
+    opt2 = P.FusedAdam(m2.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    opt2.load_state_dict(optim_state)
+    assert opt2.steps_taken() == 1
+    a, b = opt._flat_state[id(m)], opt2._flat_state[id(m2)]
+    assert torch.equal(a["m"], b["m"]) and torch.equal(a["v"], b["v"])
+    # a REFERENCE SimpleFHVAE checkpoint (no table, no input_size) loads too
+    sref = O.SimpleFHVAEOracle(24, [8, 8], [8, 8], 8, 8, [8, 8], num_seqs=4)
+    ref_sd = {k: v for k, v in sref.state_dict().items() if k != "mu2_table"}
+    torch.save({"model_type": "simple_fhvae", "model_params": ([8, 8], [8, 8], 8, 8, [8, 8]), "state_dict": ref_sd,
+                "optimizer": {}, "epoch": 0, "best_val_lb": 0, "summary_vals": [], "values": {}, "best_epoch": 0},
+               tmp_path / "ref.tar")
+    m3 = P.load_checkpoint_file(tmp_path / "ref.tar", finetune=True, input_size=24, num_seqs=4)[0]
+    assert torch.equal(m3.state_dict()["pre_decoder.fc2.linear.weight"], ref_sd["pre_decoder.fc2.linear.weight"])
