@@ -71,14 +71,17 @@ int fhvae_gemm_batch(const fhvae_gemm_problem* problems, int n_problems, int mod
  *   gates_t = P[t] (T,B,4H, may be NULL) + Q (B,4H, time-invariant, may be NULL) + h_{t-1} W_hh^T
  *   (biases are folded into P or Q by the projection GEMM).
  * Saves for BPTT: h_all (T,B,H), c_all (T,B,H), acts (T,B,4H) = post-activation i,f,g,o.
+ * xchg: caller-allocated scratch of 16*B*H floats (contents undefined), the L2-resident exchange buffer of
+ * the cluster kernels (may be NULL in FHVAE_MODE_F32_SIMT).
  * ------------------------------------------------------------------------------------------- */
 int fhvae_lstm_fwd(const float* P, const float* Q, const float* W_hh,
-                   float* h_all, float* c_all, float* acts,
+                   float* h_all, float* c_all, float* acts, float* xchg,
                    int T, int B, int H, int mode, void* stream);
 /* BPTT.  dh_all (T,B,H) = dL/dh_t from the consumer of all outputs (may be NULL);
  * dh_last (B,H) = extra dL/dh_{T-1} from the final-state consumer (may be NULL).
  * Outputs: dgates (T,B,4H) pre-activation gate gradients; dgsum (B,4H) = sum_t dgates (may be NULL).
- * Scratch: dh_rec (2,B,H) and dc (B,H), caller-allocated, contents undefined on entry. */
+ * Scratch: dh_rec (16,B,H) (exchange buffer of the cluster kernel) and dc (B,H), caller-allocated,
+ * contents undefined on entry. */
 int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
                    const float* c_all, const float* acts,
                    float* dgates, float* dgsum, float* dh_rec, float* dc,

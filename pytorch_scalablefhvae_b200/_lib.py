@@ -40,7 +40,7 @@ _p, _i, _l, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 # name -> argtypes (all return int except the two noted below); mirrors include/fhvae_b200.h
 PROTOTYPES = {
     "fhvae_gemm_batch": [C.POINTER(GemmProblem), _i, _i, _p],
-    "fhvae_lstm_fwd": [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "fhvae_lstm_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fhvae_lstm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fhvae_reparam_fwd": [_p, _l, _p, _p, _l, _i, _i, _p],
     "fhvae_reparam_bwd": [_p, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p],

@@ -26,10 +26,10 @@ int lstm_bwd_simt(const float* dh_all, const float* dh_last, const float* W_hh, 
 
 bool lstm_cluster_supported(int B, int H);
 int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
-                     float* acts, int T, int B, int H, int mode, cudaStream_t st);
+                     float* acts, float* xchg, int T, int B, int H, int mode, cudaStream_t st);
 
 int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
-                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
+                     const float* acts, float* dgates, float* dgsum, float* xchg, int T, int B, int H, int mode,
                      cudaStream_t st);
 
 }  // namespace fhvae
@@ -60,11 +60,14 @@ extern "C" int fhvae_gemm_batch(const fhvae_gemm_problem* problems, int n_proble
 }
 
 extern "C" int fhvae_lstm_fwd(const float* P, const float* Q, const float* W_hh, float* h_all,
-                              float* c_all, float* acts, int T, int B, int H, int mode, void* stream) {
+                              float* c_all, float* acts, float* xchg, int T, int B, int H, int mode,
+                              void* stream) {
     FHVAE_CHECK_ARG(W_hh && h_all && c_all && acts && (P || Q), "lstm_fwd: null pointer");
     FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_fwd: need T,B>0 and H %% 8 == 0");
-    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H))
-        return lstm_fwd_cluster(P, Q, W_hh, h_all, c_all, acts, T, B, H, mode, as_stream(stream));
+    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H)) {
+        FHVAE_CHECK_ARG(xchg, "lstm_fwd: the cluster kernel needs the 16*B*H-float exchange scratch");
+        return lstm_fwd_cluster(P, Q, W_hh, h_all, c_all, acts, xchg, T, B, H, mode, as_stream(stream));
+    }
     return lstm_fwd_simt(P, Q, W_hh, h_all, c_all, acts, T, B, H, as_stream(stream));
 }
 
@@ -73,9 +76,11 @@ extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const f
                               float* dh_rec, float* dc, int T, int B, int H, int mode, void* stream) {
     FHVAE_CHECK_ARG(W_hh && c_all && acts && dgates && dc && (dh_all || dh_last), "lstm_bwd: null pointer");
     FHVAE_CHECK_ARG(T > 0 && B > 0 && H > 0 && H % 8 == 0, "lstm_bwd: need T,B>0 and H %% 8 == 0");
-    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H))
-        return lstm_bwd_cluster(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, H, mode,
+    if (mode != FHVAE_MODE_F32_SIMT && lstm_cluster_supported(B, H)) {
+        FHVAE_CHECK_ARG(dh_rec, "lstm_bwd: the cluster kernel needs the 16*B*H-float exchange scratch (dh_rec)");
+        return lstm_bwd_cluster(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dh_rec, T, B, H, mode,
                                 as_stream(stream));
+    }
     return lstm_bwd_simt(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dc, T, B, H,
                          as_stream(stream));
 }

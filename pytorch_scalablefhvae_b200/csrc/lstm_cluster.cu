@@ -115,8 +115,14 @@ template <int NB, bool X3, int NT>
 __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q,
                         const float* __restrict__ W_hh, float* __restrict__ h_all,
-                        float* __restrict__ c_all, float* __restrict__ acts, int T, int B) {
+                        float* __restrict__ c_all, float* __restrict__ acts, float* __restrict__ xchg,
+                        int T, int B) {
     using S = FwdSmem<NB, X3>;
+    constexpr int VEC_PER_PART = 4 * NB;       // 16-byte vectors of one CTA's h slice, per bf16 part
+    constexpr int NVEC = (X3 ? 2 : 1) * VEC_PER_PART;
+    // L2-resident exchange buffer of this cluster: [2 buffers][CL slices][NVEC] uint4 (DSMEM moves only
+    // ~17 B/clk/SM; an all-gather through L2 is ~2x faster)
+    uint4* xg = reinterpret_cast<uint4*>(xchg) + (size_t)(blockIdx.x / CL) * (2 * CL * NVEC);
     constexpr int NCG = NT / 128;              // column groups: warps sharing one TMEM lane quarter
     constexpr int CPW = NB / NCG;              // batch rows (TMEM columns) per thread in the gate phase
     constexpr int RPT = NB * 32 / NT;          // batch rows per thread in the cell phase
@@ -195,12 +201,29 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
         for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
 
         TL(0, t, 0);
-        cluster_wait();        // h_{t-1} slices of all 8 CTAs have landed in hbuf[t&1]
+        cluster_wait();        // every CTA's h_{t-1} slice is visible in the L2 exchange buffer
         TL(0, t, 1);
         float acc[CPW];
         if (t > 0) {
+            {   // pull the 7 peer slices into this CTA's MMA operand buffer (own slice was written locally)
+                uint8_t* hb = smem + S::H_OFF + (t & 1) * S::H_BUF;
+                const uint4* xr = xg + (size_t)((t & 1) * CL) * NVEC;
+                constexpr int PER = CL * NVEC / NT;
+                uint4 val[PER];
+#pragma unroll
+                for (int i = 0; i < PER; ++i) val[i] = __ldcg(xr + tid + i * NT);
+#pragma unroll
+                for (int i = 0; i < PER; ++i) {
+                    const int idx = tid + i * NT, src = idx / NVEC, v = idx % NVEC;
+                    const int part = v / VEC_PER_PART, rem = v % VEC_PER_PART;
+                    const int kcl = rem / NB, row = rem % NB;
+                    if (src != (int)rank)
+                        *reinterpret_cast<uint4*>(hb + part * S::H_PART + (uint32_t)(src * 4 + kcl) * (NB * 16) + row * 16) = val[i];
+                }
+                fence_proxy_async();
+                __syncthreads();
+            }
             if (tid == 0) {
-                fence_proxy_async();           // .shared::cta: peers' generic-proxy h stores -> tensor-core reads
                 tc_fence_after();
                 TL(0, t, 12);
                 const uint32_t hb = smem_u32(smem + S::H_OFF + (t & 1) * S::H_BUF);
@@ -277,20 +300,13 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
         TL(0, t, 7);
         __syncthreads();
         TL(0, t, 8);
-        // broadcast this CTA's slice (4 K-chunks x NB rows x 16 B per part) to the 7 peers
-        if (t + 1 < T) {
-            constexpr int VEC_PER_PART = 4 * NB;
-            constexpr int NVEC = (X3 ? 2 : 1) * VEC_PER_PART;
-            for (int v = tid; v < NVEC; v += NT) {
-                const int part = v / VEC_PER_PART, rem = v % VEC_PER_PART;
-                const int kcl = rem / NB, row = rem % NB;
-                uint8_t* src = hnext + part * S::H_PART + (uint32_t)(rank * 4 + kcl) * H_LBO + row * 16;
-                const uint4 val = *reinterpret_cast<const uint4*>(src);
-                const uint32_t laddr = smem_u32(src);
-#pragma unroll
-                for (uint32_t d = 0; d < CL; ++d)
-                    if (d != rank) st_remote_v4(map_remote(laddr, d), val);
-            }
+        // publish this CTA's slice (4 K-chunks x NB rows x 16 B per part) in the L2 exchange buffer
+        if (t + 1 < T && tid < NVEC) {
+            const int part = tid / VEC_PER_PART, rem = tid % VEC_PER_PART;
+            const int kcl = rem / NB, row = rem % NB;
+            const uint4 val = *reinterpret_cast<const uint4*>(hnext + part * S::H_PART +
+                                                             (uint32_t)(rank * 4 + kcl) * H_LBO + row * 16);
+            xg[(size_t)(((t + 1) & 1) * CL + rank) * NVEC + tid] = val;
         }
         TL(0, t, 9);
         cluster_arrive();
@@ -336,8 +352,10 @@ __global__ void __cluster_dims__(CL, 1, 1) __launch_bounds__(NT, 1)
 lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restrict__ dh_last,
                         const float* __restrict__ W_hh, const float* __restrict__ c_all,
                         const float* __restrict__ acts, float* __restrict__ dgates,
-                        float* __restrict__ dgsum, int T, int B) {
+                        float* __restrict__ dgsum, float* __restrict__ xchg, int T, int B) {
     using S = BwdSmem<NB, X3>;
+    // L2-resident reduce-scatter buffer of this cluster: [2 buffers][dst CTA][src CTA][NB rows][32 units] fp32
+    float* xg = xchg + (size_t)(blockIdx.x / CL) * (2 * CL * CL * NB * UC);
     constexpr int NCG = NT / 128;                              // column groups per TMEM lane quarter
     constexpr int CPW = NB / NCG;                              // TMEM columns per thread in the scatter phase
     constexpr int RPT = NB * 32 / NT;                          // batch rows per thread in the pointwise phase
@@ -417,25 +435,24 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
             if (t == T - 1 && dh_last) d += __ldg(dh_last + (size_t)b * CH + ucol);
             dh[i] = d;
         }
+        TL(1, T - 1 - t, 0);
         cluster_wait();        // the 8 partial dh tiles for this step have landed in recv
+        TL(1, T - 1 - t, 1);
         if (t < T - 1) {
+            // sum the 8 partial tiles of this CTA's 32 units (fixed order: deterministic), coalesced from L2
+            const float* rp = xg + (size_t)((((t + 1) & 1) * CL + rank) * CL) * (NB * UC) + lane;
+            float part[CL][RPT];
 #pragma unroll
-            for (int src = 0; src < CL; ++src) {
-                const float* rp = recv + (src * UC + lane) * S::RSTRIDE + warp * RPT;
-                if (RPT == 1) {
-                    dh[0] += rp[0];
-                } else if (RPT == 2) {
-                    const float2 p = *reinterpret_cast<const float2*>(rp);
-                    dh[0] += p.x; dh[RPT - 1] += p.y;
-                } else {
+            for (int src = 0; src < CL; ++src)
 #pragma unroll
-                    for (int i = 0; i + 3 < RPT; i += 4) {
-                        const float4 p = *reinterpret_cast<const float4*>(rp + i);
-                        dh[i] += p.x; dh[i + 1] += p.y; dh[i + 2] += p.z; dh[i + 3] += p.w;
-                    }
-                }
-            }
+                for (int i = 0; i < RPT; ++i)
+                    part[src][i] = __ldcg(rp + (size_t)src * (NB * UC) + (warp * RPT + i) * UC);
+#pragma unroll
+            for (int src = 0; src < CL; ++src)
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) dh[i] += part[src][i];
         }
+        TL(1, T - 1 - t, 2);
         // ---- pointwise BPTT; running sum, bf16 operand in smem (HBM store deferred)
         float gkeep[4][RPT];
 #pragma unroll
@@ -460,9 +477,11 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
                 if (X3) *reinterpret_cast<__nv_bfloat16*>(g_lo + off) = __float2bfloat16_rn(gq[g] - __bfloat162float(hh));
             }
         }
+        TL(1, T - 1 - t, 3);
         if (t > 0) {
             fence_proxy_async();
             __syncthreads();
+            TL(1, T - 1 - t, 4);
             // ---- partial dh_{t-1}[unit, b] = sum over this CTA's 128 gate columns
             if (tid == 0) {
                 tc_fence_after();
@@ -488,8 +507,10 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
                     }
                 }
                 umma_commit(mma_bar);
+                TL(1, T - 1 - t, 5);
             }
             mbar_wait(mma_bar, (T - 1 - t) & 1);
+            TL(1, T - 1 - t, 6);
             tc_fence_after();
             // ---- reduce-scatter: TMEM lane = unit; quarter q holds units 32q.. (-> CTA q) and 128+32q.. (-> CTA 4+q)
 #pragma unroll
@@ -504,16 +525,15 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
                     for (int b = 0; b < CPW; ++b) pv[b] += part[b];
                 }
                 const uint32_t dst = hf * 4 + q;
-                const uint32_t laddr = smem_u32(recv + (rank * UC + lane) * S::RSTRIDE + cg * CPW);
-                const uint32_t raddr = map_remote(laddr, dst);
+                float* wp = xg + (size_t)(((t & 1) * CL + dst) * CL + rank) * (NB * UC) + (cg * CPW) * UC + lane;
 #pragma unroll
-                for (int i = 0; i < CPW; i += 4)
-                    st_remote_v4(raddr + i * 4, make_uint4(__float_as_uint(pv[i]), __float_as_uint(pv[i + 1]),
-                                                           __float_as_uint(pv[i + 2]), __float_as_uint(pv[i + 3])));
+                for (int i = 0; i < CPW; ++i) wp[i * UC] = pv[i];           // 128-byte lines per row
             }
             tc_fence_before();
         }
+        TL(1, T - 1 - t, 7);
         cluster_arrive();
+        TL(1, T - 1 - t, 8);
 #pragma unroll
         for (int i = 0; i < RPT; ++i) {
             float* dg = dgates + ((size_t)t * B + b0 + warp * RPT + i) * H4 + ucol;
@@ -537,7 +557,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
 
 template <int NB, bool X3>
 static int launch_bwd(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
-                      const float* acts, float* dgates, float* dgsum, int T, int B, cudaStream_t st) {
+                      const float* acts, float* dgates, float* dgsum, float* xchg, int T, int B, cudaStream_t st) {
     using S = BwdSmem<NB, X3>;
     static bool attr = false;
     auto kern = lstm_bwd_cluster_kernel<NB, X3, CNT>;
@@ -549,7 +569,7 @@ static int launch_bwd(const float* dh_all, const float* dh_last, const float* W_
         }
         attr = true;
     }
-    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B);
+    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, xchg, T, B);
     FHVAE_LAUNCH_CHECK("lstm_bwd_cluster");
     return 0;
 }
@@ -559,7 +579,7 @@ int lstm_fwd_simt(const float* P, const float* Q, const float* W_hh, float* h_al
 
 template <int NB, bool X3>
 static int launch_fwd(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
-                      float* acts, int T, int B, cudaStream_t st) {
+                      float* acts, float* xchg, int T, int B, cudaStream_t st) {
     using S = FwdSmem<NB, X3>;
     static bool attr = false;
     auto kern = lstm_fwd_cluster_kernel<NB, X3, CNT>;
@@ -571,7 +591,7 @@ static int launch_fwd(const float* P, const float* Q, const float* W_hh, float* 
         }
         attr = true;
     }
-    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(P, Q, W_hh, h_all, c_all, acts, T, B);
+    kern<<<(B / NB) * CL, CNT, S::TOTAL, st>>>(P, Q, W_hh, h_all, c_all, acts, xchg, T, B);
     FHVAE_LAUNCH_CHECK("lstm_fwd_cluster");
     return 0;
 }
@@ -612,24 +632,24 @@ static int pick_nb(int B) {
 }
 
 int lstm_fwd_cluster(const float* P, const float* Q, const float* W_hh, float* h_all, float* c_all,
-                     float* acts, int T, int B, int H, int mode, cudaStream_t st) {
+                     float* acts, float* xchg, int T, int B, int H, int mode, cudaStream_t st) {
     const bool x3 = (mode == FHVAE_MODE_BF16X3);
     if (pick_nb(B) == 16)
-        return x3 ? launch_fwd<16, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st)
-                  : launch_fwd<16, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
-    return x3 ? launch_fwd<32, true>(P, Q, W_hh, h_all, c_all, acts, T, B, st)
-              : launch_fwd<32, false>(P, Q, W_hh, h_all, c_all, acts, T, B, st);
+        return x3 ? launch_fwd<16, true>(P, Q, W_hh, h_all, c_all, acts, xchg, T, B, st)
+                  : launch_fwd<16, false>(P, Q, W_hh, h_all, c_all, acts, xchg, T, B, st);
+    return x3 ? launch_fwd<32, true>(P, Q, W_hh, h_all, c_all, acts, xchg, T, B, st)
+              : launch_fwd<32, false>(P, Q, W_hh, h_all, c_all, acts, xchg, T, B, st);
 }
 
 int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_hh, const float* c_all,
-                     const float* acts, float* dgates, float* dgsum, int T, int B, int H, int mode,
+                     const float* acts, float* dgates, float* dgsum, float* xchg, int T, int B, int H, int mode,
                      cudaStream_t st) {
     const bool x3 = (mode == FHVAE_MODE_BF16X3);
     if (pick_nb(B) == 16)
-        return x3 ? launch_bwd<16, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st)
-                  : launch_bwd<16, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
-    return x3 ? launch_bwd<32, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st)
-              : launch_bwd<32, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, T, B, st);
+        return x3 ? launch_bwd<16, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, xchg, T, B, st)
+                  : launch_bwd<16, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, xchg, T, B, st);
+    return x3 ? launch_bwd<32, true>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, xchg, T, B, st)
+              : launch_bwd<32, false>(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, xchg, T, B, st);
 }
 
 #ifdef FHVAE_TIMELINE

@@ -507,6 +507,7 @@ class _FHVAEPlan(_Plan):
                 if not (k == "dec" and l == 0):
                     self.P[k, l] = f(T, B, 4 * H)
         self.Q = {"z1": f(B, 4 * self.H["z1"]), "dec": f(B, 4 * self.H["dec"])}
+        self.xchg = f(16, B, max(self.H.values()))      # L2-resident exchange scratch of the cluster kernels
         self.xhead = f(T, B, 2 * F)
         self._build_fwd()
 
@@ -545,7 +546,7 @@ class _FHVAEPlan(_Plan):
                 Pp = ptr(self.P[k, l]) if (k, l) in self.P else None
                 Qp = q0 if l == 0 else None
                 c.add("fhvae_lstm_fwd", Pp, Qp, m.poff(whh), ptr(self.h[k, l]), ptr(self.c[k, l]),
-                      ptr(self.acts[k, l]), T, B, H, mode)
+                      ptr(self.acts[k, l]), ptr(self.xchg), T, B, H, mode)
 
         def final_h(k):
             H = self.H[k]
@@ -592,7 +593,7 @@ class _FHVAEPlan(_Plan):
                     self.dg[k, l] = f(T, B, 4 * self.H[k])
                     self.dgsum[k, l] = f(B, 4 * self.H[k])
             self.dzcat = f(B, Z1 + Z2)
-            self.dh_rec, self.dc = f(2, B, Hmax), f(B, Hmax)
+            self.dh_rec, self.dc = self.xchg, f(B, Hmax)
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
         cs: List = []          # bias column sums (one grouped side launch at the end)
 

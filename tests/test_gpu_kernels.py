@@ -16,6 +16,16 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda"
 
 
+_XCH = {}
+
+
+def XCH(B, H):
+    """exchange scratch (16,B,H) of the cluster LSTM kernels, kept alive for the whole test session"""
+    if (B, H) not in _XCH:
+        _XCH[B, H] = torch.zeros(16, B, H, device=DEV)
+    return _XCH[B, H]
+
+
 def rnd(*s, seed=0, scale=1.0):
     g = torch.Generator().manual_seed(seed)
     return (torch.randn(*s, generator=g) * scale).to(DEV)
@@ -142,10 +152,10 @@ def test_lstm_fwd_bwd_vs_fp64(T, B, H):
     f = lambda *s: torch.zeros(*s, device=DEV)
     h_all, c_all, acts = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
     Pd, Qd, Wd = d(P), d(Q), d(W)
-    call("fhvae_lstm_fwd", ptr(Pd), ptr(Qd), ptr(Wd), ptr(h_all), ptr(c_all), ptr(acts), T, B, H, 0)
+    call("fhvae_lstm_fwd", ptr(Pd), ptr(Qd), ptr(Wd), ptr(h_all), ptr(c_all), ptr(acts), ptr(XCH(B, H)), T, B, H, 0)
     assert_close(h_all, hs, 2e-5, "h_all")
     assert_close(c_all, cs, 2e-5, "c_all")
-    dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(2, B, H), f(B, H)
+    dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(16, B, H), f(B, H)
     Ra, Rl = d(R_all), d(R_last)          # keep alive: ptr() of a temporary dangles
     call("fhvae_lstm_bwd", ptr(Ra), ptr(Rl), ptr(Wd), ptr(c_all), ptr(acts), ptr(dg), ptr(dgsum),
          ptr(dh_rec), ptr(dc), T, B, H, 0)
@@ -168,8 +178,8 @@ def test_lstm_cluster_fwd_matches_simt(T, B, mode):
     f = lambda *s: torch.zeros(*s, device=DEV)
     ref = [f(T, B, H), f(T, B, H), f(T, B, 4 * H)]
     out = [f(T, B, H), f(T, B, H), f(T, B, 4 * H)]
-    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(ref[0]), ptr(ref[1]), ptr(ref[2]), T, B, H, 0)
-    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(out[0]), ptr(out[1]), ptr(out[2]), T, B, H, mode)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(ref[0]), ptr(ref[1]), ptr(ref[2]), ptr(XCH(B, H)), T, B, H, 0)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(out[0]), ptr(out[1]), ptr(out[2]), ptr(XCH(B, H)), T, B, H, mode)
     torch.cuda.synchronize()
     for a, b, n in zip(out, ref, ["h_all", "c_all", "acts"]):
         assert_close(a, b, TC_TOL[mode], f"{n} mode {mode}")
@@ -184,11 +194,11 @@ def test_lstm_cluster_bwd_matches_simt(T, B, use_all, use_last, mode):
     P, Q = rnd(T, B, 4 * H, seed=1, scale=0.7), rnd(B, 4 * H, seed=2, scale=0.3)
     W = rnd(4 * H, H, seed=3, scale=1.0 / 16)
     h_all, c_all, acts = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
-    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(h_all), ptr(c_all), ptr(acts), T, B, H, 0)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W), ptr(h_all), ptr(c_all), ptr(acts), ptr(XCH(B, H)), T, B, H, 0)
     dh_all, dh_last = rnd(T, B, H, seed=4), rnd(B, H, seed=5)
     res = []
     for md in (0, mode):
-        dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(2, B, H), f(B, H)
+        dg, dgsum, dh_rec, dc = f(T, B, 4 * H), f(B, 4 * H), f(16, B, H), f(B, H)
         call("fhvae_lstm_bwd", ptr(dh_all) if use_all else None, ptr(dh_last) if use_last else None, ptr(W),
              ptr(c_all), ptr(acts), ptr(dg), ptr(dgsum), ptr(dh_rec), ptr(dc), T, B, H, md)
         torch.cuda.synchronize()
@@ -202,12 +212,12 @@ def test_lstm_null_inputs():
     f = lambda *s: torch.zeros(*s, device=DEV)
     Q, W = rnd(B, 4 * H, seed=1), rnd(4 * H, H, seed=2, scale=0.2)
     h1, c1, a1 = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
-    call("fhvae_lstm_fwd", None, ptr(Q), ptr(W), ptr(h1), ptr(c1), ptr(a1), T, B, H, 0)
+    call("fhvae_lstm_fwd", None, ptr(Q), ptr(W), ptr(h1), ptr(c1), ptr(a1), None, T, B, H, 0)
     P = Q.unsqueeze(0).expand(T, B, 4 * H).contiguous()
     h2, c2, a2 = f(T, B, H), f(T, B, H), f(T, B, 4 * H)
-    call("fhvae_lstm_fwd", ptr(P), None, ptr(W), ptr(h2), ptr(c2), ptr(a2), T, B, H, 0)
+    call("fhvae_lstm_fwd", ptr(P), None, ptr(W), ptr(h2), ptr(c2), ptr(a2), None, T, B, H, 0)
     assert torch.equal(h1, h2) and torch.equal(c1, c2)
-    assert _lib.fn("fhvae_lstm_fwd")(None, None, ptr(W), ptr(h1), ptr(c1), ptr(a1), T, B, H, 0, None) == -1
+    assert _lib.fn("fhvae_lstm_fwd")(None, None, ptr(W), ptr(h1), ptr(c1), ptr(a1), None, T, B, H, 0, None) == -1
 
 
 # ------------------------------------------------------------------------------- reparam / ELBO

@@ -44,8 +44,8 @@ def lstm(mode, T, B=256, H=256):
     z = lambda *s: torch.randn(*s, device=dev) * 0.3
     Pp, Q, W = z(T, B, 4 * H), z(B, 4 * H), z(4 * H, H) / 16
     h, c, a = z(T, B, H), z(T, B, H), z(T, B, 4 * H)
-    dg, dgs, dhr, dc, dh = z(T, B, 4 * H), z(B, 4 * H), z(2, B, H), z(B, H), z(T, B, H)
-    fw = lambda: _lib.check(_lib.fn("fhvae_lstm_fwd")(ptr(Pp), ptr(Q), ptr(W), ptr(h), ptr(c), ptr(a), T, B, H, mode, st()))
+    dg, dgs, dhr, dc, dh = z(T, B, 4 * H), z(B, 4 * H), z(16, B, H), z(B, H), z(T, B, H)
+    fw = lambda: _lib.check(_lib.fn("fhvae_lstm_fwd")(ptr(Pp), ptr(Q), ptr(W), ptr(h), ptr(c), ptr(a), ptr(dhr), T, B, H, mode, st()))
     bw = lambda: _lib.check(_lib.fn("fhvae_lstm_bwd")(ptr(dh), None, ptr(W), ptr(c), ptr(a), ptr(dg), ptr(dgs), ptr(dhr), ptr(dc), T, B, H, mode, st()))
     return timeit(fw), timeit(bw)
 
