@@ -29,14 +29,70 @@ constexpr int BM = 128, BN = 128;
 constexpr int TCT = 256;                        // producer / epilogue threads per CTA
 constexpr int TCT_ALL = TCT + 32;               // + the MMA-issuing warp
 constexpr int NSTAGE = 3;                       // 96 KB: two CTAs per SM (296 slots for the 320-tile projections)
-constexpr uint32_t LBO = BM * 16, SBO = 128;
+constexpr uint32_t LBO = BM * 16 + 32, SBO = 128;   // K-chunk planes padded by 32 B: 2-way instead of 4-way
+                                                    // bank conflicts for the producers' 16-byte stores
+template <bool X3>
+struct Cfg;
+
+// ---- coalesced path for K-contiguous operands (16-byte aligned): a warp-wide LDG.128 reads whole 128-byte
+// lines (8 or 16 lanes per row) instead of 32 different rows -- the lane<->row mapping capped the L1 tag
+// stage at one 32-byte sector per cycle (~3.7 TB/s chip-wide, tools/gemm_timeline.py).  A lane pair then
+// swaps one float4 each (4 shuffles) so that every thread owns whole 8-element K chunks for the 16-byte
+// UMMA-layout stores.
+template <int BK, int NV>
+__device__ __forceinline__ void load_tile_c(const float* __restrict__ src, long long rs, int row0, int rows,
+                                            int k0, int kend, float4 (&v)[NV]) {
+    constexpr int LPR = BK / 4;                          // lanes per row
+    constexpr int RPW = 32 / LPR;                        // rows per warp-instruction
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane % LPR, rg = lane / LPR;
+    const int gk = k0 + j * 4;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int gr = row0 + warp * (NV * RPW) + i * RPW + rg;
+        v[i] = (gr < rows && gk + 4 <= kend) ? __ldg(reinterpret_cast<const float4*>(src + (long long)gr * rs + gk))
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+template <bool X3, int BK, int NV>
+__device__ __forceinline__ void store_tile_c(const float4 (&v)[NV], uint8_t* s_hi, uint8_t* s_lo) {
+    constexpr int LPR = BK / 4, RPW = 32 / LPR;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int j = lane % LPR, rg = lane / LPR;
+    const bool odd = j & 1;
+#pragma unroll
+    for (int i = 0; i < NV; i += 2) {
+        // even lane keeps row i (gets the partner's upper half), odd lane keeps row i+1 (gets the lower half)
+        const float4 send = odd ? v[i] : v[i + 1];
+        float4 recv;
+        recv.x = __shfl_xor_sync(0xffffffffu, send.x, 1);
+        recv.y = __shfl_xor_sync(0xffffffffu, send.y, 1);
+        recv.z = __shfl_xor_sync(0xffffffffu, send.z, 1);
+        recv.w = __shfl_xor_sync(0xffffffffu, send.w, 1);
+        const float4 lo4 = odd ? recv : v[i], hi4 = odd ? v[i + 1] : recv;
+        const float c[8] = {lo4.x, lo4.y, lo4.z, lo4.w, hi4.x, hi4.y, hi4.z, hi4.w};
+        const int r = warp * (NV * RPW) + (i + (odd ? 1 : 0)) * RPW + rg, kc = j >> 1;
+        const uint32_t off = (uint32_t)kc * LBO + (uint32_t)r * 16;
+        if (X3) {
+            uint4 hi, lo;
+            split_bf16(c, hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + off) = hi;
+            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        } else {
+            *reinterpret_cast<uint4*>(s_hi + off) = make_uint4(pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]),
+                                                               pack_bf16(c[4], c[5]), pack_bf16(c[6], c[7]));
+        }
+    }
+}
+
 template <bool X3>
 struct Cfg {
     static constexpr int BK = X3 ? 32 : 64;
-    static constexpr int TILE_BYTES = BM * BK * 2;          // one bf16 operand tile
+    static constexpr int TILE_BYTES = (BK / 8) * (int)LBO;  // one bf16 operand tile (K-chunk planes of LBO bytes)
     static constexpr int OPS = X3 ? 4 : 2;                  // A_hi [A_lo] B_hi [B_lo]
     static constexpr int STAGE_BYTES = OPS * TILE_BYTES;    // 32 KB
     static constexpr int IT = BM * (BK / 8) / TCT;          // (row, k-chunk) items per thread per operand
+    static constexpr int NV = 2 * IT;                       // float4 loads per thread per operand
     static constexpr int DEPTH = X3 ? 2 : 1;                // K-blocks of global loads in flight per thread
     static constexpr int SMEM = NSTAGE * STAGE_BYTES + 128;
 };
@@ -101,7 +157,7 @@ __device__ __forceinline__ void store_tile(const float (&v)[IT][8], uint8_t* s_h
     for (int i = 0; i < IT; ++i) {
         const int item = threadIdx.x + i * TCT;
         const int r = item & (BM - 1), kc = item >> 7;
-        const uint32_t off = (uint32_t)(kc * BM + r) * 16;
+        const uint32_t off = (uint32_t)kc * LBO + (uint32_t)r * 16;
         if (X3) {
             uint4 hi, lo;
             split_bf16(v[i], hi, lo);
@@ -194,14 +250,22 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
         __syncwarp();
     } else {
         // ================= producers (8 warps), then epilogue =================
-        constexpr int DEPTH = C::DEPTH;
-        float va[DEPTH][IT][8], vb[DEPTH][IT][8];
+        constexpr int DEPTH = C::DEPTH, NV = C::NV;
+        // register ring: DEPTH K-blocks of loads in flight per thread.  A float4[NV] slot holds either NV
+        // coalesced float4 loads (K-contiguous, aligned operand) or IT items of 8 floats (any other operand).
+        float4 ra[DEPTH][NV], rb[DEPTH][NV];
+        const bool ca = P.a_vec, cb = P.b_vec;           // CTA-uniform
+        auto LOAD_A = [&](int k0, float4 (&slot)[NV]) {
+            if (ca) load_tile_c<BK, NV>(P.A, P.a_rs, m0, P.M, k0, P.K, slot);
+            else load_tile<IT>(P.A, P.a_rs, P.a_ks, 0, m0, P.M, k0, P.K, reinterpret_cast<float (&)[IT][8]>(slot));
+        };
+        auto LOAD_B = [&](int k0, float4 (&slot)[NV]) {
+            if (cb) load_tile_c<BK, NV>(P.B, P.b_rs, n0, P.N, k0, P.K, slot);
+            else load_tile<IT>(P.B, P.b_rs, P.b_ks, 0, n0, P.N, k0, P.K, reinterpret_cast<float (&)[IT][8]>(slot));
+        };
 #pragma unroll
         for (int d = 0; d < DEPTH; ++d)
-            if (d < nit) {
-                load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, (kb0 + d) * BK, P.K, va[d]);
-                load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, (kb0 + d) * BK, P.K, vb[d]);
-            }
+            if (d < nit) { LOAD_A((kb0 + d) * BK, ra[d]); LOAD_B((kb0 + d) * BK, rb[d]); }
         for (int it0 = 0; it0 < nit; it0 += DEPTH) {
 #pragma unroll
             for (int d = 0; d < DEPTH; ++d) {
@@ -210,12 +274,15 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
                     const int s = it % NSTAGE;
                     uint8_t* st = smem + s * STAGE_BYTES;
                     if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
-                    store_tile<X3, IT>(va[d], st, st + TILE_BYTES);
-                    store_tile<X3, IT>(vb[d], st + (X3 ? 2 : 1) * TILE_BYTES, st + 3 * TILE_BYTES);
+                    uint8_t* sb = st + (X3 ? 2 : 1) * TILE_BYTES;
+                    if (ca) store_tile_c<X3, BK, NV>(ra[d], st, st + TILE_BYTES);
+                    else store_tile<X3, IT>(reinterpret_cast<float (&)[IT][8]>(ra[d]), st, st + TILE_BYTES);
+                    if (cb) store_tile_c<X3, BK, NV>(rb[d], sb, st + 3 * TILE_BYTES);
+                    else store_tile<X3, IT>(reinterpret_cast<float (&)[IT][8]>(rb[d]), sb, st + 3 * TILE_BYTES);
                     if (it + DEPTH < nit) {        // refill this ring slot: DEPTH K-blocks stay in flight
                         const int k0 = (kb0 + it + DEPTH) * BK;
-                        load_tile<IT>(P.A, P.a_rs, P.a_ks, P.a_vec, m0, P.M, k0, P.K, va[d]);
-                        load_tile<IT>(P.B, P.b_rs, P.b_ks, P.b_vec, n0, P.N, k0, P.K, vb[d]);
+                        LOAD_A(k0, ra[d]);
+                        LOAD_B(k0, rb[d]);
                     }
                     fence_proxy_async();
                     __syncwarp();
@@ -331,8 +398,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         q.A = p.A; q.B = p.B; q.C = p.C; q.bias = p.bias;
         q.M = p.M; q.N = p.N; q.K = p.K; q.relu = p.relu; q.beta = p.beta; q.ldc = p.ldc;
         q.a_rs = p.sa_m; q.a_ks = p.sa_k; q.b_rs = p.sb_n; q.b_ks = p.sb_k;
-        q.a_vec = (p.sa_k == 1 && p.sa_m % 4 == 0 && aligned16(p.A));
-        q.b_vec = (p.sb_k == 1 && p.sb_n % 4 == 0 && aligned16(p.B));
+        q.a_vec = (p.sa_k == 1 && p.sa_m % 4 == 0 && p.K % 4 == 0 && aligned16(p.A));
+        q.b_vec = (p.sb_k == 1 && p.sb_n % 4 == 0 && p.K % 4 == 0 && aligned16(p.B));
         q.c_vec = (p.ldc % 4 == 0 && aligned16(p.C) && (p.bias == nullptr || aligned16(p.bias)));
         const int nkb = cdiv(p.K, bk);
         int ks = 1;
