@@ -88,6 +88,23 @@ int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
                    int T, int B, int H, int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Layer-wavefront recurrence over a stack of 1 or 2 LSTM layers in ONE launch (H == 256, B % 32 == 0,
+ * T <= 63, tensor-core modes only).  Layer 1 runs one step behind layer 0 and computes its own input
+ * projection  h0_t W_ih1^T + bias1  from the words layer 0 publishes, so the (T,B,4H) projection buffer and
+ * the projection GEMM of layer 1 do not exist.  Replaces the nn.LSTM(num_layers=2) forward of the
+ * restatement (reference fhvae.py:4-14 is a stub).
+ *   layer 0: P0 (T,B,4H) and/or Q0 (B,4H) as in fhvae_lstm_fwd;  layer 1: W_ih1 (4H,H), bias1 (4H) = b_ih+b_hh.
+ *   xchg: caller-allocated, ZERO-INITIALISED ONCE, fhvae_lstm_wave_xchg_bytes(T,B,H,nlayers) bytes, dedicated
+ *   to one (T,B,nlayers) geometry; it holds the exchange words and per-CTA launch counters and must not be
+ *   written by the caller afterwards.  fhvae_lstm_wave_supported returns 1 if the shape/mode is served.
+ * ------------------------------------------------------------------------------------------- */
+int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int mode);
+long long fhvae_lstm_wave_xchg_bytes(int T, int B, int H, int nlayers);
+int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0, float* acts0,
+                        const float* W_ih1, const float* bias1, const float* W_hh1, float* h1, float* c1,
+                        float* acts1, void* xchg, int T, int B, int H, int nlayers, int mode, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * K2/K4/K6: reparameterisation + ELBO terms (simple_fhvae.py:56-69, :106-116, :213-216).
  * ------------------------------------------------------------------------------------------- */
 /* head (B, 2Z) = [mu | logvar] rows of leading dim ld_head;  sample[b*ld_s + d] = mu + eps*exp(.5 logvar) */

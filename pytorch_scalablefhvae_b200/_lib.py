@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfhvae_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_simt.cu", "lstm_cluster.cu", "elbo.cu", "disc.cu",
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "disc.cu",
            "table_adam_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -42,6 +42,9 @@ PROTOTYPES = {
     "fhvae_gemm_batch": [C.POINTER(GemmProblem), _i, _i, _p],
     "fhvae_lstm_fwd": [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fhvae_lstm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
+    "fhvae_lstm_wave_supported": [_i, _i, _i, _i, _i],
+    "fhvae_lstm_wave_xchg_bytes": [_i, _i, _i, _i],
+    "fhvae_lstm_wave_fwd": [_p] * 13 + [_i, _i, _i, _i, _i, _p],
     "fhvae_reparam_fwd": [_p, _l, _p, _p, _l, _i, _i, _p],
     "fhvae_reparam_bwd": [_p, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p],
     "fhvae_elbo_fwd": [_p, _p, _l, _l, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
@@ -69,7 +72,7 @@ PROTOTYPES = {
     "fhvae_built_for_sm": [],
     "fhvae_launch_count": [],
 }
-NO_STATUS = {"fhvae_disc_nsplit", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
+NO_STATUS = {"fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
 EXPORTS = sorted(list(PROTOTYPES) + ["fhvae_last_error_string"])
 
 _lib = None
@@ -107,7 +110,8 @@ def load():
     for name, args in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.argtypes = args
-        fn.restype = C.c_ulonglong if name == "fhvae_launch_count" else C.c_int
+        fn.restype = (C.c_ulonglong if name == "fhvae_launch_count" else
+                      C.c_longlong if name == "fhvae_lstm_wave_xchg_bytes" else C.c_int)
     _lib = lib
     return lib
 

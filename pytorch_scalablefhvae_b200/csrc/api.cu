@@ -32,6 +32,12 @@ int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_h
                      const float* acts, float* dgates, float* dgsum, float* xchg, int T, int B, int H, int mode,
                      cudaStream_t st);
 
+bool lstm_wave_supported(int T, int B, int H, int L);
+size_t lstm_wave_xchg_bytes(int T, int B, int L);
+int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
+                  const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
+                  void* xchg, int T, int B, int L, int mode, cudaStream_t st);
+
 }  // namespace fhvae
 
 using namespace fhvae;
@@ -83,4 +89,25 @@ extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const f
     }
     return lstm_bwd_simt(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dc, T, B, H,
                          as_stream(stream));
+}
+
+extern "C" int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int mode) {
+    return (mode == FHVAE_MODE_BF16X3 || mode == FHVAE_MODE_BF16) && lstm_wave_supported(T, B, H, nlayers) ? 1 : 0;
+}
+
+extern "C" long long fhvae_lstm_wave_xchg_bytes(int T, int B, int H, int nlayers) {
+    if (!lstm_wave_supported(T, B, H, nlayers)) return 0;
+    return (long long)lstm_wave_xchg_bytes(T, B, nlayers);
+}
+
+extern "C" int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0,
+                                   float* acts0, const float* W_ih1, const float* bias1, const float* W_hh1,
+                                   float* h1, float* c1, float* acts1, void* xchg, int T, int B, int H,
+                                   int nlayers, int mode, void* stream) {
+    FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
+                    "lstm_wave_fwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+    FHVAE_CHECK_ARG(W_hh0 && h0 && c0 && acts0 && xchg && (P0 || Q0), "lstm_wave_fwd: null pointer (layer 0)");
+    FHVAE_CHECK_ARG(nlayers == 1 || (W_ih1 && W_hh1 && h1 && c1 && acts1), "lstm_wave_fwd: null pointer (layer 1)");
+    return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, nlayers,
+                         mode, as_stream(stream));
 }

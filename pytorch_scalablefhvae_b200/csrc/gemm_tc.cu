@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
 
     if (warp == TCT / 32) {
         // ================= MMA issuer: one elected lane =================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int it = 0; it < nit; ++it) {
                 const int s = it % NSTAGE;
                 mbar_wait(&full[s], (it / NSTAGE) & 1);

@@ -57,47 +57,6 @@ __device__ long long g_timeline[2][32][16];
 #define TL(k, step, slot) do { } while (0)
 #endif
 
-template <int NCOL>
-__device__ __forceinline__ void tmem_ld_nb(uint32_t taddr, float (&v)[NCOL]);
-template <>
-__device__ __forceinline__ void tmem_ld_nb<32>(uint32_t taddr, float (&v)[32]) { tmem_ld32(taddr, v); }
-template <>
-__device__ __forceinline__ void tmem_ld_nb<16>(uint32_t taddr, float (&v)[16]) {
-    uint32_t r[16];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_nb<4>(uint32_t taddr, float (&v)[4]) {
-    uint32_t r[4];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
-}
-template <>
-__device__ __forceinline__ void tmem_ld_nb<8>(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
-                 : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
-}
-
 // shared-memory map of the forward kernel (bytes)
 template <int NB, bool X3>
 struct FwdSmem {
@@ -223,7 +182,7 @@ lstm_fwd_cluster_kernel(const float* __restrict__ P, const float* __restrict__ Q
                 fence_proxy_async();
                 __syncthreads();
             }
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 TL(0, t, 12);
                 const uint32_t hb = smem_u32(smem + S::H_OFF + (t & 1) * S::H_BUF);
@@ -483,7 +442,7 @@ lstm_bwd_cluster_kernel(const float* __restrict__ dh_all, const float* __restric
             __syncthreads();
             TL(1, T - 1 - t, 4);
             // ---- partial dh_{t-1}[unit, b] = sum over this CTA's 128 gate columns
-            if (tid == 0) {
+            if (warp == 0 && elect_one()) {
                 tc_fence_after();
                 const uint64_t dwh0 = make_smem_desc(smem_u32(w_hi), W_LBO, SBO_);
                 const uint64_t dwl0 = make_smem_desc(smem_u32(w_lo), W_LBO, SBO_);

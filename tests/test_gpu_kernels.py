@@ -207,6 +207,43 @@ def test_lstm_cluster_bwd_matches_simt(T, B, use_all, use_last, mode):
     assert_close(res[1][1], res[0][1], TC_TOL[mode], f"dgsum mode {mode}")
 
 
+def _wave_xchg(T, B, H, L):
+    n = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, H, L)
+    assert n > 0
+    return torch.zeros(n // 4, device=DEV)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("T,B,L,repeat", [(1, 32, 1, 1), (3, 64, 2, 2), (20, 256, 1, 2), (20, 256, 2, 3), (7, 320, 2, 1),
+                                           (20, 608, 1, 1)])
+def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
+    """Layer-wavefront recurrence (one launch for the stack, LL exchange through L2, layer-1 projection
+    in-kernel) against the exact fp32 per-layer kernels + fp32 projection GEMM.  Repeated launches reuse the
+    exchange buffer (per-CTA launch counters make the flags unique)."""
+    H = 256
+    P = rnd(T, B, 4 * H, seed=1, scale=0.7)
+    Q = rnd(B, 4 * H, seed=2, scale=0.3)
+    W0 = rnd(4 * H, H, seed=3, scale=1.0 / 16)
+    Wi1, W1, b1 = rnd(4 * H, H, seed=4, scale=1.0 / 16), rnd(4 * H, H, seed=5, scale=1.0 / 16), rnd(4 * H, seed=6, scale=0.2)
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    ref = [[f(T, B, H), f(T, B, H), f(T, B, 4 * H)] for _ in range(2)]
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W0), ptr(ref[0][0]), ptr(ref[0][1]), ptr(ref[0][2]), None, T, B, H, 0)
+    if L == 2:
+        P1 = f(T, B, 4 * H)
+        gemm(ref[0][0], Wi1, P1, T * B, 4 * H, H, (H, 1), (1, H), 4 * H, bias=b1)
+        call("fhvae_lstm_fwd", ptr(P1), None, ptr(W1), ptr(ref[1][0]), ptr(ref[1][1]), ptr(ref[1][2]), None, T, B, H, 0)
+    xchg = _wave_xchg(T, B, H, L)
+    for rep in range(repeat):
+        out = [[f(T, B, H), f(T, B, H), f(T, B, 4 * H)] for _ in range(2)]
+        l1 = [ptr(Wi1), ptr(b1), ptr(W1), ptr(out[1][0]), ptr(out[1][1]), ptr(out[1][2])] if L == 2 else [None] * 6
+        call("fhvae_lstm_wave_fwd", ptr(P), ptr(Q), ptr(W0), ptr(out[0][0]), ptr(out[0][1]), ptr(out[0][2]), *l1,
+             ptr(xchg), T, B, H, L, mode)
+        torch.cuda.synchronize()
+        for l in range(L):
+            for a, b, n in zip(out[l], ref[l], ["h_all", "c_all", "acts"]):
+                assert_close(a, b, TC_TOL[mode], f"layer {l} {n} mode {mode} rep {rep}")
+
+
 def test_lstm_null_inputs():
     T, B, H = 3, 8, 16
     f = lambda *s: torch.zeros(*s, device=DEV)

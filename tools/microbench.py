@@ -50,6 +50,19 @@ def lstm(mode, T, B=256, H=256):
     return timeit(fw), timeit(bw)
 
 
+def wave(mode, T, L, B=256, H=256):
+    z = lambda *s: torch.randn(*s, device=dev) * 0.3
+    Pp, Q = z(T, B, 4 * H), z(B, 4 * H)
+    W0, Wi1, W1, b1 = z(4 * H, H) / 16, z(4 * H, H) / 16, z(4 * H, H) / 16, z(4 * H)
+    o = [[z(T, B, H), z(T, B, H), z(T, B, 4 * H)] for _ in range(2)]
+    n = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, H, L)
+    xchg = torch.zeros(n // 4, device=dev)
+    l1 = [ptr(Wi1), ptr(b1), ptr(W1), ptr(o[1][0]), ptr(o[1][1]), ptr(o[1][2])] if L == 2 else [None] * 6
+    fw = lambda: _lib.check(_lib.fn("fhvae_lstm_wave_fwd")(ptr(Pp), ptr(Q), ptr(W0), ptr(o[0][0]), ptr(o[0][1]), ptr(o[0][2]),
+                                                          *l1, ptr(xchg), T, B, H, L, mode, st()))
+    return (timeit(fw),)
+
+
 def gemm(mode, M, N, K, kind):
     A = torch.randn(M, K, device=dev); Bm = torch.randn(N, K, device=dev); C = torch.zeros(M, N, device=dev)
     if kind == "nt":
@@ -70,6 +83,13 @@ if __name__ == "__main__":
     for mode in (1, 2):
         for T in (1, 2, 5, 20):
             out[f"lstm mode{mode} T{T} fwd/bwd us"] = lstm(mode, T)
+    for mode in (1, 2):
+        for T, L in ((1, 1), (20, 1), (1, 2), (5, 2), (20, 2)):
+            out[f"wave mode{mode} T{T} L{L} fwd us"] = wave(mode, T, L)
+    if os.environ.get("ONLY_LSTM"):
+        for k, v in out.items():
+            print(k, [round(x, 2) for x in v])
+        sys.exit(0)
     shapes = [("nt", 5120, 1024, 80), ("nt", 5120, 1024, 256), ("nt", 5120, 160, 256), ("nt", 256, 1024, 64),
               ("nt", 256, 64, 256), ("nn", 5120, 256, 1024), ("nn", 5120, 256, 160), ("nn", 256, 64, 1024),
               ("tn", 1024, 256, 4864), ("tn", 1024, 256, 5120), ("tn", 1024, 80, 5120), ("tn", 160, 256, 5120),
