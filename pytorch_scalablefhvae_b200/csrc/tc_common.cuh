@@ -33,7 +33,7 @@ __device__ __forceinline__ void fence_mbar_init() {
 }
 // Bounded spin: a protocol bug traps (launch error on the host) instead of hanging the GPU.
 #ifndef FHVAE_SPIN_LIMIT
-#define FHVAE_SPIN_LIMIT (1u << 24)
+#define FHVAE_SPIN_LIMIT (1u << 20)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok, spins = 0;

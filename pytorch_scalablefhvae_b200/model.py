@@ -16,6 +16,7 @@ replayed list of kernel launches on preallocated workspaces, optionally captured
 from __future__ import annotations
 
 import math
+import os
 import weakref
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -499,12 +500,22 @@ class _FHVAEPlan(_Plan):
         self.x_tm = f(T, B, F)
         self.bsum = f(m._bias_block_len)
         self.h, self.c, self.acts, self.P = {}, {}, {}, {}
+        # two-layer stacks run as ONE layer-wavefront launch (lstm_wave.cu): no layer-1 projection GEMM / buffer
+        use_wave = os.environ.get("FHVAE_WAVE", "1") != "0"
+        self.wave = {k: bool(use_wave and self.L[k] == 2 and len(set(hus)) == 1 and
+                             _lib.fn("fhvae_lstm_wave_supported")(T, B, self.H[k], 2, self.mode))
+                     for (k, _), hus in zip(self.NETS, (m.z2_hus, m.z1_hus, m.x_hus))}
+        self.wave_xchg = None
+        if any(self.wave.values()):
+            Hw = next(self.H[k] for k in self.wave if self.wave[k])
+            nbytes = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, Hw, 2)
+            self.wave_xchg = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)   # zeroed ONCE
         for k, _ in self.NETS:
             H = self.H[k]
             for l in range(self.L[k]):
                 self.h[k, l], self.c[k, l] = f(T, B, H), f(T, B, H)
                 self.acts[k, l] = f(T, B, 4 * H)
-                if not (k == "dec" and l == 0):
+                if not (k == "dec" and l == 0) and not (self.wave[k] and l == 1):
                     self.P[k, l] = f(T, B, 4 * H)
         self.Q = {"z1": f(B, 4 * self.H["z1"]), "dec": f(B, 4 * self.H["dec"])}
         self.xchg = f(16, B, max(self.H.values()))      # L2-resident exchange scratch of the cluster kernels
@@ -538,6 +549,14 @@ class _FHVAEPlan(_Plan):
 
         def stack(k, q0):
             H = self.H[k]
+            if self.wave[k]:
+                _, whh0, _, _ = _lstm_names(pre[k], 0)
+                wih1, whh1, _, _ = _lstm_names(pre[k], 1)
+                c.add("fhvae_lstm_wave_fwd", ptr(self.P[k, 0]) if (k, 0) in self.P else None, q0, m.poff(whh0),
+                      ptr(self.h[k, 0]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), m.poff(wih1), self._bs(k, 1),
+                      m.poff(whh1), ptr(self.h[k, 1]), ptr(self.c[k, 1]), ptr(self.acts[k, 1]),
+                      ptr(self.wave_xchg), T, B, H, 2, mode)
+                return
             for l in range(self.L[k]):
                 wih, whh, _, _ = _lstm_names(pre[k], l)
                 if l > 0:

@@ -17,7 +17,7 @@ P, Q = z(T, B, 4 * H), z(B, 4 * H)
 W0, Wi1, W1, b1 = z(4 * H, H) / 16, z(4 * H, H) / 16, z(4 * H, H) / 16, z(4 * H)
 o = [[z(T, B, H), z(T, B, H), z(T, B, 4 * H)] for _ in range(2)]
 vp = lambda t: ctypes.c_void_p(ptr(t))
-names = ["top", "pulled", "issued", "mma_done", "tmem_ld", "gates+sync", "cell+xpull+sync", "publish", "in_issue+hbm"]
+names = ["top", "pull+hbm_st+arrive(+P prefetch)", "rec_done", "tmem_ld", "gates+sync", "cell+sync", "publish", "p1_readout"]
 for L in (1, 2):
     xchg = torch.zeros(lib.fhvae_lstm_wave_xchg_bytes(T, B, H, L) // 4, device="cuda")
     for mode in (1, 2):
@@ -32,8 +32,9 @@ for L in (1, 2):
             tl = [[buf[(layer * 32 + t) * 16 + k] for k in range(16)] for t in range(T)]
             print(f"L={L} mode {mode} layer {layer}: cycles per phase (steps 8..11)")
             for t in range(8, 12):
-                d = [tl[t][k] - tl[t][k - 1] for k in range(1, 9)]
-                print("  ", t, dict(zip(names[1:], d)), "period", tl[t][0] - tl[t - 1][0])
+                r = tl[t]
+                print("  ", t, "loads_issued", r[6] - r[0], "waited+stored", r[7] - r[6], "pull_total", r[1] - r[0], "rec_done", r[2] - r[1], "tmem_ld", r[3] - r[2],
+                      "gates", r[4] - r[3], "cell", r[5] - r[4], "rest(publish,p1)", tl[t + 1][0] - r[5], "period", r[0] - tl[t - 1][0])
         if L == 2:
             print("   layer-1 lag behind layer 0 at step 10 top (cycles; clocks of different SMs, indicative):",
                   buf[(32 + 10) * 16] - buf[10 * 16])
