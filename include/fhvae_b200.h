@@ -104,6 +104,19 @@ int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float* W_hh0, fl
                         const float* W_ih1, const float* bias1, const float* W_hh1, float* h1, float* c1,
                         float* acts1, void* xchg, int T, int B, int H, int nlayers, int mode, void* stream);
 
+/* BPTT of the same stack in ONE launch, top layer first; the bottom layer receives
+ *   dh0_t = dgates0_{t+1} W_hh0 + dgates1_t W_ih1 (+ dh_last_bot at t = T-1)
+ * inside the kernel (cross-layer product accumulated into the recurrent split-K accumulator), so the layer-1 dgrad
+ * GEMM and its (T,B,H) buffer do not exist.  nlayers == 1: only the *_top arguments are used.
+ * Outputs as fhvae_lstm_bwd: dgates_* (T,B,4H), dgsum_* (B,4H, may be NULL).  xchg: ZERO-INITIALISED ONCE,
+ * fhvae_lstm_wave_bwd_xchg_bytes bytes, dedicated to one (T,B,nlayers) geometry and to this entry point. */
+long long fhvae_lstm_wave_bwd_xchg_bytes(int T, int B, int H, int nlayers);
+int fhvae_lstm_wave_bwd(const float* dh_all_top, const float* dh_last_top, const float* dh_last_bot,
+                        const float* W_hh_top, const float* c_top, const float* acts_top, float* dgates_top,
+                        float* dgsum_top, const float* W_ih_top, const float* W_hh_bot, const float* c_bot,
+                        const float* acts_bot, float* dgates_bot, float* dgsum_bot, void* xchg, int T, int B, int H,
+                        int nlayers, int mode, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K2/K4/K6: reparameterisation + ELBO terms (simple_fhvae.py:56-69, :106-116, :213-216).
  * ------------------------------------------------------------------------------------------- */

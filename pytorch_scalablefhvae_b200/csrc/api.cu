@@ -37,6 +37,10 @@ size_t lstm_wave_xchg_bytes(int T, int B, int L);
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
                   void* xchg, int T, int B, int L, int mode, cudaStream_t st);
+size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L);
+int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
+                  const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
+                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st);
 
 }  // namespace fhvae
 
@@ -110,4 +114,24 @@ extern "C" int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih1 && W_hh1 && h1 && c1 && acts1), "lstm_wave_fwd: null pointer (layer 1)");
     return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, nlayers,
                          mode, as_stream(stream));
+}
+
+extern "C" long long fhvae_lstm_wave_bwd_xchg_bytes(int T, int B, int H, int nlayers) {
+    if (!lstm_wave_supported(T, B, H, nlayers)) return 0;
+    return (long long)lstm_wave_bwd_xchg_bytes(T, B, nlayers);
+}
+
+extern "C" int fhvae_lstm_wave_bwd(const float* dh_all_top, const float* dh_last_top, const float* dh_last_bot,
+                                   const float* W_hh_top, const float* c_top, const float* acts_top, float* dgates_top,
+                                   float* dgsum_top, const float* W_ih_top, const float* W_hh_bot, const float* c_bot,
+                                   const float* acts_bot, float* dgates_bot, float* dgsum_bot, void* xchg, int T, int B,
+                                   int H, int nlayers, int mode, void* stream) {
+    FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
+                    "lstm_wave_bwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+    FHVAE_CHECK_ARG(W_hh_top && c_top && acts_top && dgates_top && xchg, "lstm_wave_bwd: null pointer (top layer)");
+    FHVAE_CHECK_ARG(nlayers == 1 || (W_ih_top && W_hh_bot && c_bot && acts_bot && dgates_bot),
+                    "lstm_wave_bwd: null pointer (bottom layer)");
+    FHVAE_CHECK_ARG(dh_all_top || dh_last_top || (nlayers == 2 && dh_last_bot), "lstm_wave_bwd: no incoming gradient");
+    return lstm_wave_bwd(dh_all_top, dh_last_top, dh_last_bot, W_hh_top, c_top, acts_top, dgates_top, dgsum_top, W_ih_top,
+                         W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, nlayers, mode, as_stream(stream));
 }

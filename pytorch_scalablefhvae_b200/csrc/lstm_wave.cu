@@ -447,6 +447,377 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     if (warp == NT / 32) tmem_dealloc<TCOLS>(tmem_base);
 }
 
+// ================================================================================================
+// BPTT wavefront (top layer first)
+// ================================================================================================
+// Per step t (descending) the CTA that owns 32 units computes dgates_t pointwise and contributes the split-K
+// partial  W_hh^T[:, its 128 gate columns] * dgates_t  of dh_{t-1} for ALL 256 units (TMEM lane = unit); the
+// 8 partial tiles of a unit slice are exchanged as LL words (reduce-scatter through L2, 2-deep) and summed in
+// a fixed order by the owner.  In a 2-layer stack the layer-1 CTA of rank j also publishes its dgates1_t slice
+// (bf16 hi/lo operand words); the layer-0 CTA of rank j multiplies it by ITS W_ih1^T slice (resident smem A
+// operand) into the same accumulator that later receives W_hh0^T * dgates0_{t+1}:
+//      dh0_t = dgates0_{t+1} W_hh0 + dgates1_t W_ih1          -> ONE reduce-scatter, no dgrad GEMM, no dh buffer.
+// The cross-layer MMAs are issued two steps ahead (accumulators double-buffered in TMEM), off the critical path.
+struct WaveBwdArgs {
+    const float* dh_all;      // top layer: dL/dh_t from the consumer of all outputs (may be NULL)
+    const float* dh_last1;    // top layer: extra dL/dh_{T-1} (may be NULL)
+    const float* dh_last0;    // bottom layer of a 2-layer stack: extra dL/dh0_{T-1} (may be NULL)
+    const float* Whh1; const float* c1; const float* a1; float* dg1; float* dgsum1;   // top layer (the only one if L == 1)
+    const float* Wih1;                                                                  // (4H, H) of the top layer
+    const float* Whh0; const float* c0; const float* a0; float* dg0; float* dgsum0;   // bottom layer
+    uint4* xchg;
+    int T, B, b_off, G, Gs, L;
+};
+
+template <bool X3>
+struct WaveBwdSmem {
+    static constexpr int G_PART = WNB * WNC * 2;               // dgates operand, 32 rows x 128 gate cols bf16 = 8 KB
+    static constexpr int G_BUF = (X3 ? 2 : 1) * G_PART;
+    static constexpr int G0_OFF = 0;                           // own dgates_t (B operand of the recurrent product)
+    static constexpr int G1_OFF = G_BUF;                       // [2] dgates1 of the layer above (bottom layer only)
+    static constexpr int BAR_OFF = 3 * G_BUF;
+    static constexpr int W_OFF = (BAR_OFF + 64 + 1023) / 1024 * 1024;
+    static constexpr int W_HALF = 128 * WNC * 2;               // 128 units x 128 gate cols bf16 = 32 KB
+    static constexpr int W_PART = 2 * W_HALF;
+    static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
+    static constexpr int TOTAL1 = W_OFF;
+    static constexpr int TOTAL2 = W_OFF + W_BYTES;
+};
+constexpr int WRS = 512;           // uint4 words of one (dst, src) partial tile: 32 units x 16 row pairs
+constexpr int WDG = 2048;          // uint4 words of one published dgates slice (2 parts x 16 chunks x 32 rows x 2 halves)
+
+template <bool X3>
+__global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
+    using S = WaveBwdSmem<X3>;
+    constexpr int NB = WNB, NT = WNT, CH = WH, UC = WU, NC = WNC;
+    constexpr int NCG = NT / 128, CPW = NB / NCG, RPT = NB * 32 / NT, H4 = 4 * CH;
+    constexpr int NPARTW = (X3 ? 2 : 1) * 1024;               // LL words of a dgates slice actually used
+    static_assert(CPW == 8 && RPT == 2, "LL packing assumes 8 columns per thread / 2 rows per thread");
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* g0 = smem + S::G0_OFF;
+    uint64_t* g_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);    // [2] compute warps -> issuer
+    uint64_t* g_pro = g_full + 2;                                          // bottom-layer prologue
+    uint64_t* rec_done = g_full + 3;                                       // issuer (commit) -> compute warps
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 4);
+    uint32_t* epoch_slot = tmem_slot + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = (warp >> 2) & 3;
+    const int role = blockIdx.x / (a.G * WG);                  // 0: top layer (scheduled first), 1: bottom layer
+    const int grp = (blockIdx.x / WG) % a.G;
+    const int rank = blockIdx.x % WG;
+    const int T = a.T, B = a.B;
+    const int b0 = a.b_off + grp * NB;
+    const bool bottom = role == 1;                             // bottom layer of a 2-layer stack
+    const bool top2 = role == 0 && a.L == 2;                   // top layer that feeds a bottom layer
+    const float* W_hh = bottom ? a.Whh0 : a.Whh1;
+    const float* c_all = bottom ? a.c0 : a.c1;
+    const float* acts = bottom ? a.a0 : a.a1;
+    float* dgates = bottom ? a.dg0 : a.dg1;
+    float* dgsum = bottom ? a.dgsum0 : a.dgsum1;
+    const float* dh_all = bottom ? nullptr : a.dh_all;
+    const float* dh_last = bottom ? a.dh_last0 : a.dh_last1;
+    // exchange buffer: [header][partials: role][group][2][dst][src][WRS] then [dgates1: group][t][rank][WDG]
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(a.xchg) + (((a.L - 1) * 2 + role) * WMAXG + grp) * WG + rank;
+    uint4* rs = a.xchg + WHDR + ((size_t)(role * a.Gs + grp) * 2) * (WG * WG * WRS);
+    uint4* dgx = a.xchg + WHDR + ((size_t)(2 * a.Gs) * 2) * (WG * WG * WRS) + ((size_t)grp * T) * (WG * WDG) + rank * WDG;
+
+    constexpr int NACC = 2;
+    constexpr int ABUF = 2 * NACC * NB;                        // one accumulator set: 2 unit halves x NACC x NB columns
+    constexpr int WCOLS = NC / 2;                              // 64 columns per (half, part) of the resident W_hh^T
+    constexpr int ACOL = (X3 ? 2 : 1) * 2 * WCOLS;             // 256 / 128
+    constexpr int TCOLS = (ACOL + 2 * ABUF) <= 256 ? 256 : 512;
+    if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
+    if (tid == 32) {
+        mbar_init(&g_full[0], NT / 32); mbar_init(&g_full[1], NT / 32); mbar_init(g_pro, NT / 32);
+        mbar_init(rec_done, 1);
+        fence_mbar_init();
+        *epoch_slot = *cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t fbase = (*epoch_slot) << 6;
+    const uint32_t tmem_acc = tmem_base + ACOL;
+    constexpr uint32_t idesc = make_idesc_bf16(128, NB);
+    constexpr uint32_t W_LBO = 128 * 16, G_LBO = NB * 16, SBO_ = 128;
+    const uint32_t g0_u = smem_u32(g0), g1_u = smem_u32(smem + S::G1_OFF), w_u = smem_u32(smem + S::W_OFF);
+
+    if (warp >= NT / 32) {
+        // ================= tcgen05 issuer =================
+        reg_dec<32>();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp == NT / 32 && elect_one()) {
+            // acc set `as` (+)= W^T * G : A from TMEM (recurrent, W_hh^T) or from smem (cross-layer, W_ih1^T)
+            auto rec = [&](uint32_t as, uint32_t accumulate) {
+                const uint64_t dgh0 = make_smem_desc(g0_u, G_LBO, SBO_), dgl0 = make_smem_desc(g0_u + S::G_PART, G_LBO, SBO_);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 2
+                    for (int s = 0; s < NC / 16; ++s) {
+                        const uint64_t ig = (uint64_t)((s * 2 * G_LBO) >> 4);
+                        const uint32_t awh = tmem_base + (uint32_t)(hf * WCOLS + s * 8), awl = awh + 2 * WCOLS;
+                        const uint32_t td = tmem_acc + as * ABUF + (uint32_t)((hf * NACC + (s % NACC)) * NB);
+                        const uint32_t first = (accumulate || s >= NACC) ? 1u : 0u;
+                        if (X3) {
+                            umma_bf16_ts(td, awl, dgh0 + ig, idesc, first);
+                            umma_bf16_ts(td, awh, dgl0 + ig, idesc, 1u);
+                            umma_bf16_ts(td, awh, dgh0 + ig, idesc, 1u);
+                        } else {
+                            umma_bf16_ts(td, awh, dgh0 + ig, idesc, first);
+                        }
+                    }
+                }
+            };
+            auto cross = [&](uint32_t as, uint32_t gbuf) {
+                const uint32_t gb = g1_u + gbuf * S::G_BUF;
+                const uint64_t dgh0 = make_smem_desc(gb, G_LBO, SBO_), dgl0 = make_smem_desc(gb + S::G_PART, G_LBO, SBO_);
+                const uint64_t dwh0 = make_smem_desc(w_u, W_LBO, SBO_), dwl0 = make_smem_desc(w_u + S::W_PART, W_LBO, SBO_);
+#pragma unroll 1
+                for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll 2
+                    for (int s = 0; s < NC / 16; ++s) {
+                        const uint64_t iw = (uint64_t)((hf * S::W_HALF + s * 2 * W_LBO) >> 4), ig = (uint64_t)((s * 2 * G_LBO) >> 4);
+                        const uint32_t td = tmem_acc + as * ABUF + (uint32_t)((hf * NACC + (s % NACC)) * NB);
+                        const uint32_t first = s >= NACC ? 1u : 0u;
+                        if (X3) {
+                            umma_bf16(td, dwl0 + iw, dgh0 + ig, idesc, first);
+                            umma_bf16(td, dwh0 + iw, dgl0 + ig, idesc, 1u);
+                            umma_bf16(td, dwh0 + iw, dgh0 + ig, idesc, 1u);
+                        } else {
+                            umma_bf16(td, dwh0 + iw, dgh0 + ig, idesc, first);
+                        }
+                    }
+                }
+            };
+            if (bottom) {
+                mbar_wait(g_pro, 0);                           // dgates1_{T-1} (and _{T-2}) are in G1
+                tc_fence_after();
+                cross((uint32_t)((T - 1) & 1), (uint32_t)((T - 1) & 1));
+                umma_commit(rec_done);                         // dh0_{T-1} partial = cross part only
+                if (T > 1) cross((uint32_t)((T - 2) & 1), (uint32_t)((T - 2) & 1));
+            }
+            for (int k = 0; k + 1 < T; ++k) {
+                const int t = T - 1 - k;                       // dgates_t ready -> partial of dh_{t-1}
+                mbar_wait(&g_full[k & 1], (k >> 1) & 1);
+                tc_fence_after();
+                rec((uint32_t)((t - 1) & 1), bottom ? 1u : 0u);
+                umma_commit(rec_done);
+                if (bottom && t >= 2) cross((uint32_t)(t & 1), (uint32_t)(t & 1));   // dh0_{t-2} += dgates1_{t-2} W_ih1
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= compute warps =================
+        reg_inc<112>();
+        {   // resident A operand of the recurrent product: lane = unit n (per half), column = (k, k+1) pair of the
+            // CTA's 128 gate columns k = g*32 + u;  A[n][k] = W_hh[(g*H + 32*rank + u) * H + n];  cg <-> gate g
+            const int g = cg;
+#pragma unroll 1
+            for (int hf = 0; hf < 2; ++hf) {
+                const int n = hf * 128 + q * 32 + lane;
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float v0 = __ldg(W_hh + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
+                    const float v1 = __ldg(W_hh + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
+                    hi[j] = pack_bf16(v0, v1);
+                    lo[j] = pack_bf16(v0 - __uint_as_float(hi[j] << 16), v1 - __uint_as_float(hi[j] & 0xffff0000u));
+                }
+                const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * WCOLS + g * 16);
+                tmem_st16(ta, hi);
+                if (X3) tmem_st16(ta + 2 * WCOLS, lo);
+            }
+            tmem_wait_st();
+        }
+        if (bottom) {
+            // resident smem A operand of the cross-layer product: A2[n][k] = W_ih1[(g*H + 32*rank + u) * H + n]
+            constexpr int WIT = CH * (NC / 8) / NT;
+#pragma unroll 2
+            for (int i = 0; i < WIT; ++i) {
+                const int item = tid + i * NT;
+                const int n = item & (CH - 1), kc = item >> 8;
+                float v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int k = kc * 8 + j, g = k >> 5, u = k & 31;
+                    v[j] = __ldg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
+                }
+                const uint32_t off = (uint32_t)(n >> 7) * S::W_HALF + (uint32_t)(kc * 128 + (n & 127)) * 16;
+                if (X3) {
+                    uint4 hi, lo;
+                    split_bf16(v, hi, lo);
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + off) = hi;
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + S::W_PART + off) = lo;
+                } else {
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + off) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+
+        // dgates1_t slice of the layer above -> G1[buf]: 2048 (1024) LL words, 4 (2) per thread
+        auto pull_dg = [&](int t, int buf) {
+            const uint4* src = dgx + (size_t)t * (WG * WDG);
+            uint8_t* dst = smem + S::G1_OFF + buf * S::G_BUF;
+            constexpr int PER = NPARTW / NT;
+            uint4 v[PER];
+#pragma unroll
+            for (int i = 0; i < PER; ++i) v[i] = ld_ll(src + tid + i * NT);
+#pragma unroll
+            for (int i = 0; i < PER; ++i) {
+                const int w = tid + i * NT;
+                wait_ll(v[i], src + w, fbase + (uint32_t)(T - t));
+                *reinterpret_cast<uint2*>(dst + (w >> 10) * S::G_PART + (w & 1023) * 8) = make_uint2(v[i].x, v[i].z);
+            }
+        };
+        if (bottom) {
+            pull_dg(T - 1, (T - 1) & 1);
+            if (T > 1) pull_dg(T - 2, (T - 2) & 1);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(g_pro);
+        }
+
+        float dcreg[RPT], gsum[4][RPT], gkeep[4][RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) {
+            dcreg[i] = 0.f;
+            gsum[0][i] = gsum[1][i] = gsum[2][i] = gsum[3][i] = 0.f;
+        }
+        const int ucol = rank * UC + lane;                     // this thread's hidden unit (pointwise phase)
+        auto store_dg = [&](int ts) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                float* dg = dgates + ((size_t)ts * B + b0 + warp * RPT + i) * H4 + ucol;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) dg[g * CH] = gkeep[g][i];
+            }
+        };
+        uint32_t nwait = 0;
+
+        for (int k = 0; k < T; ++k) {
+            const int t = T - 1 - k;
+            // ---- everything the pointwise step needs (thread = unit `lane`, rows warp*RPT + i)
+            float a_i[RPT], a_f[RPT], a_g[RPT], a_o[RPT], c_t[RPT], c_p[RPT], dh[RPT];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int b = b0 + warp * RPT + i;
+                const size_t r4 = ((size_t)t * B + b) * H4, r1 = ((size_t)t * B + b) * CH;
+                a_i[i] = __ldg(acts + r4 + ucol);
+                a_f[i] = __ldg(acts + r4 + CH + ucol);
+                a_g[i] = __ldg(acts + r4 + 2 * CH + ucol);
+                a_o[i] = __ldg(acts + r4 + 3 * CH + ucol);
+                c_t[i] = __ldg(c_all + r1 + ucol);
+                c_p[i] = t ? __ldg(c_all + r1 - (size_t)B * CH + ucol) : 0.f;
+                float d = dh_all ? __ldg(dh_all + r1 + ucol) : 0.f;
+                if (t == T - 1 && dh_last) d += __ldg(dh_last + (size_t)b * CH + ucol);
+                dh[i] = d;
+            }
+            if (k > 0 || bottom) {
+                // ---- this CTA's split-K partial of dh_t for all 256 units: TMEM -> LL words, one tile per owner
+                mbar_wait(rec_done, nwait & 1);
+                ++nwait;
+                tc_fence_after();
+                uint4* wr = rs + (size_t)(k & 1) * (WG * WG * WRS);
+#pragma unroll
+                for (int hf = 0; hf < 2; ++hf) {
+                    float pv[CPW];
+                    const uint32_t tb = tmem_acc + (uint32_t)((t & 1) * ABUF + hf * NACC * NB) + ((uint32_t)(q * 32) << 16);
+                    tmem_ld_nb<CPW>(tb + (uint32_t)(cg * CPW), pv);
+#pragma unroll
+                    for (int x = 1; x < NACC; ++x) {
+                        float part[CPW];
+                        tmem_ld_nb<CPW>(tb + (uint32_t)(x * NB + cg * CPW), part);
+#pragma unroll
+                        for (int b = 0; b < CPW; ++b) pv[b] += part[b];
+                    }
+                    const int dst = hf * 4 + q;
+                    uint4* wp = wr + ((size_t)dst * WG + rank) * WRS + (cg * 4) * 32 + lane;
+#pragma unroll
+                    for (int j = 0; j < CPW / 2; ++j)
+                        st_ll(wp + j * 32, __float_as_uint(pv[2 * j]), __float_as_uint(pv[2 * j + 1]), fbase + k + 1);
+                }
+                tc_fence_before();
+                // ---- the 8 partial tiles of this CTA's units (fixed summation order: deterministic)
+                const uint4* rd = wr + ((size_t)rank * WG) * WRS + warp * 32 + lane;
+                uint4 pr[WG];
+#pragma unroll
+                for (int src = 0; src < WG; ++src) pr[src] = ld_ll(rd + src * WRS);
+#pragma unroll
+                for (int src = 0; src < WG; ++src) {
+                    wait_ll(pr[src], rd + src * WRS, fbase + k + 1);
+                    dh[0] += __uint_as_float(pr[src].x);
+                    dh[1] += __uint_as_float(pr[src].z);
+                }
+            }
+            // ---- pointwise BPTT; bf16 operand of the next products in smem
+            uint8_t* g_hi = g0;
+            uint8_t* g_lo = g0 + S::G_PART;
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const int bl = warp * RPT + i;
+                const float tc = tanhf_fast(c_t[i]);
+                const float dc = dcreg[i] + dh[i] * a_o[i] * (1.f - tc * tc);
+                dcreg[i] = dc * a_f[i];
+                float gq[4];
+                gq[0] = dc * a_g[i] * a_i[i] * (1.f - a_i[i]);
+                gq[1] = dc * c_p[i] * a_f[i] * (1.f - a_f[i]);
+                gq[2] = dc * a_i[i] * (1.f - a_g[i] * a_g[i]);
+                gq[3] = dh[i] * tc * a_o[i] * (1.f - a_o[i]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    gkeep[g][i] = gq[g];
+                    gsum[g][i] += gq[g];
+                    const int kk = g * 32 + lane;
+                    const uint32_t off = (uint32_t)(kk >> 3) * G_LBO + (uint32_t)bl * 16 + (uint32_t)(kk & 7) * 2;
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(gq[g]);
+                    *reinterpret_cast<__nv_bfloat16*>(g_hi + off) = hh;
+                    if (X3) *reinterpret_cast<__nv_bfloat16*>(g_lo + off) = __float2bfloat16_rn(gq[g] - __bfloat162float(hh));
+                }
+            }
+            if (top2) {
+                // publish this CTA's dgates_t slice (operand layout, 8-byte halves) for the bottom-layer CTA of the same rank
+                bar_compute();
+                uint4* dp = dgx + (size_t)t * (WG * WDG);
+#pragma unroll
+                for (int i = 0; i < NPARTW / NT; ++i) {
+                    const int w = tid + i * NT;
+                    const uint2 d = *reinterpret_cast<const uint2*>(g0 + (w >> 10) * S::G_PART + (w & 1023) * 8);
+                    st_ll(dp + w, d.x, d.y, fbase + (uint32_t)(T - t));
+                }
+            }
+            if (bottom && t >= 2) pull_dg(t - 2, t & 1);       // operand of the cross-layer MMAs issued behind this step's
+            if (t > 0) {
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&g_full[k & 1]);
+            }
+            store_dg(t);                                        // HBM stores in the shadow of the MMAs
+        }
+        if (dgsum) {
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                float* o = dgsum + (size_t)(b0 + warp * RPT + i) * H4 + ucol;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) o[g * CH] = gsum[g][i];
+            }
+        }
+    }
+    if (tid == 0) *cnt = (fbase >> 6) + 1;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NT / 32) tmem_dealloc<TCOLS>(tmem_base);
+}
+
 bool lstm_wave_supported(int T, int B, int H, int L) {
     return H == WH && B % WNB == 0 && T >= 1 && T <= WMAXT && (L == 1 || L == 2);
 }
@@ -491,4 +862,44 @@ int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0
     return mode == FHVAE_MODE_BF16X3 ? launch_wave_fwd<true>(a, st) : launch_wave_fwd<false>(a, st);
 }
 
+size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L) {
+    int gs = B / WNB;
+    const int gmax = wave_groups_per_launch(L);
+    if (gs > gmax) gs = gmax;
+    return ((size_t)WHDR + (size_t)L * gs * 2 * WG * WG * WRS + (L == 2 ? (size_t)gs * T * WG * WDG : 0)) * sizeof(uint4);
+}
+
+template <bool X3>
+static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
+    using S = WaveBwdSmem<X3>;
+    static bool attr = false;
+    auto kern = lstm_wave_bwd_kernel<X3>;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL2);
+        if (e != cudaSuccess) {
+            set_error("lstm_wave_bwd: cudaFuncSetAttribute(%d B): %s", S::TOTAL2, cudaGetErrorString(e));
+            return (int)e;
+        }
+        attr = true;
+    }
+    const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L);
+    a.Gs = gtot < gmax ? gtot : gmax;
+    for (int g0 = 0; g0 < gtot; g0 += gmax) {
+        a.G = (gtot - g0) < gmax ? (gtot - g0) : gmax;
+        a.b_off = g0 * WNB;
+        kern<<<a.L * a.G * WG, WNTA, a.L == 2 ? S::TOTAL2 : S::TOTAL1, st>>>(a);
+        FHVAE_LAUNCH_CHECK("lstm_wave_bwd");
+    }
+    return 0;
+}
+
+int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
+                  const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
+                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st) {
+    WaveBwdArgs a{dh_all, dh_last1, dh_last0, Whh1, c1, a1, dg1, dgsum1, Wih1, Whh0, c0, a0, dg0, dgsum0,
+                  reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L};
+    return mode == FHVAE_MODE_BF16X3 ? launch_wave_bwd<true>(a, st) : launch_wave_bwd<false>(a, st);
+}
+
 }  // namespace fhvae
+

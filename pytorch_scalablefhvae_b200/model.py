@@ -505,7 +505,7 @@ class _FHVAEPlan(_Plan):
         self.wave = {k: bool(use_wave and self.L[k] == 2 and len(set(hus)) == 1 and
                              _lib.fn("fhvae_lstm_wave_supported")(T, B, self.H[k], 2, self.mode))
                      for (k, _), hus in zip(self.NETS, (m.z2_hus, m.z1_hus, m.x_hus))}
-        self.wave_xchg = None
+        self.wave_xchg = self.wave_xchg_bwd = None
         if any(self.wave.values()):
             Hw = next(self.H[k] for k in self.wave if self.wave[k])
             nbytes = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, Hw, 2)
@@ -627,6 +627,29 @@ class _FHVAEPlan(_Plan):
             """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum."""
             H = self.H[k]
             dh_all = dh_all_top
+            if self.wave[k]:
+                # both layers in one wavefront launch; dh of layer 0 never exists in HBM (lstm_wave.cu)
+                if self.wave_xchg_bwd is None:
+                    nbytes = _lib.fn("fhvae_lstm_wave_bwd_xchg_bytes")(T, B, H, 2)
+                    self.wave_xchg_bwd = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)
+                n0, n1 = _lstm_names(pre[k], 0), _lstm_names(pre[k], 1)
+                c.add("fhvae_lstm_wave_bwd", dh_all_top, dh_last_of(1), dh_last_of(0), m.poff(n1[1]),
+                      ptr(self.c[k, 1]), ptr(self.acts[k, 1]), ptr(self.dg[k, 1]), ptr(self.dgsum[k, 1]),
+                      m.poff(n1[0]), m.poff(n0[1]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), ptr(self.dg[k, 0]),
+                      ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd), T, B, H, 2, mode)
+                for l in (1, 0):
+                    wih, whh, bih, bhh = _lstm_names(pre[k], l)
+                    if T > 1:
+                        wg.append(gemm_tn(ptr(self.dg[k, l], B * 4 * H), 4 * H, ptr(self.h[k, l]), H, g(whh), H,
+                                          4 * H, H, (T - 1) * B))
+                    else:
+                        c.torch_op(lambda o=m._off[whh], n=4 * H * H: gflat[o:o + n].zero_())
+                    cs.append(ColsumProblem(ptr(self.dgsum[k, l]), g(bih), g(bhh), 4 * H, B, 4 * H))
+                    if l > 0:
+                        wg.append(gemm_tn(ptr(self.dg[k, l]), 4 * H, ptr(self.h[k, l - 1]), H, g(wih), H,
+                                          4 * H, H, TB))
+                wg.flush()
+                return
             for l in reversed(range(self.L[k])):
                 wih, whh, bih, bhh = _lstm_names(pre[k], l)
                 c.add("fhvae_lstm_bwd", dh_all, dh_last_of(l), m.poff(whh), ptr(self.c[k, l]),

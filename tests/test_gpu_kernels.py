@@ -244,6 +244,56 @@ def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
                 assert_close(a, b, TC_TOL[mode], f"layer {l} {n} mode {mode} rep {rep}")
 
 
+@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("T,B,L,use_all,use_last,repeat", [(1, 32, 1, True, True, 1), (4, 64, 2, False, True, 2),
+                                                           (20, 256, 1, True, False, 2), (20, 256, 2, True, True, 3),
+                                                           (20, 256, 2, False, True, 1), (2, 320, 2, True, True, 1),
+                                                           (5, 608, 1, True, True, 1)])
+def test_lstm_wave_bwd_matches_simt(T, B, L, use_all, use_last, repeat, mode):
+    """BPTT wavefront (top layer first; dh0_t = dg0_{t+1} W_hh0 + dg1_t W_ih1 inside the kernel) against the exact
+    fp32 per-layer BPTT kernels + fp32 dgrad GEMM."""
+    H = 256
+    f = lambda *s: torch.zeros(*s, device=DEV)
+    P, Q = rnd(T, B, 4 * H, seed=1, scale=0.7), rnd(B, 4 * H, seed=2, scale=0.3)
+    W0 = rnd(4 * H, H, seed=3, scale=1.0 / 16)
+    Wi1, W1, b1 = rnd(4 * H, H, seed=4, scale=1.0 / 16), rnd(4 * H, H, seed=5, scale=1.0 / 16), rnd(4 * H, seed=6, scale=0.2)
+    st = [[f(T, B, H), f(T, B, H), f(T, B, 4 * H)] for _ in range(2)]       # h, c, acts per layer (exact fp32 forward)
+    call("fhvae_lstm_fwd", ptr(P), ptr(Q), ptr(W0), ptr(st[0][0]), ptr(st[0][1]), ptr(st[0][2]), None, T, B, H, 0)
+    if L == 2:
+        P1 = f(T, B, 4 * H)
+        gemm(st[0][0], Wi1, P1, T * B, 4 * H, H, (H, 1), (1, H), 4 * H, bias=b1)
+        call("fhvae_lstm_fwd", ptr(P1), None, ptr(W1), ptr(st[1][0]), ptr(st[1][1]), ptr(st[1][2]), None, T, B, H, 0)
+    top = L - 1
+    Wtop = W1 if L == 2 else W0
+    dh_all, dh_last, dh_last0 = rnd(T, B, H, seed=7), rnd(B, H, seed=8), rnd(B, H, seed=9)
+    pa = ptr(dh_all) if use_all else None
+    pl = ptr(dh_last) if use_last else None
+    # reference: per-layer exact kernels
+    rdg = [f(T, B, 4 * H), f(T, B, 4 * H)]
+    rsum = [f(B, 4 * H), f(B, 4 * H)]
+    dc = f(B, H)
+    call("fhvae_lstm_bwd", pa, pl, ptr(Wtop), ptr(st[top][1]), ptr(st[top][2]), ptr(rdg[top]), ptr(rsum[top]), None,
+         ptr(dc), T, B, H, 0)
+    if L == 2:
+        dh0 = f(T, B, H)
+        gemm(rdg[1], Wi1, dh0, T * B, H, 4 * H, (4 * H, 1), (H, 1), H)      # dh0 = dg1 @ W_ih1
+        call("fhvae_lstm_bwd", ptr(dh0), ptr(dh_last0), ptr(W0), ptr(st[0][1]), ptr(st[0][2]), ptr(rdg[0]), ptr(rsum[0]),
+             None, ptr(dc), T, B, H, 0)
+    n = _lib.fn("fhvae_lstm_wave_bwd_xchg_bytes")(T, B, H, L)
+    assert n > 0
+    xchg = torch.zeros(n // 4, device=DEV)
+    for rep in range(repeat):
+        dg = [f(T, B, 4 * H), f(T, B, 4 * H)]
+        dgs = [f(B, 4 * H), f(B, 4 * H)]
+        bot = ([ptr(Wi1), ptr(W0), ptr(st[0][1]), ptr(st[0][2]), ptr(dg[0]), ptr(dgs[0])] if L == 2 else [None] * 6)
+        call("fhvae_lstm_wave_bwd", pa, pl, ptr(dh_last0) if L == 2 else None, ptr(Wtop), ptr(st[top][1]), ptr(st[top][2]),
+             ptr(dg[top]), ptr(dgs[top]), *bot, ptr(xchg), T, B, H, L, mode)
+        torch.cuda.synchronize()
+        for l in range(L):
+            assert_close(dg[l], rdg[l], TC_TOL[mode], f"layer {l} dgates mode {mode} rep {rep}")
+            assert_close(dgs[l], rsum[l], TC_TOL[mode], f"layer {l} dgsum mode {mode} rep {rep}")
+
+
 def test_lstm_null_inputs():
     T, B, H = 3, 8, 16
     f = lambda *s: torch.zeros(*s, device=DEV)

@@ -60,7 +60,17 @@ def wave(mode, T, L, B=256, H=256):
     l1 = [ptr(Wi1), ptr(b1), ptr(W1), ptr(o[1][0]), ptr(o[1][1]), ptr(o[1][2])] if L == 2 else [None] * 6
     fw = lambda: _lib.check(_lib.fn("fhvae_lstm_wave_fwd")(ptr(Pp), ptr(Q), ptr(W0), ptr(o[0][0]), ptr(o[0][1]), ptr(o[0][2]),
                                                           *l1, ptr(xchg), T, B, H, L, mode, st()))
-    return (timeit(fw),)
+    nb = _lib.fn("fhvae_lstm_wave_bwd_xchg_bytes")(T, B, H, L)
+    xb = torch.zeros(nb // 4, device=dev)
+    dh, dhl, dhl0 = z(T, B, H), z(B, H), z(B, H)
+    dg = [z(T, B, 4 * H), z(T, B, 4 * H)]
+    dgs = [z(B, 4 * H), z(B, 4 * H)]
+    top = L - 1
+    bot = [ptr(Wi1), ptr(W0), ptr(o[0][1]), ptr(o[0][2]), ptr(dg[0]), ptr(dgs[0])] if L == 2 else [None] * 6
+    Wt = W1 if L == 2 else W0
+    bw = lambda: _lib.check(_lib.fn("fhvae_lstm_wave_bwd")(ptr(dh), ptr(dhl), ptr(dhl0) if L == 2 else None, ptr(Wt), ptr(o[top][1]),
+                                                          ptr(o[top][2]), ptr(dg[top]), ptr(dgs[top]), *bot, ptr(xb), T, B, H, L, mode, st()))
+    return timeit(fw), timeit(bw)
 
 
 def gemm(mode, M, N, K, kind):
@@ -85,7 +95,7 @@ if __name__ == "__main__":
             out[f"lstm mode{mode} T{T} fwd/bwd us"] = lstm(mode, T)
     for mode in (1, 2):
         for T, L in ((1, 1), (20, 1), (1, 2), (5, 2), (20, 2)):
-            out[f"wave mode{mode} T{T} L{L} fwd us"] = wave(mode, T, L)
+            out[f"wave mode{mode} T{T} L{L} fwd/bwd us"] = wave(mode, T, L)
     if os.environ.get("ONLY_LSTM"):
         for k, v in out.items():
             print(k, [round(x, 2) for x in v])
