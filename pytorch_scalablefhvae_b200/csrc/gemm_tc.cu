@@ -85,6 +85,61 @@ __device__ __forceinline__ void store_tile_c(const float4 (&v)[NV], uint8_t* s_h
     }
 }
 
+// ---- MN-contiguous operands (weight gradients: A(m,k) = G[k*ld + m], B(k,n) = X[k*ld + n]; data gradients:
+// B(k,n) = W[k*ld + n]).  The tile goes into the canonical *MN-major* no-swizzle UMMA layout: a 2 KB plane per
+// group of 8 k, core matrix = 8 k x 8 mn (16 B per k), element (mn, k) at (k/8)*LBO + (mn/8)*128 + (k%8)*16 +
+// (mn%8)*2 -- same LBO/SBO numbers as the K-major planes, only the instruction descriptor's major bit differs.
+// A global 32-byte run of 8 consecutive mn is one 16-byte smem store per bf16 part: no transposition, and
+// 2 LDG.128 per item instead of 8 strided LDG.32.  Lane = (k%8) + 8*(mn-chunk%4): a warp reads 8 rows x 128 B
+// and writes 4 whole core matrices (conflict-free).
+template <int BK, int NV>
+__device__ __forceinline__ void load_tile_mn(const float* __restrict__ src, long long ks, bool vec, int row0, int rows,
+                                             int k0, int kend, float4 (&v)[NV]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NI = NV / 2;                              // items (8 mn x 1 k) per thread
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int idx = warp * NI + i, kg = idx >> 2, mg = idx & 3;
+        const int k = k0 + kg * 8 + (lane & 7), m = row0 + (mg * 4 + (lane >> 3)) * 8;
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+        if (k < kend && m < rows) {
+            const float* p = src + (long long)k * ks + m;
+            if (vec && m + 8 <= rows) {
+                x = __ldg(reinterpret_cast<const float4*>(p));
+                y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+            } else {
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = (m + j < rows) ? __ldg(p + j) : 0.f;
+                x = make_float4(t[0], t[1], t[2], t[3]);
+                y = make_float4(t[4], t[5], t[6], t[7]);
+            }
+        }
+        v[2 * i] = x;
+        v[2 * i + 1] = y;
+    }
+}
+template <bool X3, int BK, int NV>
+__device__ __forceinline__ void store_tile_mn(const float4 (&v)[NV], uint8_t* s_hi, uint8_t* s_lo) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int NI = NV / 2;
+#pragma unroll
+    for (int i = 0; i < NI; ++i) {
+        const int idx = warp * NI + i, kg = idx >> 2, mg = idx & 3;
+        const float c[8] = {v[2 * i].x, v[2 * i].y, v[2 * i].z, v[2 * i].w, v[2 * i + 1].x, v[2 * i + 1].y, v[2 * i + 1].z, v[2 * i + 1].w};
+        const uint32_t off = (uint32_t)kg * LBO + (uint32_t)(mg * 4 + (lane >> 3)) * 128 + (uint32_t)(lane & 7) * 16;
+        if (X3) {
+            uint4 hi, lo;
+            split_bf16(c, hi, lo);
+            *reinterpret_cast<uint4*>(s_hi + off) = hi;
+            *reinterpret_cast<uint4*>(s_lo + off) = lo;
+        } else {
+            *reinterpret_cast<uint4*>(s_hi + off) = make_uint4(pack_bf16(c[0], c[1]), pack_bf16(c[2], c[3]),
+                                                               pack_bf16(c[4], c[5]), pack_bf16(c[6], c[7]));
+        }
+    }
+}
+
 template <bool X3>
 struct Cfg {
     static constexpr int BK = X3 ? 32 : 64;
@@ -109,6 +164,7 @@ struct TcProblem {
     long long ldc;
     float beta;
     int a_vec, b_vec, c_vec;    // 16-byte vector access allowed
+    int a_mn, b_mn;             // operand is M/N-contiguous: staged in the MN-major UMMA layout
     int ksplit, kb_per_split;   // K blocks (of BK) per split
     int tile_start, tiles_n, tiles_mn;
 };
@@ -214,7 +270,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
-    constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+    const uint32_t idesc = make_idesc_bf16(BM, BN) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16);
     GTL(1);
 
     if (warp == TCT / 32) {
@@ -254,13 +310,16 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
         // register ring: DEPTH K-blocks of loads in flight per thread.  A float4[NV] slot holds either NV
         // coalesced float4 loads (K-contiguous, aligned operand) or IT items of 8 floats (any other operand).
         float4 ra[DEPTH][NV], rb[DEPTH][NV];
-        const bool ca = P.a_vec, cb = P.b_vec;           // CTA-uniform
+        const bool ca = P.a_vec && !P.a_mn, cb = P.b_vec && !P.b_mn;   // CTA-uniform
+        const bool ma = P.a_mn, mb = P.b_mn;
         auto LOAD_A = [&](int k0, float4 (&slot)[NV]) {
-            if (ca) load_tile_c<BK, NV>(P.A, P.a_rs, m0, P.M, k0, P.K, slot);
+            if (ma) load_tile_mn<BK, NV>(P.A, P.a_ks, P.a_vec, m0, P.M, k0, P.K, slot);
+            else if (ca) load_tile_c<BK, NV>(P.A, P.a_rs, m0, P.M, k0, P.K, slot);
             else load_tile<IT>(P.A, P.a_rs, P.a_ks, 0, m0, P.M, k0, P.K, reinterpret_cast<float (&)[IT][8]>(slot));
         };
         auto LOAD_B = [&](int k0, float4 (&slot)[NV]) {
-            if (cb) load_tile_c<BK, NV>(P.B, P.b_rs, n0, P.N, k0, P.K, slot);
+            if (mb) load_tile_mn<BK, NV>(P.B, P.b_ks, P.b_vec, n0, P.N, k0, P.K, slot);
+            else if (cb) load_tile_c<BK, NV>(P.B, P.b_rs, n0, P.N, k0, P.K, slot);
             else load_tile<IT>(P.B, P.b_rs, P.b_ks, 0, n0, P.N, k0, P.K, reinterpret_cast<float (&)[IT][8]>(slot));
         };
 #pragma unroll
@@ -275,9 +334,11 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
                     uint8_t* st = smem + s * STAGE_BYTES;
                     if (it >= NSTAGE) mbar_wait(&empty[s], ((it / NSTAGE) - 1) & 1);
                     uint8_t* sb = st + (X3 ? 2 : 1) * TILE_BYTES;
-                    if (ca) store_tile_c<X3, BK, NV>(ra[d], st, st + TILE_BYTES);
+                    if (ma) store_tile_mn<X3, BK, NV>(ra[d], st, st + TILE_BYTES);
+                    else if (ca) store_tile_c<X3, BK, NV>(ra[d], st, st + TILE_BYTES);
                     else store_tile<X3, IT>(reinterpret_cast<float (&)[IT][8]>(ra[d]), st, st + TILE_BYTES);
-                    if (cb) store_tile_c<X3, BK, NV>(rb[d], sb, st + 3 * TILE_BYTES);
+                    if (mb) store_tile_mn<X3, BK, NV>(rb[d], sb, st + 3 * TILE_BYTES);
+                    else if (cb) store_tile_c<X3, BK, NV>(rb[d], sb, st + 3 * TILE_BYTES);
                     else store_tile<X3, IT>(reinterpret_cast<float (&)[IT][8]>(rb[d]), sb, st + 3 * TILE_BYTES);
                     if (it + DEPTH < nit) {        // refill this ring slot: DEPTH K-blocks stay in flight
                         const int k0 = (kb0 + it + DEPTH) * BK;
@@ -321,7 +382,23 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
                 const int rmax = min(32, P.M - mrow0);
                 if (nok) {
                     float* cp = P.C + (long long)mrow0 * P.ldc + gn;
-                    if (atomic) {
+                    if (atomic && P.c_vec && n0 + col0 + 32 <= P.N) {
+                        // split-K partials: one red.global.add.v4.f32 per 4 columns (4x fewer L2 atomic operations
+                        // than scalar atomics: the L2 atomic units were the tail of every weight-gradient GEMM)
+                        const int cgp = lane & 7, rr = lane >> 3;
+                        float* cq = P.C + (long long)mrow0 * P.ldc + n0 + col0 + cgp * 4;
+                        const float4 b4 = (P.bias && split == 0) ? __ldg(reinterpret_cast<const float4*>(P.bias + n0 + col0 + cgp * 4))
+                                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const int r = rr + 4 * i;
+                            if (r < rmax) {
+                                const float* t4 = tr + r * 33 + cgp * 4;
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cq + (long long)r * P.ldc),
+                                             "f"(t4[0] + b4.x), "f"(t4[1] + b4.y), "f"(t4[2] + b4.z), "f"(t4[3] + b4.w) : "memory");
+                            }
+                        }
+                    } else if (atomic) {
 #pragma unroll 8
                         for (int r = 0; r < rmax; ++r) atomicAdd(cp + (long long)r * P.ldc, tr[r * 33 + lane] + bv);
                     } else if (P.beta == 0.f) {
@@ -349,16 +426,24 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
     if (warp == TCT / 32) tmem_dealloc<BN>(tmem_d);
 }
 
-// zero the C tiles of split-K problems (beta == 0) before the atomics land
+// zero the C tiles of split-K problems (beta == 0) before the atomics land: 4 CTAs per 128x128 tile
 __global__ void __launch_bounds__(256) gemm_tc_zero_kernel(const __grid_constant__ TcBatch tb) {
+    const int bt = blockIdx.x >> 2, sub = blockIdx.x & 3;
     int pi = 0;
-    while (pi + 1 < tb.n && (int)blockIdx.x >= tb.p[pi + 1].tile_start) ++pi;
+    while (pi + 1 < tb.n && bt >= tb.p[pi + 1].tile_start) ++pi;
     const TcProblem& P = tb.p[pi];
-    const int t = blockIdx.x - P.tile_start;
-    const int m0 = (t / P.tiles_n) * BM, n0 = (t % P.tiles_n) * BN;
-    for (int e = threadIdx.x; e < BM * BN; e += 256) {
-        const int m = m0 + e / BN, n = n0 + e % BN;
-        if (m < P.M && n < P.N) P.C[(long long)m * P.ldc + n] = 0.f;
+    const int t = bt - P.tile_start;
+    const int m0 = (t / P.tiles_n) * BM + sub * 32, n0 = (t % P.tiles_n) * BN;
+    const int cq = threadIdx.x & 31, r0 = threadIdx.x >> 5;           // 32 float4 columns x 8 rows per pass
+    const int n = n0 + cq * 4;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + r0 + i * 8;
+        if (m >= P.M || n >= P.N) continue;
+        float* c = P.C + (long long)m * P.ldc + n;
+        if (P.c_vec && n + 4 <= P.N) *reinterpret_cast<float4*>(c) = make_float4(0.f, 0.f, 0.f, 0.f);
+        else
+            for (int j = 0; j < 4 && n + j < P.N; ++j) c[j] = 0.f;
     }
 }
 
@@ -388,7 +473,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         if (problems[i].M > 0 && problems[i].N > 0 && problems[i].K >= 16)
             unsplit_tiles += cdiv(problems[i].M, BM) * cdiv(problems[i].N, BN);
     // split K so that the launch offers ~2 CTAs per SM, never below 128 of K per split
-    const int want_split = unsplit_tiles > 0 ? cdiv(2 * kNumSM, unsplit_tiles) : 1;
+    // (floor, not ceil: 304 CTAs on 296 slots is two waves -- measured 45 us vs 33 us for the same weight gradient)
+    const int want_split = unsplit_tiles > 0 ? ((2 * kNumSM) / unsplit_tiles > 0 ? (2 * kNumSM) / unsplit_tiles : 1) : 1;
     for (int i = 0; i < n; ++i) {
         const fhvae_gemm_problem& p = problems[i];
         if (p.M == 0 || p.N == 0) continue;
@@ -398,8 +484,10 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         q.A = p.A; q.B = p.B; q.C = p.C; q.bias = p.bias;
         q.M = p.M; q.N = p.N; q.K = p.K; q.relu = p.relu; q.beta = p.beta; q.ldc = p.ldc;
         q.a_rs = p.sa_m; q.a_ks = p.sa_k; q.b_rs = p.sb_n; q.b_ks = p.sb_k;
-        q.a_vec = (p.sa_k == 1 && p.sa_m % 4 == 0 && p.K % 4 == 0 && aligned16(p.A));
-        q.b_vec = (p.sb_k == 1 && p.sb_n % 4 == 0 && p.K % 4 == 0 && aligned16(p.B));
+        q.a_mn = (p.sa_m == 1 && p.sa_k != 1);
+        q.b_mn = (p.sb_n == 1 && p.sb_k != 1);
+        q.a_vec = q.a_mn ? (p.sa_k % 4 == 0 && aligned16(p.A)) : (p.sa_k == 1 && p.sa_m % 4 == 0 && p.K % 4 == 0 && aligned16(p.A));
+        q.b_vec = q.b_mn ? (p.sb_k % 4 == 0 && aligned16(p.B)) : (p.sb_k == 1 && p.sb_n % 4 == 0 && p.K % 4 == 0 && aligned16(p.B));
         q.c_vec = (p.ldc % 4 == 0 && aligned16(p.C) && (p.bias == nullptr || aligned16(p.bias)));
         const int nkb = cdiv(p.K, bk);
         int ks = 1;
@@ -425,7 +513,7 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         ++tb.n;
     }
     if (ztotal > 0) {
-        gemm_tc_zero_kernel<<<ztotal, 256, 0, st>>>(zb);
+        gemm_tc_zero_kernel<<<ztotal * 4, 256, 0, st>>>(zb);
         FHVAE_LAUNCH_CHECK("gemm_tc_zero");
     }
     if (total > 0) {

@@ -25,7 +25,9 @@ __global__ void scatter_reduce_kernel(const float* __restrict__ src, int64_t ld_
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
     if (b >= B) return;
     const int64_t row = idx[b];
-    // is there an earlier segment with the same row?  (warp-parallel scan + ballot)
+    // warp-parallel match of idx[] against this segment's row, 32 segments per ballot.  An earlier segment
+    // with the same row owns the sum (first occurrence); later ones are added in ascending b, so the
+    // summation order -- hence the result -- is exactly that of a serial scan.
     bool dup = false;
     for (int j0 = 0; j0 < b && !dup; j0 += 32) {
         const int j = j0 + l;
@@ -35,17 +37,38 @@ __global__ void scatter_reduce_kernel(const float* __restrict__ src, int64_t ld_
     if (touched && l == 0) touched[b] = dup ? 0 : 1;
     if (dup) return;
     float n = 1.f;
-    for (int d = l; d < Z; d += 32) {
-        float s = src[(int64_t)b * ld_src + d];
-        for (int j = b + 1; j < B; ++j)
-            if (__ldg(idx + j) == row) s += src[(int64_t)j * ld_src + d];
-        dst[row * Z + d] += s;
+    float s[4];                                           // Z <= 128 handled in registers, larger Z loops below
+    const int nd = (Z + 31) >> 5;
+    if (nd <= 4) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s[i] = (i < nd && l + 32 * i < Z) ? src[(int64_t)b * ld_src + l + 32 * i] : 0.f;
+        for (int j0 = (b + 1) & ~31; j0 < B; j0 += 32) {
+            const int j = j0 + l;
+            unsigned m = __ballot_sync(0xffffffffu, j > b && j < B && __ldg(idx + j) == row);
+            while (m) {
+                const int jj = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                n += 1.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    if (i < nd && l + 32 * i < Z) s[i] += src[(int64_t)jj * ld_src + l + 32 * i];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (i < nd && l + 32 * i < Z) dst[row * Z + l + 32 * i] += s[i];
+    } else {
+        for (int d = l; d < Z; d += 32) {
+            float t = src[(int64_t)b * ld_src + d];
+            for (int j = b + 1; j < B; ++j)
+                if (__ldg(idx + j) == row) t += src[(int64_t)j * ld_src + d];
+            dst[row * Z + d] += t;
+        }
+        if (l == 0)
+            for (int j = b + 1; j < B; ++j)
+                if (__ldg(idx + j) == row) n += 1.f;
     }
-    if (cnt && l == 0) {
-        for (int j = b + 1; j < B; ++j)
-            if (__ldg(idx + j) == row) n += 1.f;
-        cnt[row] += n;
-    }
+    if (cnt && l == 0) cnt[row] += n;
 }
 
 __global__ void mu2_estimate_finish_kernel(const float* __restrict__ zsum, const float* __restrict__ cnt,
@@ -160,10 +183,22 @@ __global__ void __launch_bounds__(1024) colsum_kernel(const __grid_constant__ Co
     const fhvae_colsum_problem& P = cb.p[pi];
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
     const int c = (blockIdx.x - cb.start[pi]) * 32 + l;
-    float s = 0.f;
-    if (c < P.C)
-        for (int r = w; r < P.R; r += 32) s += P.in[(int64_t)r * P.ld + c];
-    red[w][l] = s;
+    // warp w sums rows w, w+32, ...: 8 independent loads in flight per thread (the serial version was bound by
+    // one L2 round trip per row: 43 us for the 5120-row decoder-head bias).  Fixed order => deterministic.
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (c < P.C) {
+        const float* p = P.in + c;
+        int r = w;
+        for (; r + 7 * 32 < P.R; r += 8 * 32) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(p + (int64_t)(r + i * 32) * P.ld);
+            s0 += v[0]; s1 += v[1]; s2 += v[2]; s3 += v[3];
+            s0 += v[4]; s1 += v[5]; s2 += v[6]; s3 += v[7];
+        }
+        for (; r < P.R; r += 32) s0 += __ldg(p + (int64_t)r * P.ld);
+    }
+    red[w][l] = (s0 + s1) + (s2 + s3);
     __syncthreads();
     if (w == 0 && c < P.C) {
         float t = 0.f;
