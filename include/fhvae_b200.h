@@ -234,6 +234,31 @@ int fhvae_relu_bwd(float* dout, const float* out, int64_t n, void* stream);
 /* y = a*x + y */
 int fhvae_axpy(float* y, const float* x, float a, int64_t n, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused latent-head stages between the LSTM stacks (exact fp32, one launch each; heads.cu).
+ * Replaces GaussianLayer.forward (simple_fhvae.py:205-216) on the final hidden states and the hoisted
+ * time-invariant input projection of the next stack, and their autograd.
+ * ------------------------------------------------------------------------------------------- */
+/* head (B,2Z) = [src0 | src1] (B, nsrc*H; rows of leading dim ld_src) @ W^T (2Z x nsrc*H) + bias;
+ * if eps:  zcat[b*ld_z + zoff + d] = mu + eps[b,d]*exp(.5 logvar)   (d < Z);
+ * if Q:    Q (B,NQ) = zcat[b, qoff : qoff+Kq] @ Wq^T (NQ rows of leading dim ld_wq) + bias_q (may be NULL). */
+int fhvae_head_fwd(const float* src0, const float* src1, int64_t ld_src, int nsrc, int H, const float* W,
+                   const float* bias, float* head, int Z, const float* eps, float* zcat, int64_t ld_z, int zoff,
+                   const float* Wq, int64_t ld_wq, const float* bias_q, int qoff, int Kq, float* Q, int NQ, int B,
+                   void* stream);
+/* if dgsum: dzcat[b, dzoff : dzoff+Kq] (+= if beta) = dgsum (B,NG) @ Wq (NG rows of leading dim ld_wq);
+ * if eps:   reparameterisation backward of dzcat[b, roff : roff+Z] into dhead (B,2Z) (fhvae_reparam_bwd);
+ * if W:     dh_l (B,H) = dhead @ W[:, l*H : (l+1)*H]   for l < nsrc   (W: 2Z x nsrc*H). */
+int fhvae_head_bwd(const float* dgsum, int NG, const float* Wq, int64_t ld_wq, int Kq, float* dzcat, int64_t ld_dz,
+                   int dzoff, int beta, const float* head, const float* eps, int Z, int roff, float* dhead,
+                   int accumulate, const float* W, int nsrc, int H, float* dh0, float* dh1, int B, void* stream);
+/* coef (4,B) = [g_px, g_nk1, g_nk2, g_pmu2] from the upstream gradients gout (6,B) of the six forward outputs
+ * (rows: lower_bound, log_px_z, neg_kld_z1, neg_kld_z2, log_pmu2, log_qy; simple_fhvae.py:106-116). */
+int fhvae_step_coef(const float* gout, const int64_t* nsegs, float* coef, int detach_px, int prior_grad, int B,
+                    void* stream);
+/* loss = -mean(lower_bound + alpha*log_qy)   (train_model.py:243-251) */
+int fhvae_loss_mean(const float* lower_bound, const float* log_qy, float alpha, int B, float* loss, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfhvae_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "disc.cu",
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "heads.cu", "disc.cu",
            "table_adam_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -70,6 +70,10 @@ PROTOTYPES = {
     "fhvae_add2": [_p, _p, _p, _l, _p],
     "fhvae_relu_bwd": [_p, _p, _l, _p],
     "fhvae_axpy": [_p, _p, _f, _l, _p],
+    "fhvae_head_fwd": [_p, _p, _l, _i, _i, _p, _p, _p, _i, _p, _p, _l, _i, _p, _l, _p, _i, _i, _p, _i, _i, _p],
+    "fhvae_head_bwd": [_p, _i, _p, _l, _i, _p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _p],
+    "fhvae_step_coef": [_p, _p, _p, _i, _i, _i, _p],
+    "fhvae_loss_mean": [_p, _p, _f, _i, _p, _p],
     "fhvae_version": [],
     "fhvae_built_for_sm": [],
     "fhvae_launch_count": [],

@@ -341,6 +341,7 @@ class _Plan:
         if self.bwd[k] is None:
             self.bwd[k] = self._build_bwd(gflat)
         self.gout.copy_(gout)
+        self._gout_train = None
         if self.m.use_cuda_graphs:
             if self._graph_bwd[k] is None:
                 self._graph_bwd[k] = self._capture(lambda: self.bwd[k].run(current_stream_ptr()))
@@ -359,14 +360,22 @@ class _Plan:
             self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         B = self.B
 
+        # the upstream gradients of a plain train step are constants: filled once, outside the graph
+        if self.__dict__.get("_gout_train") != (alpha, B):
+            self.gout.zero_()
+            self.gout[0].fill_(-1.0 / B)                  # d loss / d lower_bound
+            self.gout[5].fill_(-alpha / B)                # d loss / d log_qy
+            self._gout_train = (alpha, B)
+        if self.__dict__.get("_loss_call") is None or self._loss_call[1] != alpha:
+            lc = CallList()
+            lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss), side=1)
+            self._loss_call = (lc, alpha)
+        loss_call = self._loss_call[0]
+
         def fwd_bwd():
             self.fwd.run(current_stream_ptr())
-            self.gout.zero_()
-            self.gout[0].fill_(-1.0 / B)              # d loss / d lower_bound
-            self.gout[5].fill_(-alpha / B)            # d loss / d log_qy
+            loss_call.run(current_stream_ptr(), join=False)   # side stream 1; joined by the backward list
             self.bwd[k].run(current_stream_ptr())
-            torch.sum(self.out[0] + alpha * self.out[5], dim=0, out=self.loss)
-            self.loss.mul_(-1.0 / B)
 
         def adam():
             optimizer.step_flat(m, gflat)
@@ -423,14 +432,14 @@ class _Plan:
         c, m, B = self.fwd, self.m, self.B
         tab = ptr(m.mu2_table)
         c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N)
+        c.add("fhvae_disc_fwd_partial", ptr(self.z2head), 2 * self.Z2, tab, self.N, self.Z2,
+              ptr(self.part), self.nsplit, B, side=2)
+        c.add("fhvae_disc_target", ptr(self.z2head), 2 * self.Z2, ptr(self.mu2), ptr(self.tgt), B, self.Z2, side=2)
+        c.add("fhvae_disc_combine", ptr(self.part), self.nsplit, ptr(self.tgt), ptr(self.out, 5 * B),
+              ptr(self.lse), B, side=2)
         c.add("fhvae_elbo_fwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
               ptr(self.z2head), ptr(self.mu2), ptr(self.nsegs), ptr(self.out), ptr(self.nan_flag),
               B, self.T, self.F, self.Z1, self.Z2)
-        c.add("fhvae_disc_fwd_partial", ptr(self.z2head), 2 * self.Z2, tab, self.N, self.Z2,
-              ptr(self.part), self.nsplit, B)
-        c.add("fhvae_disc_target", ptr(self.z2head), 2 * self.Z2, ptr(self.mu2), ptr(self.tgt), B, self.Z2)
-        c.add("fhvae_disc_combine", ptr(self.part), self.nsplit, ptr(self.tgt), ptr(self.out, 5 * B),
-              ptr(self.lse), B)
 
     def _tail_bwd(self, c: CallList, gflat, xhead, dxhead, xs_b, xs_t, lv_off):
         """coef from upstream grads; ELBO bwd; disc bwd; table gradient (dense + sparse rows)."""
@@ -446,32 +455,22 @@ class _Plan:
         gout, coef = self.gout, self.coef
         detach_px, prior_grad = m.detach_px, m.prior_grad
 
-        def prep():
-            # out rows: 0 lb, 1 log_px, 2 nk1, 3 nk2, 4 log_pmu2, 5 log_qy
-            torch.add(gout[1:4], gout[0], out=coef[0:3])
-            if detach_px:
-                coef[0].zero_()
-            if prior_grad:
-                self.nsegs_f.copy_(self.nsegs)
-                torch.div(gout[0], self.nsegs_f, out=coef[3])
-                coef[3].add_(gout[4])
-            else:
-                coef[3].zero_()
-        c.torch_op(prep)
+        c.add("fhvae_step_coef", ptr(gout), ptr(self.nsegs), ptr(coef), int(detach_px), int(prior_grad), B)
         dtab = ptr(gflat, m._off["mu2_table"])
         tab = ptr(m.mu2_table)
         c.add("fhvae_elbo_bwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
               ptr(self.z2head), ptr(self.mu2), ptr(coef), ptr(dxhead), ptr(self.dz1head),
               ptr(self.dz2head), ptr(self.dmu2), B, self.T, self.F, self.Z1, Z2)
         g_qy = ptr(gout, 5 * B)
+        # the discriminative / table-gradient chain only meets the main sequence again at the z2 head: side stream 2
         c.add("fhvae_disc_bwd_segs", ptr(self.z2head), 2 * Z2, tab, self.N, Z2, ptr(self.lse),
-              ptr(self.sumpm), self.nsplit, B)
+              ptr(self.sumpm), self.nsplit, B, side=2)
         c.add("fhvae_disc_bwd_rows", ptr(self.z2head), 2 * Z2, tab, self.N, Z2, ptr(self.lse), g_qy,
-              dtab, B)
+              dtab, B, side=2)
         c.add("fhvae_disc_bwd_finish", ptr(self.z2head), 2 * Z2, ptr(self.mu2), ptr(self.sumpm),
-              self.nsplit, g_qy, ptr(self.dz2head), 2 * Z2, ptr(self.dmu2), B, Z2)
+              self.nsplit, g_qy, ptr(self.dz2head), 2 * Z2, ptr(self.dmu2), B, Z2, side=2)
         c.add("fhvae_mu2_scatter_reduce", ptr(self.dmu2), ptr(self.idx), dtab, ptr(self.touched), B, Z2,
-              self.N)
+              self.N, side=2)
 
     def _head_fwd(self, c, srcs, wname, bname, head, Z):
         """head (B,2Z) = sum_l src_l @ W[:, cols_l]^T + b, W = [mulayer.weight ; logvar_layer.weight]."""
@@ -541,11 +540,12 @@ class _FHVAEPlan(_Plan):
         Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
         wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
         wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
-        # both encoders' layer-0 projections of x in one grouped launch
+        # layer-0 projections of x: the z2 encoder's is on the critical path, the z1 encoder's overlaps the
+        # z2 recurrence on side stream 1 (joined before the z1 stack)
         c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z2), F, ptr(self.P["z2", 0]), 4 * Hz2, TB, 4 * Hz2, F,
-                        bias=self._bs("z2", 0)),
-                gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
-                        4 * Hz1, F, bias=self._bs("z1", 0))], mode)
+                        bias=self._bs("z2", 0))], mode)
+        c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
+                        4 * Hz1, F, bias=self._bs("z1", 0))], mode, side=1)
 
         def stack(k, q0):
             H = self.H[k]
@@ -571,23 +571,32 @@ class _FHVAEPlan(_Plan):
             H = self.H[k]
             return [(ptr(self.h[k, l], (T - 1) * B * H), H, H) for l in range(self.L[k])]
 
-        # z2 encoder -> head -> sample (into zcat[:, Z1:])
-        stack("z2", None)
-        self._head_fwd(c, final_h("z2"), "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias",
-                       self.z2head, Z2)
-        c.add("fhvae_reparam_fwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.zcat, Z1), Z1 + Z2, B, Z2)
-        # z1 encoder: time-invariant z2 part of the input projection is done once (Q)
-        c.gemm([gemm_nt(ptr(self.zcat, Z1), Z1 + Z2, m.poff(wih_z1, F), F + Z2, ptr(self.Q["z1"]), 4 * Hz1,
-                        B, 4 * Hz1, Z2)], mode)
-        stack("z1", ptr(self.Q["z1"]))
-        self._head_fwd(c, final_h("z1"), "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias",
-                       self.z1head, Z1)
-        c.add("fhvae_reparam_fwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.zcat), Z1 + Z2, B, Z1)
-        self.n_encode_calls = len(c.calls)
-        # decoder: the whole layer-0 input is time-invariant
         wih_d, _, _, _ = _lstm_names(pre["dec"], 0)
-        c.gemm([gemm_nt(ptr(self.zcat), Z1 + Z2, m.poff(wih_d), Z1 + Z2, ptr(self.Q["dec"]), 4 * Hd, B,
-                        4 * Hd, Z1 + Z2, bias=self._bs("dec", 0))], mode)
+        self.fused_heads = (max(self.L["z2"], self.L["z1"]) <= 2 and 2 * max(Z1, Z2) <= 128 and Z1 + Z2 <= 128
+                            and max(self.L["z2"] * Hz2, self.L["z1"] * Hz1, 4 * Hz1, 4 * Hd) <= 1024
+                            and os.environ.get("FHVAE_FUSED_HEADS", "1") != "0")
+
+        def head_stage(k, H, wname, bname, head, Z, eps, zoff, Wq, ld_wq, bq, qoff, Kq, Q, NQ):
+            """Gaussian head on the final hidden states -> sample -> hoisted projection for the next stack."""
+            if self.fused_heads:
+                src = [ptr(self.h[k, l], (T - 1) * B * H) for l in range(self.L[k])] + [None]
+                c.add("fhvae_head_fwd", src[0], src[1], H, self.L[k], H, m.poff(wname), m.poff(bname), ptr(head), Z,
+                      ptr(eps), ptr(self.zcat), Z1 + Z2, zoff, Wq, ld_wq, bq, qoff, Kq, ptr(Q), NQ, B)
+                return
+            self._head_fwd(c, final_h(k), wname, bname, head, Z)
+            c.add("fhvae_reparam_fwd", ptr(head), 2 * Z, ptr(eps), ptr(self.zcat, zoff), Z1 + Z2, B, Z)
+            c.gemm([gemm_nt(ptr(self.zcat, qoff), Z1 + Z2, Wq, ld_wq, ptr(Q), NQ, B, NQ, Kq, bias=bq or 0)], mode)
+
+        # z2 encoder -> head -> sample (into zcat[:, Z1:]) -> time-invariant z2 part of the z1 encoder's input (Q)
+        stack("z2", None)
+        head_stage("z2", Hz2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias", self.z2head, Z2,
+                   self.eps2, Z1, m.poff(wih_z1, F), F + Z2, None, Z1, Z2, self.Q["z1"], 4 * Hz1)
+        c.join(1)
+        stack("z1", ptr(self.Q["z1"]))
+        # z1 head -> sample -> the decoder's whole (time-invariant) layer-0 input projection
+        head_stage("z1", Hz1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias", self.z1head, Z1,
+                   self.eps1, 0, m.poff(wih_d), Z1 + Z2, self._bs("dec", 0), 0, Z1 + Z2, self.Q["dec"], 4 * Hd)
+        self.n_encode_calls = len(c.calls)
         stack("dec", ptr(self.Q["dec"]))
         Ld = self.L["dec"]
         c.gemm([gemm_nt(ptr(self.h["dec", Ld - 1]), Hd, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
@@ -616,11 +625,14 @@ class _FHVAEPlan(_Plan):
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
         cs: List = []          # bias column sums (one grouped side launch at the end)
 
-        class _Side(list):     # weight-gradient GEMMs: flushed to the side stream right behind their inputs
+        class _Side(list):     # weight-gradient GEMMs + bias column sums: flushed to side stream 1 right behind their inputs
             def flush(self_):
                 if self_:
-                    c.gemm(list(self_), mode, side=True)
+                    c.gemm(list(self_), mode, side=1)
                     self_.clear()
+                if cs:
+                    c.colsum(list(cs), side=1)
+                    cs.clear()
         wg = _Side()
 
         def stack_bwd(k, dh_all_top, dh_last_of):
@@ -670,17 +682,29 @@ class _FHVAEPlan(_Plan):
                     dh_all = ptr(nxt)
                 wg.flush()
 
-        def head_bwd(k, dhead, Z, wname, bname):
-            """dW/db of a Gaussian head on the final hidden states + the dh_last they receive."""
+        def head_bwd(k, dhead, Z, wname, bname, eps=None, head=None, roff=0, dgsum=None, NG=0, Wq=None, ld_wq=0,
+                     Kq=0, dzoff=0, beta=0):
+            """Backward of a latent stage: d(sample) from the consumer stack's hoisted projection (dgsum @ Wq), the
+            reparameterisation into dhead, dW/db of the Gaussian head and the dh_last its final hidden states get."""
             H, L = self.H[k], self.L[k]
+            if self.fused_heads:
+                dh = [ptr(self.dhT[k, l]) for l in range(L)] + [None]
+                c.add("fhvae_head_bwd", dgsum, NG, Wq, ld_wq, Kq, ptr(self.dzcat), Z1 + Z2, dzoff,
+                      beta, ptr(head) if eps is not None else None, ptr(eps) if eps is not None else None, Z, roff,
+                      ptr(dhead), 1, m.poff(wname), L, H, dh[0], dh[1], B)
+            else:
+                if dgsum:
+                    c.gemm([gemm_nn(dgsum, NG, Wq, ld_wq, ptr(self.dzcat, dzoff), Z1 + Z2, B, Kq, NG,
+                                    beta=float(beta))], mode)
+                if eps is not None:
+                    c.add("fhvae_reparam_bwd", ptr(head), 2 * Z, ptr(eps), ptr(self.dzcat, roff), Z1 + Z2,
+                          ptr(dhead), 2 * Z, 1, B, Z)
+                c.gemm([gemm_nn(ptr(dhead), 2 * Z, m.poff(wname, l * H), L * H, ptr(self.dhT[k, l]), H, B, H, 2 * Z)
+                        for l in range(L)], mode)
             cs.append(ColsumProblem(ptr(dhead), g(bname), None, 2 * Z, B, 2 * Z))
-            probs = []
             for l in range(L):
                 hT = ptr(self.h[k, l], (T - 1) * B * H)
                 wg.append(gemm_tn(ptr(dhead), 2 * Z, hT, H, g(wname, l * H), L * H, 2 * Z, H, B))
-                probs.append(gemm_nn(ptr(dhead), 2 * Z, m.poff(wname, l * H), L * H, ptr(self.dhT[k, l]), H,
-                                     B, H, 2 * Z))
-            c.gemm(probs, mode)
 
         # ---------------- decoder
         Hd, Ld = self.H["dec"], self.L["dec"]
@@ -694,10 +718,8 @@ class _FHVAEPlan(_Plan):
             wih_d = _lstm_names(pre["dec"], 0)[0]
             wg.append(gemm_tn(ptr(self.dgsum["dec", 0]), 4 * Hd, ptr(self.zcat), Z1 + Z2, g(wih_d), Z1 + Z2,
                               4 * Hd, Z1 + Z2, B))
-            c.gemm([gemm_nn(ptr(self.dgsum["dec", 0]), 4 * Hd, m.poff(wih_d), Z1 + Z2, ptr(self.dzcat),
-                            Z1 + Z2, B, Z1 + Z2, 4 * Hd)], mode)
-            c.add("fhvae_reparam_bwd", ptr(self.z1head), 2 * Z1, ptr(self.eps1), ptr(self.dzcat), Z1 + Z2,
-                  ptr(self.dz1head), 2 * Z1, 1, B, Z1)
+            z1_from = dict(eps=self.eps1, head=self.z1head, roff=0, dgsum=ptr(self.dgsum["dec", 0]), NG=4 * Hd,
+                           Wq=m.poff(wih_d), ld_wq=Z1 + Z2, Kq=Z1 + Z2, dzoff=0, beta=0)
         else:
             # reference behaviour (simple_fhvae.py:113-115): decoder and z samples get no gradient
             dec_names = [n for n in m._names if n.startswith(("pre_decoder", "dec_gauss_layer"))]
@@ -705,28 +727,27 @@ class _FHVAEPlan(_Plan):
             hi = max(m._off[n] + _prod(m._shape[n]) for n in dec_names)
             c.torch_op(lambda: (gflat[lo:hi].zero_(), self.dzcat.zero_()))
             assert all(lo <= m._off[n] < hi for n in dec_names)
+            z1_from = {}
         # ---------------- z1 encoder
         Hz1 = self.H["z1"]
-        head_bwd("z1", self.dz1head, Z1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias")
+        head_bwd("z1", self.dz1head, Z1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias", **z1_from)
         stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]))
         wih_z1 = _lstm_names(pre["z1"], 0)[0]
         wg.append(gemm_tn(ptr(self.dg["z1", 0]), 4 * Hz1, ptr(self.x_tm), F, g(wih_z1), F + Z2, 4 * Hz1, F, TB))
         wg.append(gemm_tn(ptr(self.dgsum["z1", 0]), 4 * Hz1, ptr(self.zcat, Z1), Z1 + Z2, g(wih_z1, F), F + Z2,
                           4 * Hz1, Z2, B))
-        # dz2_sample = (decoder part, already in dzcat[:, Z1:]) + dQ @ W_z
-        c.gemm([gemm_nn(ptr(self.dgsum["z1", 0]), 4 * Hz1, m.poff(wih_z1, F), F + Z2, ptr(self.dzcat, Z1),
-                        Z1 + Z2, B, Z2, 4 * Hz1, beta=1.0)], mode)
-        c.add("fhvae_reparam_bwd", ptr(self.z2head), 2 * Z2, ptr(self.eps2), ptr(self.dzcat, Z1), Z1 + Z2,
-              ptr(self.dz2head), 2 * Z2, 1, B, Z2)
         # ---------------- z2 encoder
         Hz2 = self.H["z2"]
-        head_bwd("z2", self.dz2head, Z2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias")
+        # dz2_sample = (decoder part, already in dzcat[:, Z1:]) + dQ @ W_z ; dz2head also carries the side-2 chain's part
+        c.join(2)
+        head_bwd("z2", self.dz2head, Z2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias",
+                 eps=self.eps2, head=self.z2head, roff=Z1, dgsum=ptr(self.dgsum["z1", 0]), NG=4 * Hz1, Wq=m.poff(wih_z1, F),
+                 ld_wq=F + Z2, Kq=Z2, dzoff=Z1, beta=1)
         stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]))
         wih_z2 = _lstm_names(pre["z2"], 0)[0]
         wg.append(gemm_tn(ptr(self.dg["z2", 0]), 4 * Hz2, ptr(self.x_tm), F, g(wih_z2), F, 4 * Hz2, F, TB))
         # ---------------- remaining weight gradients + bias gradients (side stream, joined by run())
         wg.flush()
-        c.colsum(cs, side=True)
         return c
 
 
@@ -793,6 +814,7 @@ class _SimplePlan(_Plan):
             self.da = {k: torch.zeros_like(v) for k, v in self.a.items()}
             self.dzcat = f(B, Z1 + Z2)
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * TF, self.F, TF)
+        c.join(2)              # dz2head / dmu2 carry the discriminative chain's part from here on
         wg, cs = [], []
         W = lambda n: n + ".linear.weight"
         Bn = lambda n: n + ".linear.bias"

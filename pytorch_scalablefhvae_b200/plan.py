@@ -37,34 +37,35 @@ def gemm_tn(G, ldg, X, ldx, Cp, ldc, M, N, K, beta=0.0) -> GemmProblem:
 _SIDE_STREAMS = {}
 
 
-def _side_stream(device) -> "torch.cuda.Stream":
-    key = torch.cuda.current_device() if device is None else device
+def _side_stream(device, k: int = 1) -> "torch.cuda.Stream":
+    key = (torch.cuda.current_device() if device is None else device, k)
     if key not in _SIDE_STREAMS:
         _SIDE_STREAMS[key] = torch.cuda.Stream()
     return _SIDE_STREAMS[key]
 
 
 class CallList:
-    """Ordered kernel launches.  Calls tagged ``side=True`` are off the critical path (weight / bias
-    gradients): they are forked onto a second stream behind an event recorded at their position in the
-    main sequence and joined back at the end, so they fill the SMs the 64-CTA cluster recurrence leaves
-    idle.  Works identically eagerly and under CUDA-graph capture (fork/join become graph branches)."""
+    """Ordered kernel launches.  A call tagged ``side=k`` (k = 1, 2; True == 1) is off the critical path: it is
+    forked onto side stream k behind an event recorded at its position in the main sequence (calls on one side
+    stream stay in order), and joined back by ``join(k)`` or at the end of the list.  Stream 1 carries the weight /
+    bias gradients (they fill the SMs the 128-CTA recurrence leaves idle), stream 2 the short discriminative
+    chain.  Works identically eagerly and under CUDA-graph capture (fork/join become graph branches)."""
 
     def __init__(self):
         self.calls = []      # (cfunc, name, args, side)
         self.keep = []       # ctypes arrays / tensors that must outlive the list
 
-    def add(self, name: str, *args, side: bool = False):
-        self.calls.append((_lib.fn(name), name, args, side))
+    def add(self, name: str, *args, side=False):
+        self.calls.append((_lib.fn(name), name, args, int(side)))
 
-    def gemm(self, problems: List[GemmProblem], mode: int, side: bool = False):
+    def gemm(self, problems: List[GemmProblem], mode: int, side=False):
         for i in range(0, len(problems), _lib.GEMM_MAX_BATCH):
             chunk = problems[i:i + _lib.GEMM_MAX_BATCH]
             arr = (GemmProblem * len(chunk))(*chunk)
             self.keep.append(arr)
             self.add("fhvae_gemm_batch", arr, len(chunk), mode, side=side)
 
-    def colsum(self, problems: List[ColsumProblem], side: bool = False):
+    def colsum(self, problems: List[ColsumProblem], side=False):
         for i in range(0, len(problems), _lib.COLSUM_MAX_BATCH):
             chunk = problems[i:i + _lib.COLSUM_MAX_BATCH]
             arr = (ColsumProblem * len(chunk))(*chunk)
@@ -73,19 +74,35 @@ class CallList:
 
     def torch_op(self, f):
         """A host callable (tiny torch ops on static buffers; still graph-capturable)."""
-        self.calls.append((None, "torch", f, False))
+        self.calls.append((None, "torch", f, 0))
 
-    def run(self, stream: int = 0, overlap: bool = True):
+    def join(self, k: int = 1):
+        """The main sequence waits here for everything issued so far on side stream k."""
+        self.calls.append((None, "join", k, 0))
+
+    def run(self, stream: int = 0, overlap: bool = True, join: bool = True):
         main = torch.cuda.current_stream()
         mptr = main.cuda_stream
-        side = None
+        used = {}
+
+        def join_side(k):
+            s = used.pop(k, None)
+            if s is not None:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                main.wait_event(ev)
+
         for f, name, args, on_side in self.calls:
             if f is None:
-                args()
+                if name == "join":
+                    join_side(args)
+                else:
+                    args()
                 continue
             if on_side and overlap:
+                side = used.get(on_side)
                 if side is None:
-                    side = _side_stream(None)
+                    side = used[on_side] = _side_stream(None, on_side)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 side.wait_event(ev)
@@ -94,10 +111,9 @@ class CallList:
                 st = f(*args, mptr)
             if st:
                 _lib.check(st, name)
-        if side is not None:
-            ev = torch.cuda.Event()
-            ev.record(side)
-            main.wait_event(ev)
+        if join:
+            for k in list(used):
+                join_side(k)
 
     def __len__(self):
         return len(self.calls)

@@ -375,6 +375,91 @@ def test_reparam_fwd_bwd():
     assert_close(dh[:, :Z], 1 + g, 1e-6, "dmu"); assert_close(dh[:, Z:], 1 + g * 0.5 * eps * torch.exp(0.5 * head[:, Z:]), 1e-6, "dlv")
 
 
+# ------------------------------------------------------------------------------- fused latent-head stages
+@pytest.mark.parametrize("B,H,L,Z,Kq,NQ,with_q", [(256, 256, 2, 32, 32, 1024, True), (9, 32, 2, 8, 24, 128, True),
+                                                   (33, 64, 1, 16, 16, 256, True), (5, 40, 2, 12, 0, 0, False)])
+def test_head_fwd_matches_fp64(B, H, L, Z, Kq, NQ, with_q):
+    """head = [h_l0 | h_l1] W^T + b ; z = mu + eps exp(lv/2) ; Q = zcat[:, qoff:qoff+Kq] Wq^T + bq
+    (GaussianLayer, simple_fhvae.py:205-216, + the hoisted projection of the next stack)."""
+    hs = [rnd(B, H, seed=10 + l) for l in range(L)]
+    W, b, eps = rnd(2 * Z, L * H, seed=1, scale=0.1), rnd(2 * Z, seed=2), rnd(B, Z, seed=3)
+    ldz, zoff = Z + 24, 24                               # sample lands in zcat[:, 24:24+Z]; Q reads zcat[:, qoff:]
+    zcat = rnd(B, ldz, seed=4)
+    zc0 = zcat.clone()
+    qoff = ldz - Kq
+    ldw = Kq + 7
+    Wq, bq = rnd(max(NQ, 1), ldw, seed=5), rnd(max(NQ, 1), seed=6)
+    head = torch.zeros(B, 2 * Z, device=DEV)
+    Q = torch.zeros(B, max(NQ, 1), device=DEV)
+    call("fhvae_head_fwd", ptr(hs[0]), ptr(hs[1]) if L > 1 else None, H, L, H, ptr(W), ptr(b), ptr(head), Z,
+         ptr(eps), ptr(zcat), ldz, zoff, ptr(Wq, 3) if with_q else None, ldw, ptr(bq) if with_q else None, qoff, Kq,
+         ptr(Q) if with_q else None, NQ, B)
+    hc = torch.cat(hs, 1).double()
+    href = hc @ W.double().t() + b.double()
+    assert_close(head, href, 3e-6, "head")
+    zref = href[:, :Z] + eps.double() * torch.exp(0.5 * href[:, Z:])
+    assert_close(zcat[:, zoff:], zref, 3e-6, "sample")
+    assert torch.equal(zcat[:, :zoff], zc0[:, :zoff])    # nothing outside the sample slice is touched
+    if with_q:
+        zc = zc0.double().clone(); zc[:, zoff:] = zref
+        qref = zc[:, qoff:qoff + Kq] @ Wq[:, 3:3 + Kq].double().t() + bq.double()
+        assert_close(Q, qref, 3e-6, "Q")
+
+
+@pytest.mark.parametrize("B,H,L,Z,NG,Kq,beta", [(256, 256, 2, 32, 1024, 64, 0), (256, 256, 2, 32, 1024, 32, 1),
+                                                 (9, 32, 2, 8, 128, 8, 1), (33, 64, 1, 16, 256, 40, 0)])
+def test_head_bwd_matches_fp64(B, H, L, Z, NG, Kq, beta):
+    dgsum, ldw = rnd(B, NG, seed=1), Kq + 5
+    Wq = rnd(NG, ldw, seed=2, scale=0.1)
+    ldz = max(Kq, Z) + 16
+    dzoff = ldz - Kq
+    roff = ldz - Z                                       # reparam slice inside the freshly written columns
+    dzcat = rnd(B, ldz, seed=3)
+    dz0 = dzcat.clone()
+    head, eps, dhead = rnd(B, 2 * Z, seed=4), rnd(B, Z, seed=5), rnd(B, 2 * Z, seed=6)
+    dh0 = dhead.clone()
+    W = rnd(2 * Z, L * H, seed=7, scale=0.1)
+    dh = [torch.zeros(B, H, device=DEV) for _ in range(L)]
+    call("fhvae_head_bwd", ptr(dgsum), NG, ptr(Wq, 2), ldw, Kq, ptr(dzcat), ldz, dzoff, beta, ptr(head), ptr(eps), Z,
+         roff, ptr(dhead), 1, ptr(W), L, H, ptr(dh[0]), ptr(dh[1]) if L > 1 else None, B)
+    dzr = dz0.double().clone()
+    upd = dgsum.double() @ Wq[:, 2:2 + Kq].double()
+    dzr[:, dzoff:] = upd + (dzr[:, dzoff:] if beta else 0)
+    assert_close(dzcat, dzr, 3e-6, "dzcat")
+    gz = dzr[:, roff:roff + Z]
+    dhr = dh0.double().clone()
+    dhr[:, :Z] += gz
+    dhr[:, Z:] += gz * 0.5 * eps.double() * torch.exp(0.5 * head[:, Z:].double())
+    assert_close(dhead, dhr, 3e-6, "dhead")
+    full = dhr @ W.double()
+    for l in range(L):
+        assert_close(dh[l], full[:, l * H:(l + 1) * H], 3e-6, f"dh_last[{l}]")
+    # head-only form (detach_px path): no dz, no reparam
+    dh2 = [torch.zeros(B, H, device=DEV) for _ in range(L)]
+    call("fhvae_head_bwd", None, 0, None, 0, 0, None, 0, 0, 0, None, None, Z, 0, ptr(dhead), 1, ptr(W), L, H,
+         ptr(dh2[0]), ptr(dh2[1]) if L > 1 else None, B)
+    for l in range(L):
+        assert torch.equal(dh2[l], dh[l])
+
+
+def test_step_coef_and_loss_mean():
+    B = 77
+    gout = rnd(6, B, seed=1)
+    ns = torch.randint(1, 200, (B,), generator=torch.Generator().manual_seed(2)).to(DEV)
+    coef = torch.zeros(4, B, device=DEV)
+    for detach, prior in ((0, 1), (1, 0)):
+        call("fhvae_step_coef", ptr(gout), ptr(ns), ptr(coef), detach, prior, B)
+        ref = torch.stack([gout[1] + gout[0], gout[2] + gout[0], gout[3] + gout[0], gout[0] / ns.float() + gout[4]])
+        if detach:
+            ref[0] = 0
+        if not prior:
+            ref[3] = 0
+        assert torch.equal(coef, ref)
+    loss = torch.zeros((), device=DEV)
+    call("fhvae_loss_mean", ptr(gout), ptr(gout, 5 * B), 10.0, B, ptr(loss))
+    assert_close(loss.reshape(1), -(gout[0].double() + 10.0 * gout[5].double()).mean().reshape(1), 1e-6, "loss")
+
+
 # ------------------------------------------------------------------------------- discriminative term
 @pytest.mark.parametrize("B,N,Z", [(5, 12, 16), (64, 1000, 16), (256, 5000, 32), (33, 129, 8)])
 def test_disc_fwd_bwd(B, N, Z):
