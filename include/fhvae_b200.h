@@ -259,6 +259,34 @@ int fhvae_step_coef(const float* gout, const int64_t* nsegs, float* coef, int de
 /* loss = -mean(lower_bound + alpha*log_qy)   (train_model.py:243-251) */
 int fhvae_loss_mean(const float* lower_bound, const float* log_qy, float alpha, int B, float* loss, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Weight-gradient GEMM from pre-split bf16 planes, TMA-fed (gemm_wgrad.cu).
+ * Replaces the autograd of nn.Linear / nn.LSTM weights for the long contractions (K = T*B rows):
+ *   C[m*ldc + n] = sum_k (A_hi + A_lo)[k][m] * (B_hi + B_lo)[k][n]      (hi*hi + hi*lo + lo*hi, fp32 accumulate)
+ * A, B: bf16, element (plane, k, m) at plane*plane_stride + k*ld + m, plane 0 = hi = bf16(x), plane 1 = lo =
+ * bf16(x - hi); 16-byte aligned, strides multiples of 8 elements.  mode = FHVAE_MODE_BF16X3 (three products) or
+ * FHVAE_MODE_BF16 (hi*hi only).  C is overwritten.
+ * ------------------------------------------------------------------------------------------- */
+#define FHVAE_WGRAD_MAX_BATCH 8
+#define FHVAE_SPLIT_MAX_BATCH 16
+typedef struct fhvae_wgrad_problem {
+    const void* A;
+    const void* B;
+    float*      C;
+    int32_t     M, N, K, reserved;
+    int64_t     lda, a_plane_stride, ldb, b_plane_stride, ldc;
+} fhvae_wgrad_problem;
+int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int n_problems, int mode, void* stream);
+/* dst planes (bf16) <- src (rows x cols fp32, leading dim ld_src): hi at dst[r*ld_dst + c], lo at
+ * dst[plane_stride + r*ld_dst + c].  cols % 8 == 0. */
+typedef struct fhvae_split_problem {
+    const float* src;
+    void*        dst;
+    int64_t      ld_src, ld_dst, plane_stride;
+    int32_t      rows, cols;
+} fhvae_split_problem;
+int fhvae_split_planes_batch(const fhvae_split_problem* problems, int n_problems, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

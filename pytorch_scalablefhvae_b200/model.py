@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ColsumProblem
+from ._lib import ColsumProblem, SplitProblem, WgradProblem
 from .plan import CallList, current_stream_ptr, gemm_nn, gemm_nt, gemm_tn, ptr
 
 PZ2_LOGVAR = math.log(0.5 ** 2)      # simple_fhvae.py:88
@@ -625,8 +625,54 @@ class _FHVAEPlan(_Plan):
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
         cs: List = []          # bias column sums (one grouped side launch at the end)
 
+        # Long-K weight gradients (K = T*B rows) run on the TMA-fed kernel from bf16 hi/lo planes (gemm_wgrad.cu):
+        # the saved activations (h, x) are split once at the start of the backward, each dgates tensor right
+        # behind the BPTT launch that produced it -- all on side stream 1.
+        use_tma = (mode != _lib.MODE_F32_SIMT and os.environ.get("FHVAE_TMA_WGRAD", "1") != "0"
+                   and F % 8 == 0 and all(h % 8 == 0 for h in self.H.values()))
+        if not hasattr(self, "planes"):
+            self.planes = {}
+
+        def planes_of(t: torch.Tensor) -> torch.Tensor:
+            key = t.data_ptr()
+            if key not in self.planes:
+                self.planes[key] = (torch.zeros(2, t.numel(), dtype=torch.bfloat16, device=self.dev), t)
+            return self.planes[key][0]
+
+        def split(ts, side=1):
+            probs = [SplitProblem(ptr(t), planes_of(t).data_ptr(), t.shape[-1], t.shape[-1], t.numel(),
+                                  t.numel() // t.shape[-1], t.shape[-1]) for t in ts]
+            for i in range(0, len(probs), _lib.SPLIT_MAX_BATCH):
+                chunk = probs[i:i + _lib.SPLIT_MAX_BATCH]
+                arr = (SplitProblem * len(chunk))(*chunk)
+                c.keep.append(arr)
+                c.add("fhvae_split_planes_batch", arr, len(chunk), side=side)
+
+        wgp: List = []         # WgradProblem (TMA path)
+        fresh: List = []       # tensors to split right before the next flush (gradients produced by the last launch)
+
+        def wgrad_tn(G, g_row, X, x_row, Cp, ldc, M, N, K, fresh_g=True):
+            """dW (M,N) = G[g_row : g_row+K]^T @ X[x_row : x_row+K]  (G (rows,M), X (rows,N) contiguous fp32)."""
+            if use_tma and K >= 1024:
+                pg, px = planes_of(G), planes_of(X)
+                if fresh_g and all(G is not t for t in fresh):
+                    fresh.append(G)
+                wgp.append(WgradProblem(pg.data_ptr() + 2 * g_row * M, px.data_ptr() + 2 * x_row * N, Cp, M, N, K, 0,
+                                        M, G.numel(), N, X.numel(), ldc))
+            else:
+                wg.append(gemm_tn(ptr(G, g_row * M), M, ptr(X, x_row * N), N, Cp, ldc, M, N, K))
+
         class _Side(list):     # weight-gradient GEMMs + bias column sums: flushed to side stream 1 right behind their inputs
             def flush(self_):
+                if fresh:
+                    split(list(fresh))
+                    fresh.clear()
+                for i in range(0, len(wgp), _lib.WGRAD_MAX_BATCH):
+                    chunk = wgp[i:i + _lib.WGRAD_MAX_BATCH]
+                    arr = (WgradProblem * len(chunk))(*chunk)
+                    c.keep.append(arr)
+                    c.add("fhvae_wgrad_planes_batch", arr, len(chunk), mode, side=1)
+                wgp.clear()
                 if self_:
                     c.gemm(list(self_), mode, side=1)
                     self_.clear()
@@ -634,9 +680,12 @@ class _FHVAEPlan(_Plan):
                     c.colsum(list(cs), side=1)
                     cs.clear()
         wg = _Side()
+        if use_tma and TB >= 1024:
+            split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k])] + [self.x_tm])
 
-        def stack_bwd(k, dh_all_top, dh_last_of):
-            """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum."""
+        def stack_bwd(k, dh_all_top, dh_last_of, extra=None):
+            """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum.  ``extra`` appends
+            the weight gradients that only need this stack's dgates, so that they share its side-stream flush."""
             H = self.H[k]
             dh_all = dh_all_top
             if self.wave[k]:
@@ -652,14 +701,14 @@ class _FHVAEPlan(_Plan):
                 for l in (1, 0):
                     wih, whh, bih, bhh = _lstm_names(pre[k], l)
                     if T > 1:
-                        wg.append(gemm_tn(ptr(self.dg[k, l], B * 4 * H), 4 * H, ptr(self.h[k, l]), H, g(whh), H,
-                                          4 * H, H, (T - 1) * B))
+                        wgrad_tn(self.dg[k, l], B, self.h[k, l], 0, g(whh), H, 4 * H, H, (T - 1) * B)
                     else:
                         c.torch_op(lambda o=m._off[whh], n=4 * H * H: gflat[o:o + n].zero_())
                     cs.append(ColsumProblem(ptr(self.dgsum[k, l]), g(bih), g(bhh), 4 * H, B, 4 * H))
                     if l > 0:
-                        wg.append(gemm_tn(ptr(self.dg[k, l]), 4 * H, ptr(self.h[k, l - 1]), H, g(wih), H,
-                                          4 * H, H, TB))
+                        wgrad_tn(self.dg[k, l], 0, self.h[k, l - 1], 0, g(wih), H, 4 * H, H, TB)
+                if extra:
+                    extra()
                 wg.flush()
                 return
             for l in reversed(range(self.L[k])):
@@ -669,17 +718,17 @@ class _FHVAEPlan(_Plan):
                       ptr(self.dc), T, B, H, mode)
                 # dW_hh = dg[1:]^T @ h[:-1]
                 if T > 1:
-                    wg.append(gemm_tn(ptr(self.dg[k, l], B * 4 * H), 4 * H, ptr(self.h[k, l]), H, g(whh), H,
-                                      4 * H, H, (T - 1) * B))
+                    wgrad_tn(self.dg[k, l], B, self.h[k, l], 0, g(whh), H, 4 * H, H, (T - 1) * B)
                 else:
                     c.torch_op(lambda o=m._off[whh], n=4 * H * H: gflat[o:o + n].zero_())
                 cs.append(ColsumProblem(ptr(self.dgsum[k, l]), g(bih), g(bhh), 4 * H, B, 4 * H))
                 if l > 0:
-                    wg.append(gemm_tn(ptr(self.dg[k, l]), 4 * H, ptr(self.h[k, l - 1]), H, g(wih), H,
-                                      4 * H, H, TB))
+                    wgrad_tn(self.dg[k, l], 0, self.h[k, l - 1], 0, g(wih), H, 4 * H, H, TB)
                     nxt = self.dhA if dh_all != ptr(self.dhA) else self.dhB
                     c.gemm([gemm_nn(ptr(self.dg[k, l]), 4 * H, m.poff(wih), H, ptr(nxt), H, TB, H, 4 * H)], mode)
                     dh_all = ptr(nxt)
+                if extra and l == 0:
+                    extra()
                 wg.flush()
 
         def head_bwd(k, dhead, Z, wname, bname, eps=None, head=None, roff=0, dgsum=None, NG=0, Wq=None, ld_wq=0,
@@ -709,8 +758,7 @@ class _FHVAEPlan(_Plan):
         # ---------------- decoder
         Hd, Ld = self.H["dec"], self.L["dec"]
         if not m.detach_px:
-            wg.append(gemm_tn(ptr(self.dxhead), 2 * F, ptr(self.h["dec", Ld - 1]), Hd,
-                              g("dec_gauss_layer.mulayer.weight"), Hd, 2 * F, Hd, TB))
+            wgrad_tn(self.dxhead, 0, self.h["dec", Ld - 1], 0, g("dec_gauss_layer.mulayer.weight"), Hd, 2 * F, Hd, TB)
             cs.append(ColsumProblem(ptr(self.dxhead), g("dec_gauss_layer.mulayer.bias"), None, 2 * F, TB, 2 * F))
             c.gemm([gemm_nn(ptr(self.dxhead), 2 * F, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
                             ptr(self.dhA), Hd, TB, Hd, 2 * F)], mode)
@@ -731,11 +779,13 @@ class _FHVAEPlan(_Plan):
         # ---------------- z1 encoder
         Hz1 = self.H["z1"]
         head_bwd("z1", self.dz1head, Z1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias", **z1_from)
-        stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]))
         wih_z1 = _lstm_names(pre["z1"], 0)[0]
-        wg.append(gemm_tn(ptr(self.dg["z1", 0]), 4 * Hz1, ptr(self.x_tm), F, g(wih_z1), F + Z2, 4 * Hz1, F, TB))
-        wg.append(gemm_tn(ptr(self.dgsum["z1", 0]), 4 * Hz1, ptr(self.zcat, Z1), Z1 + Z2, g(wih_z1, F), F + Z2,
-                          4 * Hz1, Z2, B))
+
+        def z1_extra():
+            wgrad_tn(self.dg["z1", 0], 0, self.x_tm, 0, g(wih_z1), F + Z2, 4 * Hz1, F, TB)
+            wg.append(gemm_tn(ptr(self.dgsum["z1", 0]), 4 * Hz1, ptr(self.zcat, Z1), Z1 + Z2, g(wih_z1, F), F + Z2,
+                              4 * Hz1, Z2, B))
+        stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]), extra=z1_extra)
         # ---------------- z2 encoder
         Hz2 = self.H["z2"]
         # dz2_sample = (decoder part, already in dzcat[:, Z1:]) + dQ @ W_z ; dz2head also carries the side-2 chain's part
@@ -743,10 +793,9 @@ class _FHVAEPlan(_Plan):
         head_bwd("z2", self.dz2head, Z2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias",
                  eps=self.eps2, head=self.z2head, roff=Z1, dgsum=ptr(self.dgsum["z1", 0]), NG=4 * Hz1, Wq=m.poff(wih_z1, F),
                  ld_wq=F + Z2, Kq=Z2, dzoff=Z1, beta=1)
-        stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]))
         wih_z2 = _lstm_names(pre["z2"], 0)[0]
-        wg.append(gemm_tn(ptr(self.dg["z2", 0]), 4 * Hz2, ptr(self.x_tm), F, g(wih_z2), F, 4 * Hz2, F, TB))
-        # ---------------- remaining weight gradients + bias gradients (side stream, joined by run())
+        stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]),
+                  extra=lambda: wgrad_tn(self.dg["z2", 0], 0, self.x_tm, 0, g(wih_z2), F, 4 * Hz2, F, TB))
         wg.flush()
         return c
 

@@ -8,7 +8,7 @@ import torch
 
 from oracle import fhvae_oracle as O
 from pytorch_scalablefhvae_b200 import _lib
-from pytorch_scalablefhvae_b200._lib import ColsumProblem, GemmProblem
+from pytorch_scalablefhvae_b200._lib import ColsumProblem, GemmProblem, SplitProblem, WgradProblem
 from pytorch_scalablefhvae_b200.plan import ptr
 from util import FP32_RTOL, assert_close, call, gemm, relerr
 
@@ -117,6 +117,62 @@ def test_gemm_tc_grouped_mixed():
     call("fhvae_gemm_batch", (GemmProblem * 4)(*probs), 4, 1)
     for i in range(4):
         assert_close(keep[3 * i + 2], refs[i], 2e-5, f"group {i}")
+
+
+# ------------------------------------------------------------------------------- TMA weight-gradient GEMM on bf16 planes
+def _planes(x):
+    """(rows, cols) fp32 -> (2, rows, cols) bf16 planes through the library's split kernel"""
+    rows, cols = x.shape
+    ps = (rows * cols + 7) // 8 * 8                      # plane stride: multiple of 8 elements
+    dst = torch.zeros(2, ps, dtype=torch.bfloat16, device=DEV)
+    p = SplitProblem(ptr(x), dst.data_ptr(), x.stride(0), cols, ps, rows, cols)
+    call("fhvae_split_planes_batch", (SplitProblem * 1)(p), 1)
+    return dst[:, :rows * cols].view(2, rows, cols), dst, ps
+
+
+def test_split_planes_exact():
+    x = rnd(77, 40, seed=1, scale=3.0)
+    pl = _planes(x)[0]
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    assert torch.equal(pl[0], hi) and torch.equal(pl[1], lo)
+    # strided source (a column slice of a wider matrix)
+    w = rnd(33, 64, seed=2)
+    pl2 = _planes(w[:, 16:48])[0]
+    assert torch.equal(pl2[0], w[:, 16:48].to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K,mode,tol", [(1024, 256, 5120, 1, 2e-5), (1024, 256, 4864, 1, 2e-5), (1024, 80, 5120, 1, 2e-5),
+                                           (160, 256, 5120, 1, 2e-5), (64, 256, 256, 1, 2e-5), (72, 24, 100, 1, 2e-5),
+                                           (304, 520, 333, 1, 2e-5), (1024, 256, 5120, 2, 1e-2)])
+def test_wgrad_planes_matches_fp64(M, N, K, mode, tol):
+    """C = A^T B from pre-split planes (hi*hi + hi*lo + lo*hi) against fp64, ragged M/N/K and split-K included."""
+    A, Bm = rnd(K, M, seed=1), rnd(K, N, seed=2)
+    (_, pa, psa), (_, pb, psb) = _planes(A), _planes(Bm)
+    ldc = N + 4
+    Cc = torch.full((M, ldc), 7.0, device=DEV)
+    p = WgradProblem(pa.data_ptr(), pb.data_ptr(), ptr(Cc), M, N, K, 0, M, psa, N, psb, ldc)
+    call("fhvae_wgrad_planes_batch", (WgradProblem * 1)(p), 1, mode)
+    ref = A.double().t() @ Bm.double()
+    assert_close(Cc[:, :N], ref, tol, f"wgrad_planes {M}x{N}x{K}")
+    assert torch.all(Cc[:, N:] == 7.0)                   # nothing outside the N columns is touched
+
+
+def test_wgrad_planes_grouped_and_shifted():
+    """One launch, several problems, including the dW_hh form: A rows shifted by one time step against B."""
+    T, Bt, H = 6, 64, 256
+    dg, h, x = rnd(T * Bt, 4 * H, seed=1), rnd(T * Bt, H, seed=2), rnd(T * Bt, 80, seed=3)
+    (_, pdg, ps_dg), (_, ph, ps_h), (_, px, ps_x) = _planes(dg), _planes(h), _planes(x)
+    c_hh, c_ih, c_x = (torch.zeros(4 * H, H, device=DEV), torch.zeros(4 * H, H, device=DEV), torch.zeros(4 * H, 112, device=DEV))
+    e = 2                                                 # bytes per bf16
+    probs = [WgradProblem(pdg.data_ptr() + Bt * 4 * H * e, ph.data_ptr(), ptr(c_hh), 4 * H, H, (T - 1) * Bt, 0, 4 * H, ps_dg, H, ps_h, H),
+             WgradProblem(pdg.data_ptr(), ph.data_ptr(), ptr(c_ih), 4 * H, H, T * Bt, 0, 4 * H, ps_dg, H, ps_h, H),
+             WgradProblem(pdg.data_ptr(), px.data_ptr(), ptr(c_x), 4 * H, 80, T * Bt, 0, 4 * H, ps_dg, 80, ps_x, 112)]
+    call("fhvae_wgrad_planes_batch", (WgradProblem * 3)(*probs), 3, 1)
+    assert_close(c_hh, dg[Bt:].double().t() @ h[:-Bt].double(), 2e-5, "dW_hh")
+    assert_close(c_ih, dg.double().t() @ h.double(), 2e-5, "dW_ih")
+    assert_close(c_x[:, :80], dg.double().t() @ x.double(), 2e-5, "dW_x")
+    assert torch.all(c_x[:, 80:] == 0)
 
 
 # ------------------------------------------------------------------------------- LSTM
