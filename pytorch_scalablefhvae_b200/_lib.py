@@ -59,6 +59,8 @@ PROTOTYPES = {
     "fhvae_lstm_wave_xchg_bytes": [_i, _i, _i, _i],
     "fhvae_lstm_wave_fwd": [_p] * 13 + [_i, _i, _i, _i, _i, _p],
     "fhvae_lstm_wave_bwd_xchg_bytes": [_i, _i, _i, _i],
+    "fhvae_lstm_wave_fwd_planes": [_p] * 15 + [_l, _i, _i, _i, _i, _i, _p],
+    "fhvae_lstm_wave_bwd_planes": [_p] * 17 + [_l, _i, _i, _i, _i, _i, _p],
     "fhvae_lstm_wave_bwd": [_p] * 15 + [_i, _i, _i, _i, _i, _p],
     "fhvae_reparam_fwd": [_p, _l, _p, _p, _l, _i, _i, _p],
     "fhvae_reparam_bwd": [_p, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p],

@@ -74,6 +74,7 @@ struct WaveFwdArgs {
     const float* Wih1; const float* b1; const float* Whh1; float* h1; float* c1; float* a1;
     uint4* xchg;
     int T, B, b_off, G, Gs, L;     // B = row stride (whole batch), G groups in this launch, Gs = slot stride
+    __nv_bfloat16* hp0; __nv_bfloat16* hp1; long long hps;   // optional bf16 hi/lo planes of h (lo at +hps), for gemm_wgrad.cu
 };
 
 template <bool X3>
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     const float* Q = layer ? nullptr : a.Q0;
     const float* W_hh = layer ? a.Whh1 : a.Whh0;
     float* h_all = layer ? a.h1 : a.h0;
+    __nv_bfloat16* h_pl = layer ? a.hp1 : a.hp0;
     float* c_all = layer ? a.c1 : a.c0;
     float* acts = layer ? a.a1 : a.a0;
     // exchange buffer: [header][h: layer][group][t][src CTA][WSLICE] uint4, then [p1: group][t][CTA][WPSLICE]
@@ -324,6 +326,11 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 const size_t o = ((size_t)ts * B + b0 + warp * RPT + i) * CH + kglob;
                 h_all[o] = hreg[i];
                 c_all[o] = creg[i];
+                if (h_pl) {                                   // x = hi + lo planes: the weight-gradient GEMM's TMA operand
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(hreg[i]);
+                    h_pl[o] = hh;
+                    h_pl[o + a.hps] = __float2bfloat16_rn(hreg[i] - __bfloat162float(hh));
+                }
             }
         };
 
@@ -467,6 +474,7 @@ struct WaveBwdArgs {
     const float* Whh0; const float* c0; const float* a0; float* dg0; float* dgsum0;   // bottom layer
     uint4* xchg;
     int T, B, b_off, G, Gs, L;
+    __nv_bfloat16* dgp1; __nv_bfloat16* dgp0; long long dgps;   // optional bf16 hi/lo planes of dgates (lo at +dgps)
 };
 
 template <bool X3>
@@ -514,6 +522,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     const float* c_all = bottom ? a.c0 : a.c1;
     const float* acts = bottom ? a.a0 : a.a1;
     float* dgates = bottom ? a.dg0 : a.dg1;
+    __nv_bfloat16* dg_pl = bottom ? a.dgp0 : a.dgp1;
     float* dgsum = bottom ? a.dgsum0 : a.dgsum1;
     const float* dh_all = bottom ? nullptr : a.dh_all;
     const float* dh_last = bottom ? a.dh_last0 : a.dh_last1;
@@ -696,9 +705,19 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
         auto store_dg = [&](int ts) {
 #pragma unroll
             for (int i = 0; i < RPT; ++i) {
-                float* dg = dgates + ((size_t)ts * B + b0 + warp * RPT + i) * H4 + ucol;
+                const size_t o = ((size_t)ts * B + b0 + warp * RPT + i) * H4 + ucol;
+                if (dgates) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g) dg[g * CH] = gkeep[g][i];
+                    for (int g = 0; g < 4; ++g) dgates[o + g * CH] = gkeep[g][i];
+                }
+                if (dg_pl) {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) {
+                        const __nv_bfloat16 hh = __float2bfloat16_rn(gkeep[g][i]);
+                        dg_pl[o + g * CH] = hh;
+                        dg_pl[o + g * CH + a.dgps] = __float2bfloat16_rn(gkeep[g][i] - __bfloat162float(hh));
+                    }
+                }
             }
         };
         uint32_t nwait = 0;
@@ -857,8 +876,9 @@ static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
 
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
-                  void* xchg, int T, int B, int L, int mode, cudaStream_t st) {
-    WaveFwdArgs a{P0, Q0, Whh0, h0, c0, a0, Wih1, b1, Whh1, h1, c1, a1, reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L};
+                  void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0, void* hp1, long long hps) {
+    WaveFwdArgs a{P0, Q0, Whh0, h0, c0, a0, Wih1, b1, Whh1, h1, c1, a1, reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
+                  reinterpret_cast<__nv_bfloat16*>(hp0), reinterpret_cast<__nv_bfloat16*>(hp1), hps};
     return mode == FHVAE_MODE_BF16X3 ? launch_wave_fwd<true>(a, st) : launch_wave_fwd<false>(a, st);
 }
 
@@ -895,9 +915,11 @@ static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
 
 int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
                   const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
-                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st) {
+                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st,
+                  void* dgp1, void* dgp0, long long dgps) {
     WaveBwdArgs a{dh_all, dh_last1, dh_last0, Whh1, c1, a1, dg1, dgsum1, Wih1, Whh0, c0, a0, dg0, dgsum0,
-                  reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L};
+                  reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
+                  reinterpret_cast<__nv_bfloat16*>(dgp1), reinterpret_cast<__nv_bfloat16*>(dgp0), dgps};
     return mode == FHVAE_MODE_BF16X3 ? launch_wave_bwd<true>(a, st) : launch_wave_bwd<false>(a, st);
 }
 

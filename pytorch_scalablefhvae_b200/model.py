@@ -516,10 +516,23 @@ class _FHVAEPlan(_Plan):
                 self.acts[k, l] = f(T, B, 4 * H)
                 if not (k == "dec" and l == 0) and not (self.wave[k] and l == 1):
                     self.P[k, l] = f(T, B, 4 * H)
+        # Long-K weight gradients (K = T*B rows) run on the TMA-fed kernel from bf16 hi/lo planes (gemm_wgrad.cu).
+        # Wavefront stacks write the planes of h (forward) and dgates (backward) themselves; everything else
+        # (x, non-wave stacks, the decoder-head gradient) goes through fhvae_split_planes_batch.
+        self.tma_wgrad = (self.mode != _lib.MODE_F32_SIMT and os.environ.get("FHVAE_TMA_WGRAD", "1") != "0"
+                          and F % 8 == 0 and all(h % 8 == 0 for h in self.H.values()) and (T - 1) * B >= 1024)
+        self.planes = {}
         self.Q = {"z1": f(B, 4 * self.H["z1"]), "dec": f(B, 4 * self.H["dec"])}
         self.xchg = f(16, B, max(self.H.values()))      # L2-resident exchange scratch of the cluster kernels
         self.xhead = f(T, B, 2 * F)
         self._build_fwd()
+
+    def planes_of(self, t: torch.Tensor) -> torch.Tensor:
+        """bf16 (2, numel) hi/lo planes that shadow the fp32 tensor t (allocated on first use)."""
+        key = t.data_ptr()
+        if key not in self.planes:
+            self.planes[key] = (torch.zeros(2, t.numel(), dtype=torch.bfloat16, device=self.dev), t)
+        return self.planes[key][0]
 
     def px_views(self):
         F = self.F
@@ -552,10 +565,11 @@ class _FHVAEPlan(_Plan):
             if self.wave[k]:
                 _, whh0, _, _ = _lstm_names(pre[k], 0)
                 wih1, whh1, _, _ = _lstm_names(pre[k], 1)
-                c.add("fhvae_lstm_wave_fwd", ptr(self.P[k, 0]) if (k, 0) in self.P else None, q0, m.poff(whh0),
+                hp = [self.planes_of(self.h[k, l]).data_ptr() if self.tma_wgrad else None for l in (0, 1)]
+                c.add("fhvae_lstm_wave_fwd_planes", ptr(self.P[k, 0]) if (k, 0) in self.P else None, q0, m.poff(whh0),
                       ptr(self.h[k, 0]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), m.poff(wih1), self._bs(k, 1),
                       m.poff(whh1), ptr(self.h[k, 1]), ptr(self.c[k, 1]), ptr(self.acts[k, 1]),
-                      ptr(self.wave_xchg), T, B, H, 2, mode)
+                      ptr(self.wave_xchg), hp[0], hp[1], T * B * H, T, B, H, 2, mode)
                 return
             for l in range(self.L[k]):
                 wih, whh, _, _ = _lstm_names(pre[k], l)
@@ -625,19 +639,9 @@ class _FHVAEPlan(_Plan):
         self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
         cs: List = []          # bias column sums (one grouped side launch at the end)
 
-        # Long-K weight gradients (K = T*B rows) run on the TMA-fed kernel from bf16 hi/lo planes (gemm_wgrad.cu):
-        # the saved activations (h, x) are split once at the start of the backward, each dgates tensor right
-        # behind the BPTT launch that produced it -- all on side stream 1.
-        use_tma = (mode != _lib.MODE_F32_SIMT and os.environ.get("FHVAE_TMA_WGRAD", "1") != "0"
-                   and F % 8 == 0 and all(h % 8 == 0 for h in self.H.values()))
-        if not hasattr(self, "planes"):
-            self.planes = {}
-
-        def planes_of(t: torch.Tensor) -> torch.Tensor:
-            key = t.data_ptr()
-            if key not in self.planes:
-                self.planes[key] = (torch.zeros(2, t.numel(), dtype=torch.bfloat16, device=self.dev), t)
-            return self.planes[key][0]
+        use_tma = self.tma_wgrad
+        planes_of = self.planes_of
+        made = set()           # fp32 tensors whose planes are written by the kernel that produces them
 
         def split(ts, side=1):
             probs = [SplitProblem(ptr(t), planes_of(t).data_ptr(), t.shape[-1], t.shape[-1], t.numel(),
@@ -655,7 +659,7 @@ class _FHVAEPlan(_Plan):
             """dW (M,N) = G[g_row : g_row+K]^T @ X[x_row : x_row+K]  (G (rows,M), X (rows,N) contiguous fp32)."""
             if use_tma and K >= 1024:
                 pg, px = planes_of(G), planes_of(X)
-                if fresh_g and all(G is not t for t in fresh):
+                if fresh_g and G.data_ptr() not in made and all(G is not t for t in fresh):
                     fresh.append(G)
                 wgp.append(WgradProblem(pg.data_ptr() + 2 * g_row * M, px.data_ptr() + 2 * x_row * N, Cp, M, N, K, 0,
                                         M, G.numel(), N, X.numel(), ldc))
@@ -677,11 +681,11 @@ class _FHVAEPlan(_Plan):
                     c.gemm(list(self_), mode, side=1)
                     self_.clear()
                 if cs:
-                    c.colsum(list(cs), side=1)
+                    c.colsum(list(cs), side=2)     # tiny, latency-bound: next to, not behind, the GEMMs
                     cs.clear()
         wg = _Side()
-        if use_tma and TB >= 1024:
-            split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k])] + [self.x_tm])
+        if use_tma:
+            split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k]) if not self.wave[k]] + [self.x_tm])
 
         def stack_bwd(k, dh_all_top, dh_last_of, extra=None):
             """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum.  ``extra`` appends
@@ -694,10 +698,15 @@ class _FHVAEPlan(_Plan):
                     nbytes = _lib.fn("fhvae_lstm_wave_bwd_xchg_bytes")(T, B, H, 2)
                     self.wave_xchg_bwd = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)
                 n0, n1 = _lstm_names(pre[k], 0), _lstm_names(pre[k], 1)
-                c.add("fhvae_lstm_wave_bwd", dh_all_top, dh_last_of(1), dh_last_of(0), m.poff(n1[1]),
-                      ptr(self.c[k, 1]), ptr(self.acts[k, 1]), ptr(self.dg[k, 1]), ptr(self.dgsum[k, 1]),
-                      m.poff(n1[0]), m.poff(n0[1]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), ptr(self.dg[k, 0]),
-                      ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd), T, B, H, 2, mode)
+                dgp = [planes_of(self.dg[k, l]).data_ptr() if use_tma else None for l in (0, 1)]
+                if use_tma:
+                    made.update(self.dg[k, l].data_ptr() for l in (0, 1))
+                # with the planes as output the fp32 dgates are never read again: not written at all
+                c.add("fhvae_lstm_wave_bwd_planes", dh_all_top, dh_last_of(1), dh_last_of(0), m.poff(n1[1]),
+                      ptr(self.c[k, 1]), ptr(self.acts[k, 1]), None if use_tma else ptr(self.dg[k, 1]),
+                      ptr(self.dgsum[k, 1]), m.poff(n1[0]), m.poff(n0[1]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]),
+                      None if use_tma else ptr(self.dg[k, 0]), ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd),
+                      dgp[1], dgp[0], T * B * 4 * H, T, B, H, 2, mode)
                 for l in (1, 0):
                     wih, whh, bih, bhh = _lstm_names(pre[k], l)
                     if T > 1:
@@ -754,6 +763,7 @@ class _FHVAEPlan(_Plan):
             for l in range(L):
                 hT = ptr(self.h[k, l], (T - 1) * B * H)
                 wg.append(gemm_tn(ptr(dhead), 2 * Z, hT, H, g(wname, l * H), L * H, 2 * Z, H, B))
+            wg.flush()         # everything queued so far is ready: runs beside this stack's BPTT, not after it
 
         # ---------------- decoder
         Hd, Ld = self.H["dec"], self.L["dec"]

@@ -298,6 +298,19 @@ def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
         for l in range(L):
             for a, b, n in zip(out[l], ref[l], ["h_all", "c_all", "acts"]):
                 assert_close(a, b, TC_TOL[mode], f"layer {l} {n} mode {mode} rep {rep}")
+    # same launch with the bf16 hi/lo planes of h as extra outputs (TMA operands of the weight-gradient GEMM):
+    # fp32 outputs unchanged bit for bit, planes == split of the fp32 h
+    out2 = [[f(T, B, H), f(T, B, H), f(T, B, 4 * H)] for _ in range(2)]
+    hp = [torch.zeros(2, T * B * H, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
+    l1 = [ptr(Wi1), ptr(b1), ptr(W1), ptr(out2[1][0]), ptr(out2[1][1]), ptr(out2[1][2])] if L == 2 else [None] * 6
+    call("fhvae_lstm_wave_fwd_planes", ptr(P), ptr(Q), ptr(W0), ptr(out2[0][0]), ptr(out2[0][1]), ptr(out2[0][2]), *l1,
+         ptr(xchg), hp[0].data_ptr(), hp[1].data_ptr() if L == 2 else None, T * B * H, T, B, H, L, mode)
+    torch.cuda.synchronize()
+    for l in range(L):
+        assert torch.equal(out2[l][0], out[l][0]) and torch.equal(out2[l][2], out[l][2])
+        hi = out2[l][0].reshape(-1).to(torch.bfloat16)
+        assert torch.equal(hp[l][0], hi)
+        assert torch.equal(hp[l][1], (out2[l][0].reshape(-1) - hi.float()).to(torch.bfloat16))
 
 
 @pytest.mark.parametrize("mode", [1, 2])
@@ -348,6 +361,19 @@ def test_lstm_wave_bwd_matches_simt(T, B, L, use_all, use_last, repeat, mode):
         for l in range(L):
             assert_close(dg[l], rdg[l], TC_TOL[mode], f"layer {l} dgates mode {mode} rep {rep}")
             assert_close(dgs[l], rsum[l], TC_TOL[mode], f"layer {l} dgsum mode {mode} rep {rep}")
+    # planes-only form: fp32 dgates not written at all, planes == split of the fp32 dgates of the plain launch
+    dgp = [torch.zeros(2, T * B * 4 * H, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
+    dgs2 = [f(B, 4 * H), f(B, 4 * H)]
+    bot = ([ptr(Wi1), ptr(W0), ptr(st[0][1]), ptr(st[0][2]), None, ptr(dgs2[0])] if L == 2 else [None] * 6)
+    call("fhvae_lstm_wave_bwd_planes", pa, pl, ptr(dh_last0) if L == 2 else None, ptr(Wtop), ptr(st[top][1]),
+         ptr(st[top][2]), None, ptr(dgs2[top]), *bot, ptr(xchg), dgp[top].data_ptr(),
+         dgp[0].data_ptr() if L == 2 else None, T * B * 4 * H, T, B, H, L, mode)
+    torch.cuda.synchronize()
+    for l in range(L):
+        hi = dg[l].reshape(-1).to(torch.bfloat16)
+        assert torch.equal(dgp[l][0], hi), f"layer {l} dgates hi plane"
+        assert torch.equal(dgp[l][1], (dg[l].reshape(-1) - hi.float()).to(torch.bfloat16)), f"layer {l} dgates lo plane"
+        assert torch.equal(dgs2[l], dgs[l])
 
 
 def test_lstm_null_inputs():
