@@ -325,7 +325,20 @@ def dominant_kernel_roofline(m, P, xd, idd, nsd, opt, args):
     pk = peaks()
     H, T, B = c["H"], c["T"], c["B"]
     top = max(fam.items(), key=lambda kv: kv[1][0])[0]
-    if top in ("fhvae_lstm_fwd", "fhvae_lstm_bwd"):
+    if top.startswith("fhvae_lstm_wave"):
+        # one call = one 2-layer stack, T wavefront steps: two recurrent products (h W_hh^T, or dgates W_hh) and the
+        # in-kernel cross-layer product (layer-1 input projection / its data gradient), 2*B*4H*H flops each per step.
+        # Canonical single-pass count; the bf16x3 mode issues three tcgen05.mma per product.
+        calls = fam[top][1] / reps
+        ms_call = fam[top][0] / reps / calls
+        flops = 3 * 2.0 * B * 4 * H * H * T
+        ach = flops / (ms_call * 1e-3) / 1e12
+        roof = {"kernel": top + " (one 2-layer LSTM stack, T dependent wavefront steps, 128 CTAs)", "bound": "tensor",
+                "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"], "traffic": None,
+                "avg_call_ms": ms_call, "peak_kind": "bf16 sustained, " + pk["src"],
+                "note": "latency-bound recurrence: T strictly dependent steps of a 256x1024x256 product; "
+                        "canonical flops (x3 MMAs executed in bf16x3 mode)"}
+    elif top in ("fhvae_lstm_fwd", "fhvae_lstm_bwd"):
         # one call = T recurrent steps of one layer: 2 * B * 4H * H flops per step (fwd: h W_hh^T, bwd: dg W_hh)
         calls = fam[top][1] / reps
         ms_call = fam[top][0] / reps / calls
@@ -343,6 +356,18 @@ def dominant_kernel_roofline(m, P, xd, idd, nsd, opt, args):
         roof = {"kernel": "fhvae_gemm_batch (all grouped GEMM launches of the step)", "bound": "tensor",
                 "achieved": ach, "peak": pk["tf_sus"], "unit": "TFLOP/s", "frac": ach / pk["tf_sus"],
                 "traffic": None, "peak_kind": "bf16 sustained, " + pk["src"]}
+    wg = fam.get("fhvae_wgrad_planes_batch")
+    if wg:
+        # executed MMA work of the weight gradients: 3 stacks x (3 x [4H,H,TB] + [4H,F or 2F->H...]) -- counted from the
+        # plan's problems: per stack 3*H + F (z1,z2) or 3*H + 2F*H/(4H) (decoder head) columns of a [4H x TB] contraction
+        cols = 3 * (3 * H) + 2 * c["F"] + (2 * c["F"]) * H / (4.0 * H)
+        canon = 2.0 * 4 * H * T * B * cols
+        passes = 3 if args.mode == "bf16x3" else 1
+        t_s = wg[0] / reps * 1e-3
+        roof["wgrad_gemm"] = {"kernel": "wgrad_tma_kernel (fhvae_wgrad_planes_batch, all launches of the step)",
+                              "ms_per_step": wg[0] / reps, "canonical_tflops": canon / t_s / 1e12,
+                              "executed_mma_tflops": passes * canon / t_s / 1e12,
+                              "executed_frac_of_bf16_sustained": passes * canon / t_s / 1e12 / pk["tf_sus"]}
     if args.breakdown:
         sys.stderr.write(json.dumps(breakdown, indent=1) + "\n")
     return roof, breakdown

@@ -187,10 +187,10 @@ class _FHVAECore(nn.Module):
         if grad_on:
             if self._anchor is None or self._anchor.device != x.device:
                 self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
-            out = _StepFn.apply(self, plan, self._anchor, *self._plist)
+            out = _StepFn.apply(self, plan, self._anchor, *self._plist)     # six (B,) rows of one buffer
         else:
             plan.run_forward()
-            out = plan.out.clone()
+            out = plan.out.clone().unbind(0)
         self._publish(plan)
         lb, log_qy, log_px_z, nk1, nk2, log_pmu2 = (out[i] for i in _OUT_ORDER)
         if self.ref_log_qy:                      # reference returns mean(+CE) (simple_fhvae.py:37,122)
@@ -250,17 +250,39 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, model, plan, anchor, *params):
         plan.run_forward()
         ctx.model, ctx.plan = model, plan
-        return plan.out.clone()               # (6,B): lb, log_px, nk1, nk2, log_pmu2, log_qy
+        ctx.set_materialize_grads(False)      # unused outputs arrive as None instead of zero tensors
+        # rows of the (6,B) buffer: lb, log_px, nk1, nk2, log_pmu2, log_qy -- returned as six outputs so that
+        # autograd hands their gradients straight back (no per-row SelectBackward zeros + copy)
+        return tuple(plan.out.clone().unbind(0))
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, *gouts):
         model, plan = ctx.model, ctx.plan
         k = model._free_grad_slot()
-        gflat = plan.run_backward(gout, k)
+        gflat = plan.run_backward(gouts, k)
         grads = [gflat[model._off[n]:model._off[n] + p.numel()].view(model._shape[n])
                  if p.requires_grad else None
                  for n, p in zip(model._names, model._plist)]
         return (None, None, None, *grads)
+
+
+class _LossFn(torch.autograd.Function):
+    """-mean(lower_bound + alpha*log_qy) (train_model.py:243-251) as one launch; the backward is two scalings."""
+
+    @staticmethod
+    def forward(ctx, lb, log_qy, alpha):
+        B = lb.numel()
+        loss = torch.empty((), dtype=torch.float32, device=lb.device)
+        _lib.check(_lib.fn("fhvae_loss_mean")(ptr(lb), ptr(log_qy), float(alpha), B, ptr(loss), current_stream_ptr()),
+                   "fhvae_loss_mean")
+        ctx.B, ctx.alpha = B, float(alpha)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        glb = (g * (-1.0 / ctx.B)).expand(ctx.B)
+        gqy = (g * (-ctx.alpha / ctx.B)).expand(ctx.B)
+        return glb, gqy, None
 
 
 # =====================================================================================
@@ -340,7 +362,14 @@ class _Plan:
         gflat = self.m._grad_buffer(k)
         if self.bwd[k] is None:
             self.bwd[k] = self._build_bwd(gflat)
-        self.gout.copy_(gout)
+        if torch.is_tensor(gout):
+            self.gout.copy_(gout)
+        else:                                  # six per-output gradients, None where an output was not used
+            if any(g_ is None for g_ in gout):
+                self.gout.zero_()
+            for row, g_ in enumerate(gout):
+                if g_ is not None:
+                    self.gout[row].copy_(g_)
         self._gout_train = None
         if self.m.use_cuda_graphs:
             if self._graph_bwd[k] is None:
@@ -1087,5 +1116,10 @@ class FHVAE(_FHVAECore):
 
 
 def loss_function(lower_bound, log_qy, alpha=10.0):
-    """train_model.py:243-251."""
+    """train_model.py:243-251: ``-mean(lower_bound + alpha * log_qy)``.  Per-segment CUDA fp32 vectors take the
+    one-launch path; anything else (the reference's scalar log_qy, other dtypes) the literal expression."""
+    if (torch.is_tensor(log_qy) and lower_bound.is_cuda and log_qy.is_cuda and lower_bound.dtype == torch.float32
+            and log_qy.dtype == torch.float32 and lower_bound.dim() == 1 and log_qy.shape == lower_bound.shape
+            and lower_bound.is_contiguous() and log_qy.is_contiguous()):
+        return _LossFn.apply(lower_bound, log_qy, alpha)
     return -1 * torch.mean(lower_bound + alpha * log_qy)

@@ -23,12 +23,25 @@ def main():
     opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
     x, idx, nsegs = bench.synth(c["B"], c["T"], c["F"], c["N"], 1234)
     xd, idd, nsd = x.to(dev), idx.to(dev), nsegs.to(dev)
+    e2e = "--e2e" in sys.argv
+    xh, idh, nsh = x.pin_memory(), idx.pin_memory(), nsegs.pin_memory()
+
+    def step():
+        if not e2e:
+            return m.train_step(xd, idd, nsd, opt, c["alpha"])
+        opt.zero_grad()
+        out = m(xh.to(dev, non_blocking=True), idh, c["N"], nsh)
+        lss = P.loss_function(out[0], out[1], c["alpha"])
+        lss.backward()
+        opt.step()
+        return float(lss.detach())
+
     for _ in range(10):
-        m.train_step(xd, idd, nsd, opt, c["alpha"])
+        step()
     torch.cuda.synchronize()
     with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
         for _ in range(4):
-            m.train_step(xd, idd, nsd, opt, c["alpha"])
+            step()
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
