@@ -19,6 +19,20 @@ constexpr int HMAXK = 1024;      // max L*H of a head / max 4H of dgsum staged i
 constexpr int HMAXZ = 128;       // max 2Z, max Kq
 constexpr int HTILE = 40960;     // floats of the weight-tile staging buffer (160 KB of dynamic shared memory)
 
+// e / d and e % d for a CTA-uniform runtime divisor: a shift when d is a power of two (every size of the
+// benchmark configuration is), the ~30-instruction integer division otherwise.  These kernels are index-math bound.
+struct FastDiv {
+    int d, lg;
+    __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), lg(-1) {
+        if ((d_ & (d_ - 1)) == 0) {
+            lg = 0;
+            while ((1 << lg) < d_) ++lg;
+        }
+    }
+    __device__ __forceinline__ int div(int e) const { return lg >= 0 ? (e >> lg) : e / d; }
+    __device__ __forceinline__ int mod(int e) const { return lg >= 0 ? (e & (d - 1)) : e % d; }
+};
+
 // Cooperative copy of a rows x cols tile of W (leading dim ld) into shared memory (leading dim s_ld): every
 // thread has all of its loads in flight before the first store (one exposed L2 round trip per tile instead of
 // one per dependent load -- the scalar version of these kernels spent 30-50 us in serialized L2 latency).
@@ -90,6 +104,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
     const int tid = threadIdx.x;
     const int b0 = blockIdx.x * HB;
     const int K = a.nsrc * a.H, Z2 = 2 * a.Z;
+    const FastDiv dK(K), dH(a.H), dZ(a.Z), dZ2(Z2), dKq(a.Kq > 0 ? a.Kq : 1);
     HTL(0, 0);
     // every independent global read of the CTA is issued up front (they overlap the first weight tile):
     // its HB rows of final hidden states, eps, and the part of the projection input another launch produced
@@ -99,17 +114,17 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
         const int e = tid + i * HT;
         hreg[i] = 0.f;
         if (e < HB * K) {
-            const int r = e / K, k = e - r * K, l = k / a.H, u = k - l * a.H;
+            const int r = dK.div(e), k = dK.mod(e), l = dH.div(k), u = dH.mod(k);
             if (b0 + r < a.B) hreg[i] = __ldg(a.src[l] + (int64_t)(b0 + r) * a.ld_src + u);
         }
     }
     float epsreg = 0.f, zreg = 0.f;
     if (a.eps && tid < HB * a.Z) {
-        const int r = tid / a.Z, d = tid - r * a.Z;
+        const int r = dZ.div(tid), d = dZ.mod(tid);
         if (b0 + r < a.B) epsreg = __ldg(a.eps + (int64_t)(b0 + r) * a.Z + d);
     }
     if (a.Q && tid < HB * a.Kq) {
-        const int r = tid / a.Kq, col = a.qoff + tid - r * a.Kq;
+        const int r = dKq.div(tid), col = a.qoff + dKq.mod(tid);
         const bool own = a.eps && col >= a.zoff && col < a.zoff + a.Z;
         if (!own && b0 + r < a.B) zreg = a.zcat[(int64_t)(b0 + r) * a.ld_z + col];
     }
@@ -117,8 +132,8 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
     // == TPO (mod 32): the (32/TPO outputs) x (TPO slices) of a warp hit 32 different banks; the slices are summed
     // by a fixed xor-shuffle tree.
     {
-        int TPO = 8;
-        while (TPO > 1 && Z2 * TPO > HT) TPO >>= 1;
+        int TPO = 8, lgT = 3;
+        while (TPO > 1 && Z2 * TPO > HT) { TPO >>= 1; --lgT; }
         const int sld = (K + 31) / 32 * 32 + (TPO == 1 ? 1 : TPO);
         const int TN = min(Z2, HTILE / sld);
         for (int n0 = 0; n0 < Z2; n0 += TN) {
@@ -130,13 +145,13 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
 #pragma unroll
                 for (int i = 0; i < HB * HMAXK / HT; ++i) {
                     const int e = tid + i * HT;
-                    if (e < HB * K) s_h[e / K][e % K] = hreg[i];
+                    if (e < HB * K) s_h[dK.div(e)][dK.mod(e)] = hreg[i];
                 }
             }
             __syncthreads();
             HTL(0, 2);
             for (int o0 = 0; o0 < TPO * tn; o0 += HT) {        // CTA-uniform trip count (shuffles below)
-                const int o = o0 + tid, n = o / TPO, p = o % TPO;
+                const int o = o0 + tid, n = o >> lgT, p = o & (TPO - 1);
                 const bool valid = o < TPO * tn;
                 float acc[HB];
 #pragma unroll
@@ -165,12 +180,12 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
     __syncthreads();
     HTL(0, 3);
     for (int e = tid; e < HB * Z2; e += HT) {
-        const int r = e / Z2, n = e - r * Z2;
+        const int r = dZ2.div(e), n = dZ2.mod(e);
         if (b0 + r < a.B) a.head[(int64_t)(b0 + r) * Z2 + n] = s_head[r][n];
     }
     // ---- sample (same expression as reparam_fwd_kernel)
     if (a.eps && tid < HB * a.Z) {
-        const int r = tid / a.Z, d = tid - r * a.Z;
+        const int r = dZ.div(tid), d = dZ.mod(tid);
         const float z = fmaf(epsreg, expf(0.5f * s_head[r][a.Z + d]), s_head[r][d]);
         s_smp[r][d] = z;
         if (b0 + r < a.B) a.zcat[(int64_t)(b0 + r) * a.ld_z + a.zoff + d] = z;
@@ -178,7 +193,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
     if (!a.Q) return;
     __syncthreads();
     if (tid < HB * a.Kq) {
-        const int r = tid / a.Kq, j = tid - r * a.Kq, col = a.qoff + j;
+        const int r = dKq.div(tid), j = dKq.mod(tid), col = a.qoff + j;
         const bool own = a.eps && col >= a.zoff && col < a.zoff + a.Z;
         s_z[r][j] = own ? s_smp[r][col - a.zoff] : zreg;
     }
@@ -229,11 +244,12 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * HB;
     const int Z2 = 2 * a.Z;
+    const FastDiv dNG(a.NG > 0 ? a.NG : 1), dKq(a.Kq > 0 ? a.Kq : 1), dZ(a.Z), dZ2(Z2), dH(a.H > 0 ? a.H : 1);
     // ---- dz[b][j] = sum_n dgsum[b][n] Wq[n][j]: tiles of TR rows of Wq; lanes along j, the rows of a tile are
     // split across the warps, partial sums combined across warps in a fixed order
     if (a.dgsum) {
         for (int e = tid; e < HB * a.NG; e += HT) {
-            const int r = e / a.NG, n = e - r * a.NG;
+            const int r = dNG.div(e), n = dNG.mod(e);
             s_g[r][n] = (b0 + r < a.B) ? __ldg(a.dgsum + (int64_t)(b0 + r) * a.NG + n) : 0.f;
         }
         const int TR = min(a.NG, HTILE / a.Kq / 8 * 8);
@@ -269,7 +285,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
                 if (lane + 32 * q < a.Kq) s_part[warp][r][lane + 32 * q] = acc[r][q];
         __syncthreads();
         for (int e = tid; e < HB * a.Kq; e += HT) {
-            const int r = e / a.Kq, j = e - r * a.Kq;
+            const int r = dKq.div(e), j = dKq.mod(e);
             float s = 0.f;
 #pragma unroll
             for (int w = 0; w < HT / 32; ++w) s += s_part[w][r][j];
@@ -284,7 +300,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
     // ---- reparameterisation backward into dhead (same expressions as reparam_bwd_kernel)
     if (a.eps) {
         for (int e = tid; e < HB * a.Z; e += HT) {
-            const int r = e / a.Z, d = e - r * a.Z;
+            const int r = dZ.div(e), d = dZ.mod(e);
             if (b0 + r < a.B) {
                 const int64_t b = b0 + r;
                 const float lv = __ldg(a.head + b * Z2 + a.Z + d);
@@ -299,7 +315,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
     }
     if (!a.W) return;
     for (int e = tid; e < HB * Z2; e += HT) {
-        const int r = e / Z2, j = e - r * Z2;
+        const int r = dZ2.div(e), j = dZ2.mod(e);
         s_dhead[r][j] = (b0 + r < a.B) ? a.dhead[(int64_t)(b0 + r) * Z2 + j] : 0.f;
     }
     // ---- dh_last of every layer: dh[l][b][u] = sum_j dhead[b][j] W[j][l*H + u]; tiles of TJ rows of W, threads along u
@@ -332,7 +348,7 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
     for (int q = 0; q < (HMAXK + HT - 1) / HT; ++q) {
         const int k = tid + q * HT;
         if (k < K) {
-            const int l = k / a.H, u = k - l * a.H;
+            const int l = dH.div(k), u = dH.mod(k);
 #pragma unroll
             for (int r = 0; r < HB; ++r)
                 if (b0 + r < a.B) a.dh[l][(int64_t)(b0 + r) * a.H + u] = acc[r][q];
