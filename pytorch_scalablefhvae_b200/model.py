@@ -456,16 +456,22 @@ class _Plan:
             f()
         return g
 
-    # ---- shared tail: gather + ELBO + discriminative term
-    def _tail_fwd(self, xhead, xs_b, xs_t, lv_off):
+    # ---- shared tail: gather + discriminative term (side stream 2: needs only z2head) + ELBO
+    def _disc_fwd(self):
         c, m, B = self.fwd, self.m, self.B
         tab = ptr(m.mu2_table)
-        c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N)
+        c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N, side=2)
         c.add("fhvae_disc_fwd_partial", ptr(self.z2head), 2 * self.Z2, tab, self.N, self.Z2,
               ptr(self.part), self.nsplit, B, side=2)
         c.add("fhvae_disc_target", ptr(self.z2head), 2 * self.Z2, ptr(self.mu2), ptr(self.tgt), B, self.Z2, side=2)
         c.add("fhvae_disc_combine", ptr(self.part), self.nsplit, ptr(self.tgt), ptr(self.out, 5 * B),
               ptr(self.lse), B, side=2)
+
+    def _tail_fwd(self, xhead, xs_b, xs_t, lv_off, disc=True):
+        c, B = self.fwd, self.B
+        if disc:
+            self._disc_fwd()
+        c.join(2)                                    # mu2 rows (gather) for the KL(z2 || mu2) term
         c.add("fhvae_elbo_fwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
               ptr(self.z2head), ptr(self.mu2), ptr(self.nsegs), ptr(self.out), ptr(self.nan_flag),
               B, self.T, self.F, self.Z1, self.Z2)
@@ -576,9 +582,10 @@ class _FHVAEPlan(_Plan):
         Z1, Z2, mode = self.Z1, self.Z2, self.mode
         TB = T * B
         pre = dict(self.NETS)
-        c.add("fhvae_transpose_bt", ptr(self.x), ptr(self.x_tm), B, T, F)
         c.add("fhvae_add2", ptr(self.bsum), m.poff(m._bias_first[0]), m.poff(m._bias_first[1]),
-              m._bias_block_len)
+              m._bias_block_len, side=2)             # fused (b_ih + b_hh), beside the transpose
+        c.add("fhvae_transpose_bt", ptr(self.x), ptr(self.x_tm), B, T, F)
+        c.join(2)
         Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
         wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
         wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
@@ -634,6 +641,7 @@ class _FHVAEPlan(_Plan):
         stack("z2", None)
         head_stage("z2", Hz2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias", self.z2head, Z2,
                    self.eps2, Z1, m.poff(wih_z1, F), F + Z2, None, Z1, Z2, self.Q["z1"], 4 * Hz1)
+        self._disc_fwd()       # log q(i|z2) only needs the z2 posterior: side stream 2, beside the z1 / decoder stacks
         c.join(1)
         stack("z1", ptr(self.Q["z1"]))
         # z1 head -> sample -> the decoder's whole (time-invariant) layer-0 input projection
@@ -645,7 +653,7 @@ class _FHVAEPlan(_Plan):
         c.gemm([gemm_nt(ptr(self.h["dec", Ld - 1]), Hd, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
                         ptr(self.xhead), 2 * F, TB, 2 * F, Hd,
                         bias=m.poff("dec_gauss_layer.mulayer.bias"))], mode)
-        self._tail_fwd(self.xhead, 2 * F, B * 2 * F, F)
+        self._tail_fwd(self.xhead, 2 * F, B * 2 * F, F, disc=False)
 
     def _build_bwd(self, gflat) -> CallList:
         c, m, B, T, F = CallList(), self.m, self.B, self.T, self.F
