@@ -368,6 +368,14 @@ def dominant_kernel_roofline(m, P, xd, idd, nsd, opt, args):
                               "ms_per_step": wg[0] / reps, "canonical_tflops": canon / t_s / 1e12,
                               "executed_mma_tflops": passes * canon / t_s / 1e12,
                               "executed_frac_of_bf16_sustained": passes * canon / t_s / 1e12 / pk["tf_sus"]}
+    # DRAM traffic of the dominant kernel: taken from the committed ncu --set full capture of this round
+    # (never measured under a profiler here)
+    tp = os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")
+    if os.path.exists(tp):
+        t = json.load(open(tp)).get(top)
+        if t:
+            roof["traffic"] = t["bytes_per_launch"]
+            roof["traffic_source"] = "profiles/r01_ncu_traffic.json (ncu dram__bytes_read+write per launch)"
     if args.breakdown:
         sys.stderr.write(json.dumps(breakdown, indent=1) + "\n")
     return roof, breakdown
