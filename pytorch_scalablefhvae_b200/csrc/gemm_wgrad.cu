@@ -38,11 +38,14 @@ struct WgProblem {
     int M, N, K;
     int c_vec;
     int tile_start, tiles_m, tiles_n, ksplit, kb_per_split;
-    int pad[3];
+    int store;                  // ksplit == 1: the epilogue stores (no pre-zero pass, no atomics)
+    int pad[2];
 };
 struct WgBatch {
     WgProblem p[FHVAE_WGRAD_MAX_BATCH];
     int n, passes;
+    int ns;                     // stages of the ring actually used: 4 (1 CTA/SM) for long K, 2 (two CTAs/SM share the
+                                // SM: one tile's epilogue overlaps the other's loads) when every CTA has <= 4 K-blocks
 };
 
 __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
@@ -63,10 +66,11 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_constant__ WgBatch wb) {
+__global__ void __launch_bounds__(WG_THREADS, 2) wgrad_tma_kernel(const __grid_constant__ WgBatch wb) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + WG_NS * WG_STAGE);
+    const int NS = wb.ns;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * WG_STAGE);
     uint64_t* empty = full + WG_NS;
     uint64_t* accd = empty + WG_NS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accd + 1);
@@ -90,7 +94,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
 
     if (warp == 1) tmem_alloc<WG_BN>(tmem_slot);
     if (tid == 0) {
-        for (int i = 0; i < WG_NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+        for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
         mbar_init(accd, 1);
         fence_mbar_init();
     }
@@ -104,8 +108,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
         if (elect_one()) {
             const uint32_t bytes = (uint32_t)(planes * (nbox_a + nbox_b) * WG_BOX);
             for (int it = 0; it < nit; ++it) {
-                const int s = it % WG_NS;
-                if (it >= WG_NS) mbar_wait(&empty[s], ((it / WG_NS) - 1) & 1);
+                const int s = it % NS;
+                if (it >= NS) mbar_wait(&empty[s], ((it / NS) - 1) & 1);
                 mbar_expect_tx(&full[s], bytes);
                 const uint32_t st = smem_u32(smem + s * WG_STAGE);
                 const int k = (kb0 + it) * WG_BK;
@@ -122,8 +126,8 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
         if (elect_one()) {
             const uint32_t idesc = make_idesc_bf16(WG_BM, nt) | (1u << 15) | (1u << 16);     // A and B MN-major
             for (int it = 0; it < nit; ++it) {
-                const int s = it % WG_NS;
-                mbar_wait(&full[s], (it / WG_NS) & 1);
+                const int s = it % NS;
+                mbar_wait(&full[s], (it / NS) & 1);
                 tc_fence_after();
                 const uint32_t st = smem_u32(smem + s * WG_STAGE);
 #pragma unroll
@@ -146,7 +150,10 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
             umma_commit(accd);
         }
     } else {
-        // ================= epilogue: TMEM -> red.global.add =================
+        // ================= epilogue: TMEM -> registers -> global (store, or red.add for split-K partials) ==========
+        // A thread owns one accumulator row and writes 16-byte pieces of it straight from registers, chunk by chunk
+        // behind each tcgen05.ld.  (Staging the tile through shared memory for 512-byte coalesced rows was measured
+        // SLOWER -- 27 vs 18.6 us on the 21 MB projection output: the extra pass serialises load, barrier and store.)
         mbar_wait(accd, 0);
         tc_fence_after();
         const int q = warp & 3;                              // TMEM lane quarter this warp may read
@@ -160,12 +167,18 @@ __global__ void __launch_bounds__(WG_THREADS, 1) wgrad_tma_kernel(const __grid_c
                 for (int j = 0; j < 8; ++j) {
                     const int n = c0 + 4 * j;
                     if (P.c_vec && n + 4 <= nrem) {
-                        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + n), "f"(v[4 * j]),
-                                     "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
+                        if (P.store)
+                            *reinterpret_cast<float4*>(crow + n) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                        else
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(crow + n), "f"(v[4 * j]),
+                                         "f"(v[4 * j + 1]), "f"(v[4 * j + 2]), "f"(v[4 * j + 3]) : "memory");
                     } else {
 #pragma unroll
                         for (int i = 0; i < 4; ++i)
-                            if (n + i < nrem) atomicAdd(crow + n + i, v[4 * j + i]);
+                            if (n + i < nrem) {
+                                if (P.store) crow[n + i] = v[4 * j + i];
+                                else atomicAdd(crow + n + i, v[4 * j + i]);
+                            }
                     }
                 }
             }
@@ -182,6 +195,7 @@ __global__ void __launch_bounds__(256) wgrad_zero_kernel(const __grid_constant__
     int pi = 0, start = 0;
     while (pi + 1 < wb.n && bt >= start + wb.p[pi].tiles_m * wb.p[pi].tiles_n) { start += wb.p[pi].tiles_m * wb.p[pi].tiles_n; ++pi; }
     const WgProblem& P = wb.p[pi];
+    if (P.store) return;
     const int t = bt - start;
     const int m0 = (t / P.tiles_n) * WG_BM + sub * 32, n0 = (t % P.tiles_n) * WG_BN;
     const int cq = threadIdx.x & 63, r0 = threadIdx.x >> 6;       // 64 float4 columns x 4 rows per pass
@@ -282,7 +296,7 @@ extern "C" int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int
     }
     // split K so that the launch is one wave of 1-CTA/SM tiles; at least 4 K-blocks per split
     const int want = tiles > 0 ? (kNumSM / tiles > 0 ? kNumSM / tiles : 1) : 1;
-    int total = 0, ztotal = 0;
+    int total = 0, ztotal = 0, nzero = 0, max_nit = 0;
     for (int i = 0; i < n; ++i) {
         const fhvae_wgrad_problem& p = problems[i];
         WgProblem& q = wb.p[wb.n];
@@ -298,15 +312,21 @@ extern "C" int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int
         if (ks > nkb / 4) ks = nkb / 4 > 0 ? nkb / 4 : 1;
         q.kb_per_split = cdiv(nkb, ks);
         q.ksplit = cdiv(nkb, q.kb_per_split);
+        q.store = q.ksplit == 1;
+        if (q.kb_per_split > max_nit) max_nit = q.kb_per_split;
         q.tile_start = total;
         total += q.tiles_m * q.tiles_n * q.ksplit;
         ztotal += q.tiles_m * q.tiles_n;
+        nzero += q.store ? 0 : 1;
         ++wb.n;
     }
     cudaStream_t st = as_stream(stream);
-    wgrad_zero_kernel<<<ztotal * 4, 256, 0, st>>>(wb);
-    FHVAE_LAUNCH_CHECK("wgrad_zero");
-    wgrad_tma_kernel<<<total, WG_THREADS, WG_SMEM, st>>>(wb);
+    if (nzero > 0) {
+        wgrad_zero_kernel<<<ztotal * 4, 256, 0, st>>>(wb);
+        FHVAE_LAUNCH_CHECK("wgrad_zero");
+    }
+    wb.ns = max_nit <= 4 ? 2 : WG_NS;
+    wgrad_tma_kernel<<<total, WG_THREADS, wb.ns * WG_STAGE + 1024 + 256, st>>>(wb);
     FHVAE_LAUNCH_CHECK("wgrad_tma");
     return 0;
 }

@@ -143,7 +143,7 @@ def test_split_planes_exact():
 
 
 @pytest.mark.parametrize("M,N,K,mode,tol", [(1024, 256, 5120, 1, 2e-5), (1024, 256, 4864, 1, 2e-5), (1024, 80, 5120, 1, 2e-5),
-                                           (160, 256, 5120, 1, 2e-5), (64, 256, 256, 1, 2e-5), (72, 24, 100, 1, 2e-5),
+                                           (160, 256, 5120, 1, 2e-5), (64, 256, 256, 1, 2e-5), (72, 24, 100, 1, 2e-5), (5120, 1024, 88, 1, 2e-5),
                                            (304, 520, 333, 1, 2e-5), (1024, 256, 5120, 2, 1e-2)])
 def test_wgrad_planes_matches_fp64(M, N, K, mode, tol):
     """C = A^T B from pre-split planes (hi*hi + hi*lo + lo*hi) against fp64, ragged M/N/K and split-K included."""

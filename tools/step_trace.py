@@ -45,13 +45,13 @@ def main():
         torch.cuda.synchronize()
     evs = [e for e in prof.events() if e.device_type == torch.autograd.DeviceType.CUDA]
     evs.sort(key=lambda e: e.time_range.start)
-    # last full step: find the last 'transpose_bt' kernel
-    starts = [i for i, e in enumerate(evs) if "transpose_bt" in e.name]
-    if not starts:
-        print("no kernels recorded", len(evs))
+    # last full step = everything after the second-to-last Adam kernel up to (and including) the last one
+    adams = [i for i, e in enumerate(evs) if "adam_flat" in e.name and "Optimizer" not in e.name]
+    if len(adams) < 2:
+        print("no complete step recorded", len(evs))
         return
-    i0 = starts[-1]
-    # the graph's first node may be a memcpy/other kernel of load_inputs; step = [prev adam end .. this adam end]
+    i0 = adams[-2] + 1
+    evs = evs[:adams[-1] + 1]
     t0 = evs[i0].time_range.start
     prev_end = max((e.time_range.end for e in evs[:i0]), default=t0)
     print(f"# gap before step (prev kernel end -> first kernel of the step): {t0 - prev_end:.1f} us")
