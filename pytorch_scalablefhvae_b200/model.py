@@ -53,6 +53,13 @@ class _FHVAECore(nn.Module):
     """Flat parameter storage, plan cache, autograd glue and the shared forward tail."""
 
     model = "base"
+    # How the backward hands the gradients to the parameters.  True (default): the step node assigns cached views of
+    # the flat gradient buffer to ``p.grad`` itself (what ``loss.backward()`` callers, optimizers, clipping and the
+    # reference's TensorBoard histograms see is identical; the per-step host cost of ~45 parameter edges through
+    # the autograd engine -- ~0.5 ms, more than the GPU time it would hide -- disappears).  False: the parameters
+    # are inputs of the node and autograd's AccumulateGrad delivers the same views (needed only for
+    # ``torch.autograd.grad`` w.r.t. parameters or parameter hooks).
+    direct_grads = True
 
     # ------------------------------------------------------------------ parameters
     def _init_flat(self, specs: Sequence[Tuple[str, Tuple[int, ...]]], init: Dict[str, torch.Tensor]):
@@ -136,9 +143,33 @@ class _FHVAECore(nn.Module):
                 return k
         return 0
 
+    def _grad_views_of(self, k: int) -> List[torch.Tensor]:
+        """Per-parameter views of flat gradient buffer k (created once per buffer)."""
+        buf = self._grad_buffer(k)
+        cache = self.__dict__.setdefault("_gviews", {})
+        ent = cache.get(k)
+        if ent is None or ent[0] is not buf:
+            ent = (buf, [buf[self._off[n]:self._off[n] + p.numel()].view(self._shape[n])
+                         for n, p in zip(self._names, self._plist)])
+            cache[k] = ent
+        return ent[1]
+
+    def _deliver_grads(self, k: int):
+        """``p.grad`` <- view of buffer k (or accumulate into an existing ``p.grad``, like AccumulateGrad)."""
+        for p, v in zip(self._plist, self._grad_views_of(k)):
+            if not p.requires_grad:
+                continue
+            if p.grad is None:
+                p.grad = v
+            else:
+                p.grad.add_(v)
+
     def packed_grads(self) -> torch.Tensor:
         """Flat gradient buffer equal to every ``p.grad`` (zeros where None); zero-copy on the fast path."""
         self._ensure_flat()
+        for k, ent in self.__dict__.get("_gviews", {}).items():     # identity check against the cached views
+            if ent[0] is self._gflat[k] and all(p.grad is v for p, v in zip(self._plist, ent[1])):
+                return ent[0]
         for k in (0, 1):
             buf = self._gflat[k]
             if buf is None:
@@ -187,7 +218,8 @@ class _FHVAECore(nn.Module):
         if grad_on:
             if self._anchor is None or self._anchor.device != x.device:
                 self._anchor = torch.zeros(1, device=x.device, requires_grad=True)
-            out = _StepFn.apply(self, plan, self._anchor, *self._plist)     # six (B,) rows of one buffer
+            params = () if self.direct_grads else self._plist
+            out = _StepFn.apply(self, plan, self._anchor, *params)          # six (B,) rows of one buffer
         else:
             plan.run_forward()
             out = plan.out.clone().unbind(0)
@@ -249,7 +281,7 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, plan, anchor, *params):
         plan.run_forward()
-        ctx.model, ctx.plan = model, plan
+        ctx.model, ctx.plan, ctx.n_params = model, plan, len(params)
         ctx.set_materialize_grads(False)      # unused outputs arrive as None instead of zero tensors
         # rows of the (6,B) buffer: lb, log_px, nk1, nk2, log_pmu2, log_qy -- returned as six outputs so that
         # autograd hands their gradients straight back (no per-row SelectBackward zeros + copy)
@@ -259,7 +291,11 @@ class _StepFn(torch.autograd.Function):
     def backward(ctx, *gouts):
         model, plan = ctx.model, ctx.plan
         k = model._free_grad_slot()
-        gflat = plan.run_backward(gouts, k)
+        plan.run_backward(gouts, k)
+        if ctx.n_params == 0:                 # direct delivery (see _FHVAECore.direct_grads)
+            model._deliver_grads(k)
+            return (None, None, None)
+        gflat = model._grad_buffer(k)         # fresh views: AccumulateGrad steals un-shared tensors (zero copies)
         grads = [gflat[model._off[n]:model._off[n] + p.numel()].view(model._shape[n])
                  if p.requires_grad else None
                  for n, p in zip(model._names, model._plist)]

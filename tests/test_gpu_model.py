@@ -187,9 +187,13 @@ def test_train_steps_match_oracle_adam(name, graphs):
 
 
 
-def test_grad_accumulation_without_zero_grad():
+@pytest.mark.parametrize("direct", [True, False])
+def test_grad_accumulation_without_zero_grad(direct):
+    """Two backward passes without zero_grad accumulate like autograd does -- with the step node assigning p.grad
+    itself (default) and with the parameters as autograd inputs (AccumulateGrad delivers the same views)."""
     cfg = CFGS["fhvae_small"]
     m, o = _pair("fhvae", cfg)
+    m.direct_grads = direct
     x, idx, nsegs = synth_batch(cfg["B"], cfg["T"], cfg["F"], cfg["N"])
     eps = _eps(cfg["B"], m.z1_dim, m.z2_dim)
     for _ in range(2):
@@ -200,6 +204,34 @@ def test_grad_accumulation_without_zero_grad():
     po = dict(o.named_parameters())
     for k, p in m.named_parameters():
         assert_close(p.grad, po[k].grad, FP32_RTOL, k)
+
+
+@pytest.mark.parametrize("direct", [True, False])
+def test_grads_are_views_of_one_flat_buffer(direct):
+    """After zero_grad + backward every p.grad aliases the flat gradient buffer (FusedAdam then needs no packing),
+    in both delivery modes; an optimizer step through the module API matches the oracle's Adam."""
+    cfg = CFGS["fhvae_small"]
+    m, o = _pair("fhvae", cfg)
+    m.direct_grads = direct
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    oopt = O.make_adam(o.parameters())
+    x, idx, nsegs = synth_batch(cfg["B"], cfg["T"], cfg["F"], cfg["N"])
+    eps = _eps(cfg["B"], m.z1_dim, m.z2_dim)
+    for _ in range(2):
+        opt.zero_grad()
+        out = m(x.to(DEV), idx, cfg["N"], nsegs, eps=eps)
+        P.loss_function(out[0], out[1]).backward()
+        flat = m.packed_grads()
+        for n, p in zip(m._names, m._plist):
+            assert p.grad.data_ptr() == flat.data_ptr() + 4 * m._off[n], n
+        opt.step()
+        oopt.zero_grad()
+        ref = o(x, idx, cfg["N"], nsegs, eps=eps)
+        O.loss_function(ref[0], ref[1]).backward()
+        oopt.step()
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert_close(p, po[k], FP32_RTOL, k)
 
 
 def test_no_grad_forward_and_errors():
