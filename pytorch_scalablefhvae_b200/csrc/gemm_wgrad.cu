@@ -66,10 +66,10 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar)) : "memory");
 }
 
-__global__ void __launch_bounds__(WG_THREADS, 2) wgrad_tma_kernel(const __grid_constant__ WgBatch wb) {
+template <int NS>
+__global__ void __launch_bounds__(WG_THREADS, NS == 2 ? 2 : 1) wgrad_tma_kernel(const __grid_constant__ WgBatch wb) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int NS = wb.ns;
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NS * WG_STAGE);
     uint64_t* empty = full + WG_NS;
     uint64_t* accd = empty + WG_NS;
@@ -278,7 +278,9 @@ extern "C" int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int
     FHVAE_CHECK_ARG(mode == FHVAE_MODE_BF16X3 || mode == FHVAE_MODE_BF16, "wgrad_planes: mode must be BF16X3 or BF16");
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(wgrad_tma_kernel<WG_NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WG_SMEM);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(wgrad_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * WG_STAGE + 1024 + 256);
         if (e != cudaSuccess) { set_error("wgrad_planes: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return (int)e; }
         attr = true;
     }
@@ -326,7 +328,8 @@ extern "C" int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int
         FHVAE_LAUNCH_CHECK("wgrad_zero");
     }
     wb.ns = max_nit <= 4 ? 2 : WG_NS;
-    wgrad_tma_kernel<<<total, WG_THREADS, wb.ns * WG_STAGE + 1024 + 256, st>>>(wb);
+    if (wb.ns == 2) wgrad_tma_kernel<2><<<total, WG_THREADS, 2 * WG_STAGE + 1024 + 256, st>>>(wb);
+    else wgrad_tma_kernel<WG_NS><<<total, WG_THREADS, WG_SMEM, st>>>(wb);
     FHVAE_LAUNCH_CHECK("wgrad_tma");
     return 0;
 }
