@@ -765,7 +765,9 @@ class _FHVAEPlan(_Plan):
                     c.gemm(list(self_), mode, side=1)
                     self_.clear()
                 if cs:
-                    c.colsum(list(cs), side=2)     # tiny, latency-bound: next to, not behind, the GEMMs
+                    # tiny, latency-bound: next to, not behind, the GEMMs -- and on its own stream, so that the join
+                    # of the discriminative chain (side 2) at the z2 head never waits for a column sum
+                    c.colsum(list(cs), side=3)
                     cs.clear()
         wg = _Side()
         if use_tma:

@@ -45,11 +45,11 @@ def _side_stream(device, k: int = 1) -> "torch.cuda.Stream":
 
 
 class CallList:
-    """Ordered kernel launches.  A call tagged ``side=k`` (k = 1, 2; True == 1) is off the critical path: it is
+    """Ordered kernel launches.  A call tagged ``side=k`` (k = 1, 2, 3; True == 1) is off the critical path: it is
     forked onto side stream k behind an event recorded at its position in the main sequence (calls on one side
-    stream stay in order), and joined back by ``join(k)`` or at the end of the list.  Stream 1 carries the weight /
-    bias gradients (they fill the SMs the 128-CTA recurrence leaves idle), stream 2 the short discriminative
-    chain.  Works identically eagerly and under CUDA-graph capture (fork/join become graph branches)."""
+    stream stay in order), and joined back by ``join(k)`` or at the end of the list.  Stream 1 carries the weight
+    gradients (they fill the SMs the 128-CTA recurrence leaves idle), stream 2 the short discriminative chain,
+    stream 3 the bias column sums.  Works identically eagerly and under CUDA-graph capture (fork/join become graph branches)."""
 
     def __init__(self):
         self.calls = []      # (cfunc, name, args, side)
