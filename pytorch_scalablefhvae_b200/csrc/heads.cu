@@ -20,7 +20,8 @@ constexpr int HMAXZ = 128;       // max 2Z, max Kq
 constexpr int HTILE = 40960;     // floats of the weight-tile staging buffer (160 KB of dynamic shared memory)
 
 // e / d and e % d for a CTA-uniform runtime divisor: a shift when d is a power of two (every size of the
-// benchmark configuration is), the ~30-instruction integer division otherwise.  These kernels are index-math bound.
+// benchmark configuration is), the ~30-instruction integer division otherwise.  (Measured: not what bounds these
+// kernels -- each phase is ~2-4k cycles of cold instruction fetch + one L2 round trip; tools/head_timeline.py.)
 struct FastDiv {
     int d, lg;
     __device__ __forceinline__ explicit FastDiv(int d_) : d(d_), lg(-1) {
