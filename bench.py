@@ -317,6 +317,7 @@ def dominant_kernel_roofline(m, P, xd, idd, nsd, opt, args):
         plan.load_inputs(xd, idd, nsd, None)
         timed_run(plan.fwd)
         plan.gout.zero_(); plan.gout[0].fill_(-1.0 / c["B"]); plan.gout[5].fill_(-c["alpha"] / c["B"])
+        plan._gout_rows = plan._gout_train = None          # the plan's own bookkeeping of what gout holds
         if plan.bwd[0] is None:
             plan.bwd[0] = plan._build_bwd(m._grad_buffer(0))
         timed_run(plan.bwd[0])

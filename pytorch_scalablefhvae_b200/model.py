@@ -262,14 +262,15 @@ class _FHVAECore(nn.Module):
 
     def _publish(self, plan: "_Plan"):
         """Attributes the reference's callers read (utils.py:52,58)."""
-        z1h, z2h = plan.z1head, plan.z2head
-        Z1, Z2 = self.z1_dim, self.z2_dim
-        self.qz1_x = [z1h[:, :Z1], z1h[:, Z1:]]
-        self.qz2_x = [z2h[:, :Z2], z2h[:, Z2:]]
-        self.px_z = plan.px_views()
-        self.pz2 = [plan.mu2, np.float32(PZ2_LOGVAR)]
-        self.z1_sample, self.z2_sample = plan.zcat[:, :Z1], plan.zcat[:, Z1:]
-        self.nan_flag = plan.nan_flag
+        pub = plan.__dict__.get("_published")
+        if pub is None:                    # views of the plan's static buffers: built once, not per forward
+            z1h, z2h = plan.z1head, plan.z2head
+            Z1, Z2 = self.z1_dim, self.z2_dim
+            pub = plan._published = dict(
+                qz1_x=[z1h[:, :Z1], z1h[:, Z1:]], qz2_x=[z2h[:, :Z2], z2h[:, Z2:]], px_z=plan.px_views(),
+                pz2=[plan.mu2, np.float32(PZ2_LOGVAR)], z1_sample=plan.zcat[:, :Z1], z2_sample=plan.zcat[:, Z1:],
+                nan_flag=plan.nan_flag)
+        self.__dict__.update(pub)
 
     # subclasses: _make_plan(B, T, F)
 
@@ -409,9 +410,12 @@ class _Plan:
             self.bwd[k] = self._build_bwd(gflat)
         if torch.is_tensor(gout):
             self.gout.copy_(gout)
+            self._gout_rows = None
         else:                                  # six per-output gradients, None where an output was not used
-            if any(g_ is None for g_ in gout):
+            used = tuple(g_ is not None for g_ in gout)
+            if self.__dict__.get("_gout_rows") != used:      # rows that are None now may hold an older gradient
                 self.gout.zero_()
+                self._gout_rows = used
             for row, g_ in enumerate(gout):
                 if g_ is not None:
                     self.gout[row].copy_(g_)
@@ -440,6 +444,7 @@ class _Plan:
             self.gout[0].fill_(-1.0 / B)                  # d loss / d lower_bound
             self.gout[5].fill_(-alpha / B)                # d loss / d log_qy
             self._gout_train = (alpha, B)
+            self._gout_rows = None
         if self.__dict__.get("_loss_call") is None or self._loss_call[1] != alpha:
             lc = CallList()
             lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss), side=1)
