@@ -302,10 +302,11 @@ int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* dh_last_top
                                void* dg_top_planes, void* dg_bot_planes, int64_t plane_stride, int T, int B, int H,
                                int nlayers, int mode, void* stream);
 
-/* x (n_x floats), mu_idx (B int64), num_segs (B int64, may be NULL) -> the step's static input buffers, one launch
- * (device-to-device; replaces three copies of train_model.py:444-445's batch into CUDA-graph-stable storage). */
-int fhvae_load_inputs(const float* x_src, float* x_dst, int64_t n_x, const int64_t* idx_src, int64_t* idx_dst,
-                      const int64_t* nsegs_src, int64_t* nsegs_dst, int B, void* stream);
+/* x (B,T,F), mu_idx (B int64, may be NULL), num_segs (B int64, may be NULL) -> the step's static input buffers, one
+ * launch (device-to-device; the batch of train_model.py:444-445 into CUDA-graph-stable storage).  x is also written
+ * time-major (T,B,F) into x_tm when x_tm != NULL (what fhvae_transpose_bt does as a separate launch). */
+int fhvae_load_inputs(const float* x_src, float* x_dst, float* x_tm, int B, int T, int F, const int64_t* idx_src,
+                      int64_t* idx_dst, const int64_t* nsegs_src, int64_t* nsegs_dst, void* stream);
 
 #ifdef __cplusplus
 }

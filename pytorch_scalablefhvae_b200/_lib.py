@@ -87,7 +87,7 @@ PROTOTYPES = {
     "fhvae_axpy": [_p, _p, _f, _l, _p],
     "fhvae_wgrad_planes_batch": [C.POINTER(WgradProblem), _i, _i, _p],
     "fhvae_split_planes_batch": [C.POINTER(SplitProblem), _i, _p],
-    "fhvae_load_inputs": [_p, _p, _l, _p, _p, _p, _p, _i, _p],
+    "fhvae_load_inputs": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "fhvae_head_fwd": [_p, _p, _l, _i, _i, _p, _p, _p, _i, _p, _p, _l, _i, _p, _l, _p, _i, _i, _p, _i, _i, _p],
     "fhvae_head_bwd": [_p, _i, _p, _l, _i, _p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _p],
     "fhvae_step_coef": [_p, _p, _p, _i, _i, _i, _p],

@@ -156,14 +156,25 @@ __global__ void transpose_bt_kernel(const float* __restrict__ src, float* __rest
     dst[i] = __ldg(src + ((int64_t)b * T + t) * F + f);
 }
 
-// the three per-step input copies (x, mu_idx, num_segs -> the plan's static buffers) as ONE launch
-__global__ void __launch_bounds__(256) load_inputs_kernel(const float4* __restrict__ xs, float4* __restrict__ xd, int64_t n4,
+// the per-step input copies (x, mu_idx, num_segs -> the plan's static buffers) as ONE launch; x is also written in
+// the time-major (T,B,F) layout the LSTM kernels read (x_tm may be NULL)
+__global__ void __launch_bounds__(256) load_inputs_kernel(const float4* __restrict__ xs, float4* __restrict__ xd,
+                                                          float4* __restrict__ xtm, int64_t n4, int B, int T, int F4,
                                                           const int64_t* __restrict__ is, int64_t* __restrict__ id,
-                                                          const int64_t* __restrict__ ns, int64_t* __restrict__ nd, int B) {
+                                                          const int64_t* __restrict__ ns, int64_t* __restrict__ nd) {
     const int64_t i0 = (int64_t)blockIdx.x * 256 + threadIdx.x;
-    for (int64_t i = i0; i < n4; i += (int64_t)gridDim.x * 256) xd[i] = __ldg(xs + i);
+    for (int64_t i = i0; i < n4; i += (int64_t)gridDim.x * 256) {
+        const float4 v = __ldg(xs + i);
+        xd[i] = v;
+        if (xtm) {
+            const int f = (int)(i % F4);
+            const int64_t bt = i / F4;
+            const int t = (int)(bt % T), b = (int)(bt / T);
+            xtm[((int64_t)t * B + b) * F4 + f] = v;
+        }
+    }
     if (i0 < B) {
-        id[i0] = is[i0];
+        if (is) id[i0] = is[i0];
         if (ns) nd[i0] = ns[i0];
     }
 }
@@ -318,19 +329,20 @@ extern "C" int fhvae_transpose_bt(const float* src, float* dst, int B, int T, in
     return 0;
 }
 
-extern "C" int fhvae_load_inputs(const float* x_src, float* x_dst, int64_t n_x, const int64_t* idx_src, int64_t* idx_dst,
-                                 const int64_t* nsegs_src, int64_t* nsegs_dst, int B, void* stream) {
-    FHVAE_CHECK_ARG(x_src && x_dst && idx_src && idx_dst && n_x > 0 && B > 0 && (nsegs_src == nullptr || nsegs_dst),
-                    "load_inputs: bad argument");
-    FHVAE_CHECK_ARG(n_x % 4 == 0 && ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst)) & 15) == 0,
-                    "load_inputs: x must be 16-byte aligned with a multiple of 4 elements");
-    const int64_t n4 = n_x / 4;
+extern "C" int fhvae_load_inputs(const float* x_src, float* x_dst, float* x_tm, int B, int T, int F, const int64_t* idx_src,
+                                 int64_t* idx_dst, const int64_t* nsegs_src, int64_t* nsegs_dst, void* stream) {
+    FHVAE_CHECK_ARG(x_src && x_dst && B > 0 && T > 0 && F > 0 && (idx_src == nullptr || idx_dst) &&
+                    (nsegs_src == nullptr || nsegs_dst), "load_inputs: bad argument");
+    FHVAE_CHECK_ARG(F % 4 == 0 && ((reinterpret_cast<uintptr_t>(x_src) | reinterpret_cast<uintptr_t>(x_dst) |
+                                    reinterpret_cast<uintptr_t>(x_tm)) & 15) == 0,
+                    "load_inputs: x must be 16-byte aligned with F %% 4 == 0");
+    const int64_t n4 = (int64_t)B * T * F / 4;
     int grid = cdiv(n4, 256);
     if (grid < cdiv(B, 256)) grid = cdiv(B, 256);
     if (grid > 8 * kNumSM) grid = 8 * kNumSM;
     load_inputs_kernel<<<grid, 256, 0, as_stream(stream)>>>(reinterpret_cast<const float4*>(x_src),
-                                                            reinterpret_cast<float4*>(x_dst), n4, idx_src, idx_dst,
-                                                            nsegs_src, nsegs_dst, B);
+                                                            reinterpret_cast<float4*>(x_dst), reinterpret_cast<float4*>(x_tm),
+                                                            n4, B, T, F / 4, idx_src, idx_dst, nsegs_src, nsegs_dst);
     FHVAE_LAUNCH_CHECK("load_inputs");
     return 0;
 }

@@ -250,7 +250,7 @@ class _FHVAECore(nn.Module):
             raise RuntimeError("pytorch_scalablefhvae_b200 has no CPU path")
         B, T, F = x.shape
         plan = self._plan(B, T, F)
-        plan.x.copy_(x, non_blocking=True)
+        plan.set_x(x)
         if eps is None:
             plan.eps1.zero_(); plan.eps2.zero_()
         else:
@@ -358,17 +358,33 @@ class _Plan:
         self._graph_bwd = [None, None]
 
     # ---- inputs / outputs
+    def set_x(self, x, mu_idx=None, num_segs=None):
+        """x -> the plan's static (B,T,F) buffer and, where the plan keeps one, its time-major copy; optionally the
+        two id vectors in the same launch.  Every entry (forward, train_step, encode) loads x through here."""
+        x_tm = self.__dict__.get("x_tm")
+        if (x.device == self.dev and x.dtype == torch.float32 and x.is_contiguous() and x.shape == self.x.shape
+                and self.F % 4 == 0 and x.data_ptr() % 16 == 0):
+            _lib.check(_lib.fn("fhvae_load_inputs")(
+                ptr(x), ptr(self.x), ptr(x_tm) if x_tm is not None else None, self.B, self.T, self.F,
+                ptr(mu_idx) if mu_idx is not None else None, ptr(self.idx),
+                ptr(num_segs) if num_segs is not None else None, ptr(self.nsegs), current_stream_ptr()),
+                "fhvae_load_inputs")
+            return
+        self.x.copy_(x, non_blocking=True)
+        if x_tm is not None:
+            _lib.check(_lib.fn("fhvae_transpose_bt")(ptr(self.x), ptr(x_tm), self.B, self.T, self.F,
+                                                     current_stream_ptr()), "fhvae_transpose_bt")
+        if mu_idx is not None:
+            self.idx.copy_(mu_idx, non_blocking=True)
+            self.nsegs.copy_(num_segs, non_blocking=True)
+
     def load_inputs(self, x, mu_idx, num_segs, eps):
         dev = self.dev
-        if (x.device == dev and mu_idx.device == dev and torch.is_tensor(num_segs) and num_segs.device == dev
-                and x.dtype == torch.float32 and mu_idx.dtype == torch.int64 and num_segs.dtype == torch.int64
-                and x.is_contiguous() and mu_idx.is_contiguous() and num_segs.is_contiguous()
-                and x.numel() % 4 == 0 and x.data_ptr() % 16 == 0 and x.shape == self.x.shape):
-            _lib.check(_lib.fn("fhvae_load_inputs")(ptr(x), ptr(self.x), x.numel(), ptr(mu_idx), ptr(self.idx),
-                                                    ptr(num_segs), ptr(self.nsegs), self.B, current_stream_ptr()),
-                       "fhvae_load_inputs")
-        else:
-            self.x.copy_(x, non_blocking=True)
+        on_dev = lambda t: (torch.is_tensor(t) and t.device == dev and t.dtype == torch.int64 and t.is_contiguous()
+                            and t.numel() == self.B)
+        fused_ids = on_dev(mu_idx) and on_dev(num_segs)
+        self.set_x(x, mu_idx if fused_ids else None, num_segs if fused_ids else None)
+        if not fused_ids:
             self.idx.copy_(mu_idx, non_blocking=True)
             if torch.is_tensor(num_segs):
                 self.nsegs.copy_(num_segs, non_blocking=True)
@@ -637,8 +653,7 @@ class _FHVAEPlan(_Plan):
         Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
         wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
         wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
-        c.add("fhvae_transpose_bt", ptr(self.x), ptr(self.x_tm), B, T, F)
-        c.join(2)
+        c.join(2)          # (x_tm, the time-major copy of x, is written together with x by _Plan.set_x)
         # layer-0 projections of x: the z2 encoder's is on the critical path, the z1 encoder's overlaps the
         # z2 recurrence on side stream 1 (joined before the z1 stack).  (Running them on the TMA-fed kernel over
         # feature-major planes of x was tried: 19.4 us vs 22 us -- both are bound by the 21 MB output, not worth two

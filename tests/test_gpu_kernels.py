@@ -542,6 +542,21 @@ def test_step_coef_and_loss_mean():
     assert_close(loss.reshape(1), -(gout[0].double() + 10.0 * gout[5].double()).mean().reshape(1), 1e-6, "loss")
 
 
+def test_load_inputs_exact():
+    """x / mu_idx / num_segs into the static buffers in one launch, x also time-major: bit-exact copies."""
+    B, T, F = 37, 5, 8
+    x = rnd(B, T, F, seed=1)
+    g = torch.Generator().manual_seed(2)
+    idx, ns = torch.randint(0, 1000, (B,), generator=g).to(DEV), torch.randint(1, 99, (B,), generator=g).to(DEV)
+    xd, xtm = torch.zeros(B, T, F, device=DEV), torch.zeros(T, B, F, device=DEV)
+    idd, nsd = torch.zeros(B, dtype=torch.int64, device=DEV), torch.zeros(B, dtype=torch.int64, device=DEV)
+    call("fhvae_load_inputs", ptr(x), ptr(xd), ptr(xtm), B, T, F, ptr(idx), ptr(idd), ptr(ns), ptr(nsd))
+    assert torch.equal(xd, x) and torch.equal(xtm, x.permute(1, 0, 2)) and torch.equal(idd, idx) and torch.equal(nsd, ns)
+    xd2 = torch.zeros(B, T, F, device=DEV)
+    call("fhvae_load_inputs", ptr(x), ptr(xd2), None, B, T, F, None, None, None, None)
+    assert torch.equal(xd2, x)
+
+
 # ------------------------------------------------------------------------------- discriminative term
 @pytest.mark.parametrize("B,N,Z", [(5, 12, 16), (64, 1000, 16), (256, 5000, 32), (33, 129, 8)])
 def test_disc_fwd_bwd(B, N, Z):
