@@ -308,6 +308,13 @@ int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* dh_last_top
 int fhvae_load_inputs(const float* x_src, float* x_dst, float* x_tm, int B, int T, int F, const int64_t* idx_src,
                       int64_t* idx_dst, const int64_t* nsegs_src, int64_t* nsegs_dst, void* stream);
 
+/* fhvae_elbo_fwd + fhvae_step_coef + fhvae_elbo_bwd as one launch, for a step whose upstream gradients gout (6,B)
+ * are known before the forward (the fused train step).  Bit-identical to the three separate calls. */
+int fhvae_elbo_fwd_bwd(const float* x, const float* xhead, int64_t xs_b, int64_t xs_t, int64_t lv_off,
+                       const float* z1head, const float* z2head, const float* mu2, const int64_t* nsegs,
+                       const float* gout, int detach_px, int prior_grad, float* out5, int* nan_flag, float* dxhead,
+                       float* dz1head, float* dz2head, float* dmu2, int B, int T, int F, int Z1, int Z2, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

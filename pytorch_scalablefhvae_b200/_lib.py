@@ -66,6 +66,7 @@ PROTOTYPES = {
     "fhvae_reparam_bwd": [_p, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p],
     "fhvae_elbo_fwd": [_p, _p, _l, _l, _l, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fhvae_elbo_bwd": [_p, _p, _l, _l, _l, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
+    "fhvae_elbo_fwd_bwd": [_p, _p, _l, _l, _l, _p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p],
     "fhvae_disc_nsplit": [_i, _l],
     "fhvae_disc_fwd_partial": [_p, _l, _p, _l, _i, _p, _i, _i, _p],
     "fhvae_disc_target": [_p, _l, _p, _p, _i, _i, _p],

@@ -467,10 +467,12 @@ class _Plan:
             self._loss_call = (lc, alpha)
         loss_call = self._loss_call[0]
 
+        fwd_list, bwd_list = self._train_lists(k)
+
         def fwd_bwd():
-            self.fwd.run(current_stream_ptr())
+            fwd_list.run(current_stream_ptr())
             loss_call.run(current_stream_ptr(), join=False)   # side stream 1; joined by the backward list
-            self.bwd[k].run(current_stream_ptr())
+            bwd_list.run(current_stream_ptr())
 
         def adam():
             optimizer.step_flat(m, gflat)
@@ -495,6 +497,31 @@ class _Plan:
                 allreduce(gflat)
                 g2.replay()
         return self.loss
+
+    def _train_lists(self, k):
+        """Call lists of the fused train step.  The upstream gradients are known before the forward there, so the
+        chain [elbo_fwd] ... [step_coef, elbo_bwd] at the forward/backward seam collapses into one
+        ``fhvae_elbo_fwd_bwd`` launch (bit-identical results); everything else is shared with the autograd path."""
+        cache = self.__dict__.setdefault("_train_list_cache", {})
+        if k in cache:
+            return cache[k]
+        fwd, bwd = self.fwd, self.bwd[k]
+        lists = (fwd, bwd)
+        names = lambda cl, sl: [c_[1] for c_ in cl.calls[sl]]
+        if (os.environ.get("FHVAE_FUSED_ELBO", "1") != "0" and names(fwd, slice(-1, None)) == ["fhvae_elbo_fwd"]
+                and names(bwd, slice(0, 2)) == ["fhvae_step_coef", "fhvae_elbo_bwd"]):
+            fa, ca, ba = fwd.calls[-1][2], bwd.calls[0][2], bwd.calls[1][2]
+            # elbo_fwd: (x, xhead, xs_b, xs_t, lv_off, z1head, z2head, mu2, nsegs, out, nan_flag, B, T, F, Z1, Z2)
+            # step_coef: (gout, nsegs, coef, detach_px, prior_grad, B)
+            # elbo_bwd: (x, xhead, xs_b, xs_t, lv_off, z1head, z2head, mu2, coef, dxhead, dz1head, dz2head, dmu2, B, ...)
+            fused = (_lib.fn("fhvae_elbo_fwd_bwd"), "fhvae_elbo_fwd_bwd",
+                     fa[:9] + (ca[0], ca[3], ca[4]) + fa[9:11] + ba[9:13] + fa[11:], 0)
+            ft, bt = CallList(), CallList()
+            ft.calls, ft.keep = fwd.calls[:-1] + [fused], fwd.keep
+            bt.calls, bt.keep = bwd.calls[2:], bwd.keep
+            lists = (ft, bt)
+        cache[k] = lists
+        return lists
 
     def _capture(self, f, restore=None):
         # the warm-up run below really executes f once: snapshot what an optimizer step would change

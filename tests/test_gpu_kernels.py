@@ -433,6 +433,34 @@ def test_elbo_fwd_bwd(B, T, F, Z, layout):
     assert_close(dmu2, mu2.grad, 1e-5, "d mu2")
 
 
+def test_elbo_fwd_bwd_fused_is_bit_identical():
+    """fhvae_elbo_fwd_bwd == fhvae_elbo_fwd + fhvae_step_coef + fhvae_elbo_bwd, bit for bit (both decoder-head layouts)."""
+    B, T, F, Z = 37, 6, 8, 12
+    for layout in ("tbf", "btf"):
+        x = rnd(B, T, F, seed=1)
+        xh = rnd(T, B, 2 * F, seed=2) if layout == "tbf" else rnd(B, 2 * T * F, seed=2)
+        xs_b, xs_t, lv = (2 * F, B * 2 * F, F) if layout == "tbf" else (2 * T * F, F, T * F)
+        h1, h2, m2 = rnd(B, 2 * Z, seed=3), rnd(B, 2 * Z, seed=4), rnd(B, Z, seed=5)
+        ns = torch.randint(1, 300, (B,), generator=torch.Generator().manual_seed(6)).to(DEV)
+        gout = rnd(6, B, seed=7)
+        for detach, prior in ((0, 1), (1, 0)):
+            out_a, out_b = torch.zeros(5, B, device=DEV), torch.zeros(5, B, device=DEV)
+            fl = torch.zeros(1, dtype=torch.int32, device=DEV)
+            coef = torch.zeros(4, B, device=DEV)
+            d_a = [torch.zeros_like(xh), torch.zeros(B, 2 * Z, device=DEV), torch.zeros(B, 2 * Z, device=DEV), torch.zeros(B, Z, device=DEV)]
+            d_b = [torch.zeros_like(t) for t in d_a]
+            call("fhvae_elbo_fwd", ptr(x), ptr(xh), xs_b, xs_t, lv, ptr(h1), ptr(h2), ptr(m2), ptr(ns), ptr(out_a), ptr(fl),
+                 B, T, F, Z, Z)
+            call("fhvae_step_coef", ptr(gout), ptr(ns), ptr(coef), detach, prior, B)
+            call("fhvae_elbo_bwd", ptr(x), ptr(xh), xs_b, xs_t, lv, ptr(h1), ptr(h2), ptr(m2), ptr(coef), ptr(d_a[0]),
+                 ptr(d_a[1]), ptr(d_a[2]), ptr(d_a[3]), B, T, F, Z, Z)
+            call("fhvae_elbo_fwd_bwd", ptr(x), ptr(xh), xs_b, xs_t, lv, ptr(h1), ptr(h2), ptr(m2), ptr(ns), ptr(gout), detach,
+                 prior, ptr(out_b), ptr(fl), ptr(d_b[0]), ptr(d_b[1]), ptr(d_b[2]), ptr(d_b[3]), B, T, F, Z, Z)
+            assert torch.equal(out_a, out_b)
+            for a, b in zip(d_a, d_b):
+                assert torch.equal(a, b)
+
+
 def test_elbo_nan_flag():
     B, T, F, Z = 4, 2, 4, 8
     z = lambda *s: torch.zeros(*s, device=DEV)
