@@ -36,6 +36,11 @@ extern "C" {
 #define FHVAE_MODE_BF16X3   1   /* tcgen05 kind::f16, hi/lo bf16 split x3 (fp32-parity mode)   */
 #define FHVAE_MODE_BF16     2   /* tcgen05 kind::f16, single bf16 pass ("bf16 input-GEMM mode") */
 
+/* bits of the per-plan device status word (the `nan_flag` argument of fhvae_elbo_fwd, the `err_flag` of the
+ * table kernels): the host reads it when it wants to (train_model.py:464-466 is a forced sync upstream) */
+#define FHVAE_FLAG_NAN        1  /* a NaN lower bound was produced (train_model.py:464)            */
+#define FHVAE_FLAG_BAD_INDEX  2  /* mu_idx / label outside [0, N): torch.gather would have raised  */
+
 const char* fhvae_last_error_string(void);
 int fhvae_version(void);
 /* compile-time facts the host may assert on */
@@ -180,8 +185,11 @@ int fhvae_disc_bwd_finish(const float* z2mu, int64_t ld_z, const float* mu2, con
 /* ---------------------------------------------------------------------------------------------
  * K0: mu2 table (simple_fhvae.py:39-54).  Exact int64 indexing; deterministic reductions.
  * ------------------------------------------------------------------------------------------- */
+/* Rows outside [0,N) (torch.gather raises, simple_fhvae.py:53): the output row is NaN (so the lower bound trips
+ * the reference's own NaN guard) and FHVAE_FLAG_BAD_INDEX is OR-ed into *err_flag (may be NULL).  The scatter
+ * and accumulate kernels never write outside the table: such rows are skipped. */
 int fhvae_mu2_gather(const float* table, const int64_t* idx, float* mu2, int B, int Z, int64_t N,
-                     void* stream);
+                     int32_t* err_flag, void* stream);
 /* dtable[idx[b]] += sum over duplicates (ascending b, fixed order).  touched (B,) int32: 1 at the
  * first occurrence of each distinct row, else 0 (the "rows touched" set). */
 int fhvae_mu2_scatter_reduce(const float* dmu2, const int64_t* idx, float* dtable, int32_t* touched,
@@ -189,7 +197,7 @@ int fhvae_mu2_scatter_reduce(const float* dmu2, const int64_t* idx, float* dtabl
 /* utils.py:45-60 batched: zsum (K,Z) += z2mu rows, cnt (K,) += 1  (deterministic per row), then
  * fhvae_mu2_estimate_finish: table[k] = zsum[k] / (cnt[k] + r) where cnt>0.  */
 int fhvae_mu2_accumulate(const float* z2mu, int64_t ld_z, const int64_t* idx, float* zsum, float* cnt,
-                         int B, int Z, int64_t K, void* stream);
+                         int B, int Z, int64_t K, int32_t* err_flag, void* stream);
 int fhvae_mu2_estimate_finish(const float* zsum, const float* cnt, float* table, float r,
                               int64_t K, int Z, void* stream);
 /* sparse row write-back / fetch between a master shard and the active cache (hierarchical sampling):

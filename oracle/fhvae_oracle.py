@@ -255,6 +255,114 @@ class FHVAEOracle(_FHVAEBase):
 
 
 # --------------------------------------------------------------------------------------
+# Second, independent pin of O3: a hand-written fp64 numpy LSTM cell + closed-form loss (SURVEY.md
+# Appendix C), sharing NO code with torch.nn.LSTM / autograd.  tests/test_oracle.py checks FHVAEOracle
+# against it, so a change of torch's LSTM conventions (gate order i,f,g,o; b_ih + b_hh; zero initial
+# state; layer stacking) cannot silently move the oracle.
+# --------------------------------------------------------------------------------------
+def _sigm(a):
+    return 1.0 / (1.0 + np.exp(-a))
+
+
+def lstm_stack_fp64(x, weights):
+    """x (B,T,In) float64; weights = [(W_ih (4H,In_l), W_hh (4H,H), b_ih, b_hh)] per layer.
+    Returns (outputs of the last layer (B,T,H), final h of every layer [(B,H)], cache for the backward)."""
+    B, T, _ = x.shape
+    inp, finals, cache = x, [], []
+    for (W_ih, W_hh, b_ih, b_hh) in weights:
+        H = W_hh.shape[1]
+        h, c = np.zeros((B, H)), np.zeros((B, H))
+        outs, steps = np.zeros((B, T, H)), []
+        for t in range(T):
+            g = inp[:, t] @ W_ih.T + b_ih + h @ W_hh.T + b_hh
+            i, f, gg, o = _sigm(g[:, :H]), _sigm(g[:, H:2 * H]), np.tanh(g[:, 2 * H:3 * H]), _sigm(g[:, 3 * H:])
+            c_new = f * c + i * gg
+            h_new = o * np.tanh(c_new)
+            steps.append((inp[:, t], h, c, i, f, gg, o, c_new))
+            h, c = h_new, c_new
+            outs[:, t] = h
+        finals.append(h)
+        cache.append(steps)
+        inp = outs
+    return inp, finals, cache
+
+
+def lstm_stack_bwd_fp64(d_out, d_finals, weights, cache):
+    """Closed-form BPTT (Appendix C).  d_out (B,T,H) gradient of the last layer's outputs, d_finals[l] (B,H)
+    gradient of layer l's final h.  Returns (dx (B,T,In), [(dW_ih, dW_hh, db_ih, db_hh)] per layer)."""
+    grads = [None] * len(weights)
+    d_seq = d_out
+    for l in reversed(range(len(weights))):
+        W_ih, W_hh, _, _ = weights[l]
+        steps = cache[l]
+        T, H = len(steps), W_hh.shape[1]
+        B = steps[0][1].shape[0]
+        dW_ih, dW_hh, db = np.zeros_like(W_ih), np.zeros_like(W_hh), np.zeros(4 * H)
+        dx = np.zeros((B, T, W_ih.shape[1]))
+        dh_next, dc_next = np.zeros((B, H)), np.zeros((B, H))
+        for t in reversed(range(T)):
+            x_t, h_prev, c_prev, i, f, gg, o, c_new = steps[t]
+            dh = d_seq[:, t] + dh_next + (d_finals[l] if t == T - 1 else 0.0)
+            tc = np.tanh(c_new)
+            dc = dc_next + dh * o * (1 - tc * tc)
+            dg = np.concatenate([dc * gg * i * (1 - i), dc * c_prev * f * (1 - f), dc * i * (1 - gg * gg),
+                                 dh * tc * o * (1 - o)], axis=1)
+            dW_ih += dg.T @ x_t
+            dW_hh += dg.T @ h_prev
+            db += dg.sum(0)
+            dx[:, t] = dg @ W_ih
+            dh_next = dg @ W_hh
+            dc_next = dc * f
+        grads[l] = (dW_ih, dW_hh, db, db.copy())
+        d_seq = dx
+    return d_seq, grads
+
+
+def fhvae_forward_fp64(model: "FHVAEOracle", x, mu_idx, num_segs, eps, alpha=10.0):
+    """The whole FHVAE forward (Appendix B architecture, Appendix C maths) in numpy float64 from the weights of
+    an FHVAEOracle: returns dict of the six outputs + loss.  Independent of nn.LSTM and of the torch loss code."""
+    sd = {k: v.detach().double().numpy() for k, v in model.state_dict().items()}
+    x = x.double().numpy()
+    idx = mu_idx.numpy()
+    nseg = num_segs.double().numpy() if torch.is_tensor(num_segs) else np.full(x.shape[0], float(num_segs))
+    B, T, F = x.shape
+
+    def stack(prefix, L):
+        return [(sd[f"{prefix}.lstm.weight_ih_l{l}"], sd[f"{prefix}.lstm.weight_hh_l{l}"],
+                 sd[f"{prefix}.lstm.bias_ih_l{l}"], sd[f"{prefix}.lstm.bias_hh_l{l}"]) for l in range(L)]
+
+    def head(prefix, h):
+        return (h @ sd[prefix + ".mulayer.weight"].T + sd[prefix + ".mulayer.bias"],
+                h @ sd[prefix + ".logvar_layer.weight"].T + sd[prefix + ".logvar_layer.bias"])
+
+    table = sd["mu2_table"]
+    mu2 = table[idx]
+    _, fin, _ = lstm_stack_fp64(x, stack("z2_pre_encoder", len(model.z2_hus)))
+    z2_mu, z2_lv = head("z2_gauss_layer", np.concatenate(fin, axis=1))
+    z2_s = z2_mu + eps["z2"].double().numpy() * np.exp(0.5 * z2_lv)
+    x1 = np.concatenate([x, np.repeat(z2_s[:, None, :], T, axis=1)], axis=2)
+    _, fin, _ = lstm_stack_fp64(x1, stack("z1_pre_encoder", len(model.z1_hus)))
+    z1_mu, z1_lv = head("z1_gauss_layer", np.concatenate(fin, axis=1))
+    z1_s = z1_mu + eps["z1"].double().numpy() * np.exp(0.5 * z1_lv)
+    din = np.repeat(np.concatenate([z1_s, z2_s], axis=1)[:, None, :], T, axis=1)
+    out, _, _ = lstm_stack_fp64(din, stack("pre_decoder", len(model.x_hus)))
+    x_mu, x_lv = head("dec_gauss_layer", out)
+    lg = lambda v, mu, lv: -0.5 * (LOG_2PI + lv + (v - mu) ** 2 * np.exp(-lv))
+    kl = lambda pm, pl, qm, c: -0.5 * (1 + pl - c - ((pm - qm) ** 2 + np.exp(pl)) * np.exp(-c))
+    log_px = lg(x, x_mu, x_lv).sum(axis=(1, 2))
+    nk1 = -kl(z1_mu, z1_lv, 0.0, PZ1[1]).sum(1)
+    nk2 = -kl(z2_mu, z2_lv, mu2, PZ2_LOGVAR).sum(1)
+    log_pmu2 = lg(mu2, PMU2[0], PMU2[1]).sum(1)
+    lb = log_px + nk1 + nk2 + log_pmu2 / nseg
+    s = -((z2_mu[:, None, :] - table[None]) ** 2).sum(-1) / (2 * math.exp(PZ2_LOGVAR))
+    mx = s.max(1, keepdims=True)
+    lse = mx[:, 0] + np.log(np.exp(s - mx).sum(1))
+    log_qy = s[np.arange(B), idx] - lse
+    return {"lower_bound": lb, "log_qy": log_qy, "log_px_z": log_px, "neg_kld_z1": nk1, "neg_kld_z2": nk2,
+            "log_pmu2": log_pmu2, "loss": -np.mean(lb + alpha * log_qy)}
+
+
+# --------------------------------------------------------------------------------------
 # mu2 estimation (hierarchical-sampling cache refresh / inference), utils.py:45-60
 # --------------------------------------------------------------------------------------
 def estimate_mu2_dict(z2_mu_batches: Sequence[torch.Tensor], idx_batches: Sequence[torch.Tensor]):

@@ -15,6 +15,10 @@ Fixtures written:
   and the as-is gradients (encoders + table; the reference's decoder gets none) of a tiny config.
 * ``simple_fhvae_c0_kat.json`` -- the seeded config-0 known-answer scalars of SURVEY.md §4,
   regenerated with the installed torch (uninjected: the reference's own RNG draws).
+* ``fhvae_o3_small.npz`` -- O3 (the nn.LSTM restatement; the reference's fhvae.py is a stub, so this one is NOT
+  produced by the reference): weights, inputs, eps, six outputs, loss and every gradient of a small 2x32 LSTM
+  FHVAE.  It makes the authoring box and the GPU box provably use the same oracle values (a torch upgrade that moved
+  nn.LSTM would fail tests/test_oracle.py::test_o3_reproduces_its_golden).  Does not need /root/reference.
 * ``hier_sample.json`` -- np.random.choice(seqlist, K, replace=False) under np.random.seed(s)
   (train_model.py:426-428) for a 1000-utterance list, K=50.
 """
@@ -131,9 +135,38 @@ def hier():
         json.dump({"seed": 5, "n": 1000, "k": 50, "sampled": s.tolist()}, f)
 
 
+def fhvae_o3_small():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+    from oracle import fhvae_oracle as O
+    T, F, B, N, Z1, Z2, H = 6, 8, 10, 13, 8, 16, 32
+    torch.manual_seed(21)
+    m = O.FHVAEOracle(T * F, [H, H], [H, H], Z1, Z2, [H, H], seg_len=T, num_seqs=N)
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(B, T, F, generator=g)
+    idx = torch.tensor([3, 0, 12, 3, 7, 7, 7, 1, 12, 5])      # duplicates + first + last row
+    nsegs = torch.randint(1, 120, (B,), generator=g)
+    eps = {"z2": torch.randn(B, Z2, generator=g), "z1": torch.randn(B, Z1, generator=g)}
+    out = m(x, idx, N, nsegs, eps=eps)
+    loss = O.loss_function(out[0], out[1], 10.0)
+    loss.backward()
+    d = {"x": x, "idx": idx, "nsegs": nsegs, "eps_z2": eps["z2"], "eps_z1": eps["z1"], "loss": loss}
+    for n, o in zip(["lower_bound", "log_qy", "log_px_z", "neg_kld_z1", "neg_kld_z2", "log_pmu2"], out):
+        d["out_" + n] = o
+    for k, v in m.state_dict().items():
+        d["w:" + k] = v
+    for k, p in m.named_parameters():
+        d["g:" + k] = p.grad
+    d["meta"] = np.array([T, F, B, N, Z1, Z2, H])
+    np.savez_compressed(os.path.join(OUT, "fhvae_o3_small.npz"),
+                        **{k: (v.detach().numpy() if torch.is_tensor(v) else v) for k, v in d.items()})
+    print("fhvae_o3_small: loss", float(loss), "torch", torch.__version__)
+
+
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
-    ref = _import_reference()
-    tiny(ref)
-    config0_kat(ref)
-    hier()
+    fhvae_o3_small()
+    if os.path.isdir(REF):
+        ref = _import_reference()
+        tiny(ref)
+        config0_kat(ref)
+        hier()

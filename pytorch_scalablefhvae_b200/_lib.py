@@ -19,6 +19,7 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", 
               "-Xcompiler", "-fPIC", "-shared"]
 
 MODE_F32_SIMT, MODE_BF16X3, MODE_BF16 = 0, 1, 2
+FLAG_NAN, FLAG_BAD_INDEX = 1, 2          # bits of the device status word (include/fhvae_b200.h)
 GEMM_MAX_BATCH = 24
 WGRAD_MAX_BATCH = 8
 SPLIT_MAX_BATCH = 16
@@ -74,9 +75,9 @@ PROTOTYPES = {
     "fhvae_disc_bwd_rows": [_p, _l, _p, _l, _i, _p, _p, _p, _i, _p],
     "fhvae_disc_bwd_segs": [_p, _l, _p, _l, _i, _p, _p, _i, _i, _p],
     "fhvae_disc_bwd_finish": [_p, _l, _p, _p, _i, _p, _p, _l, _p, _i, _i, _p],
-    "fhvae_mu2_gather": [_p, _p, _p, _i, _i, _l, _p],
+    "fhvae_mu2_gather": [_p, _p, _p, _i, _i, _l, _p, _p],
     "fhvae_mu2_scatter_reduce": [_p, _p, _p, _p, _i, _i, _l, _p],
-    "fhvae_mu2_accumulate": [_p, _l, _p, _p, _p, _i, _i, _l, _p],
+    "fhvae_mu2_accumulate": [_p, _l, _p, _p, _p, _i, _i, _l, _p, _p],
     "fhvae_mu2_estimate_finish": [_p, _p, _p, _f, _l, _i, _p],
     "fhvae_rows_copy": [_p, _p, _p, _p, _l, _i, _p],
     "fhvae_adam_flat": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _p, _p, _p],

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(
             out5[2 * B + b] = k1;
             out5[3 * B + b] = k2;
             out5[4 * B + b] = pm;
-            if (nan_flag && isnan(lb)) *nan_flag = 1;
+            if (nan_flag && isnan(lb)) atomicOr(nan_flag, FHVAE_FLAG_NAN);
         }
     }
 }
@@ -229,7 +229,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwdbwd_kernel(
             out5[2 * B + b] = k1;
             out5[3 * B + b] = k2;
             out5[4 * B + b] = pm;
-            if (nan_flag && isnan(lb)) *nan_flag = 1;
+            if (nan_flag && isnan(lb)) atomicOr(nan_flag, FHVAE_FLAG_NAN);
         }
     }
     for (int d = tid; d < Z1; d += ELBO_THREADS) {

@@ -61,6 +61,25 @@ __device__ __forceinline__ uint32_t wait_ll(uint4& v, const uint4* p, uint32_t f
     return spins;
 }
 
+// Wait for N LL words at once: every retry round re-issues ALL still-invalid loads back to back, so a round costs
+// one L2 round trip (~260 cycles) however many words are outstanding.  (Waiting word by word -- wait_ll in a loop --
+// serialises the round trips: 7 peer slices that all miss their first poll cost 7 dependent trips, which was
+// 2900-3700 of the 10600 cycles of a forward wavefront step in round 1.)
+template <int N, typename AddrFn>
+__device__ __forceinline__ uint32_t wait_ll_all(uint4 (&v)[N], AddrFn addr, uint32_t flag) {
+    uint32_t spins = 0;
+    for (;;) {
+        uint32_t bad = 0;
+#pragma unroll
+        for (int i = 0; i < N; ++i) bad |= (v[i].y != flag || v[i].w != flag) ? (1u << i) : 0u;
+        if (!bad) return spins;
+        if (++spins > FHVAE_SPIN_LIMIT) __trap();
+#pragma unroll
+        for (int i = 0; i < N; ++i)
+            if ((bad >> i) & 1u) v[i] = ld_ll(addr(i));
+    }
+}
+
 #ifdef FHVAE_TIMELINE
 __device__ long long g_wave_tl[2][32][16];
 #define WTL(step, slot) do { if (rank == 0 && grp == 0 && threadIdx.x == 0 && (step) < 32) g_wave_tl[layer][step][slot] = clock64(); } while (0)
@@ -112,10 +131,10 @@ __device__ __forceinline__ void wave_store(const uint4* slot, int rank, uint32_t
     if (tid < NW) {
         const int part = tid >> 8, rem = tid & 255, chunk = rem >> 1, half = rem & 1;
         const int kcl = chunk / WNB, row = chunk % WNB;
+        wait_ll_all<NS>(v, [&](int i) { return slot + (SKIP_OWN ? i + (i >= rank ? 1 : 0) : i) * WSLICE + tid; }, flag);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int src = SKIP_OWN ? i + (i >= rank ? 1 : 0) : i;
-            wait_ll(v[i], slot + src * WSLICE + tid, flag);
             *reinterpret_cast<uint2*>(dst + part * S::H_PART + (uint32_t)(src * 4 + kcl) * (WNB * 16) + row * 16 + half * 8) =
                 make_uint2(v[i].x, v[i].z);
         }
@@ -338,6 +357,20 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             const bool real = t < T;
             WTL(t, 0);
             uint8_t* hbt = smem + S::H_OFF + (t & 1) * S::H_BUF;
+            // this step's input projection is requested FIRST (layer 0: the GEMM-produced P0 from HBM, layer 1: layer 0's
+            // LL words): its latency then hides behind the exchange below instead of following it
+            float pv[CPW];
+            uint4 pl[CPW / 2];
+            if (real) {
+                if (layer == 0) {
+                    const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
+#pragma unroll
+                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
+                }
+            }
             if (t > 0) {
                 // h_{t-1}: the 7 peer slices (own slice was written locally by the cell phase)
                 const uint4* slot = own + (size_t)(t - 1) * (WG * WSLICE);
@@ -351,19 +384,6 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_full[t & 1]);
                 store_saved(t - 1);          // HBM stores of the previous step ride in the shadow of this step's MMAs
-            }
-            // this step's input projection: layer 0 from the GEMM-produced P0, layer 1 from layer 0's LL words
-            float pv[CPW];
-            uint4 pl[CPW / 2];
-            if (real) {
-                if (layer == 0) {
-                    const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
-#pragma unroll
-                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
-                } else {
-#pragma unroll
-                    for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
-                }
             }
             WTL(t, 1);
             if (real) {
@@ -386,9 +406,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
                 WTL(t, 3);
                 if (layer == 1) {
+                    wait_ll_all<CPW / 2>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
 #pragma unroll
                     for (int j = 0; j < CPW / 2; ++j) {
-                        wait_ll(pl[j], p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128, fbase + t + 1);
                         pv[2 * j] = __uint_as_float(pl[j].x);
                         pv[2 * j + 1] = __uint_as_float(pl[j].z);
                     }
@@ -680,10 +700,10 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
             uint4 v[PER];
 #pragma unroll
             for (int i = 0; i < PER; ++i) v[i] = ld_ll(src + tid + i * NT);
+            wait_ll_all<PER>(v, [&](int i) { return src + tid + i * NT; }, fbase + (uint32_t)(T - t));
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int w = tid + i * NT;
-                wait_ll(v[i], src + w, fbase + (uint32_t)(T - t));
                 *reinterpret_cast<uint2*>(dst + (w >> 10) * S::G_PART + (w & 1023) * 8) = make_uint2(v[i].x, v[i].z);
             }
         };
@@ -770,9 +790,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 uint4 pr[WG];
 #pragma unroll
                 for (int src = 0; src < WG; ++src) pr[src] = ld_ll(rd + src * WRS);
+                wait_ll_all<WG>(pr, [&](int src) { return rd + src * WRS; }, fbase + k + 1);
 #pragma unroll
-                for (int src = 0; src < WG; ++src) {
-                    wait_ll(pr[src], rd + src * WRS, fbase + k + 1);
+                for (int src = 0; src < WG; ++src) {                      // fixed summation order: deterministic
                     dh[0] += __uint_as_float(pr[src].x);
                     dh[1] += __uint_as_float(pr[src].z);
                 }

@@ -8,11 +8,20 @@ namespace fhvae {
 
 // ---------------------------------------------------------------- K0: table ----------------------
 __global__ void mu2_gather_kernel(const float* __restrict__ table, const int64_t* __restrict__ idx,
-                                  float* __restrict__ mu2, int B, int Z) {
+                                  float* __restrict__ mu2, int B, int Z, int64_t N,
+                                  int32_t* __restrict__ err_flag) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * Z) return;
     const int b = i / Z, d = i % Z;
-    mu2[i] = __ldg(table + idx[b] * Z + d);        // torch.gather(table, 0, idx), simple_fhvae.py:53
+    const int64_t row = idx[b];
+    if (row < 0 || row >= N) {
+        // torch.gather raises on an out-of-range row (simple_fhvae.py:53); a device-resident idx cannot raise
+        // without a host sync, so the row is poisoned (-> NaN lower bound, train_model.py:464 guard) and flagged
+        mu2[i] = __int_as_float(0x7fc00000);
+        if (err_flag && d == 0) atomicOr(err_flag, FHVAE_FLAG_BAD_INDEX);
+        return;
+    }
+    mu2[i] = __ldg(table + row * Z + d);           // torch.gather(table, 0, idx), simple_fhvae.py:53
 }
 
 // dst[idx[b]] += sum of src rows with the same idx, summed in ascending b by the first occurrence.
@@ -21,10 +30,17 @@ __global__ void mu2_gather_kernel(const float* __restrict__ table, const int64_t
 __global__ void scatter_reduce_kernel(const float* __restrict__ src, int64_t ld_src,
                                       const int64_t* __restrict__ idx, float* __restrict__ dst,
                                       float* __restrict__ cnt, int32_t* __restrict__ touched, int B,
-                                      int Z) {
+                                      int Z, int64_t N, int32_t* __restrict__ err_flag) {
     const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), l = threadIdx.x & 31;
     if (b >= B) return;
     const int64_t row = idx[b];
+    if (row < 0 || row >= N) {                            // never write outside the table (see mu2_gather_kernel)
+        if (l == 0) {
+            if (touched) touched[b] = 0;
+            if (err_flag) atomicOr(err_flag, FHVAE_FLAG_BAD_INDEX);
+        }
+        return;
+    }
     // warp-parallel match of idx[] against this segment's row, 32 segments per ballot.  An earlier segment
     // with the same row owns the sum (first occurrence); later ones are added in ascending b, so the
     // summation order -- hence the result -- is exactly that of a serial scan.
@@ -253,9 +269,9 @@ __global__ void axpy_kernel(float* __restrict__ y, const float* __restrict__ x, 
 using namespace fhvae;
 
 extern "C" int fhvae_mu2_gather(const float* table, const int64_t* idx, float* mu2, int B, int Z,
-                                int64_t N, void* stream) {
+                                int64_t N, int32_t* err_flag, void* stream) {
     FHVAE_CHECK_ARG(table && idx && mu2 && B > 0 && Z > 0 && N > 0, "mu2_gather: bad argument");
-    mu2_gather_kernel<<<cdiv((int64_t)B * Z, 256), 256, 0, as_stream(stream)>>>(table, idx, mu2, B, Z);
+    mu2_gather_kernel<<<cdiv((int64_t)B * Z, 256), 256, 0, as_stream(stream)>>>(table, idx, mu2, B, Z, N, err_flag);
     FHVAE_LAUNCH_CHECK("mu2_gather");
     return 0;
 }
@@ -264,16 +280,16 @@ extern "C" int fhvae_mu2_scatter_reduce(const float* dmu2, const int64_t* idx, f
                                         int32_t* touched, int B, int Z, int64_t N, void* stream) {
     FHVAE_CHECK_ARG(dmu2 && idx && dtable && B > 0 && Z > 0 && N > 0, "mu2_scatter_reduce: bad argument");
     scatter_reduce_kernel<<<cdiv(B, 8), 256, 0, as_stream(stream)>>>(dmu2, Z, idx, dtable, nullptr,
-                                                                     touched, B, Z);
+                                                                     touched, B, Z, N, nullptr);
     FHVAE_LAUNCH_CHECK("mu2_scatter_reduce");
     return 0;
 }
 
 extern "C" int fhvae_mu2_accumulate(const float* z2mu, int64_t ld_z, const int64_t* idx, float* zsum,
-                                    float* cnt, int B, int Z, int64_t K, void* stream) {
+                                    float* cnt, int B, int Z, int64_t K, int32_t* err_flag, void* stream) {
     FHVAE_CHECK_ARG(z2mu && idx && zsum && cnt && B > 0 && Z > 0 && K > 0, "mu2_accumulate: bad argument");
     scatter_reduce_kernel<<<cdiv(B, 8), 256, 0, as_stream(stream)>>>(z2mu, ld_z, idx, zsum, cnt, nullptr,
-                                                                     B, Z);
+                                                                     B, Z, K, err_flag);
     FHVAE_LAUNCH_CHECK("mu2_accumulate");
     return 0;
 }

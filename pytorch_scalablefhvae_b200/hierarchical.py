@@ -70,11 +70,14 @@ class ShardedMu2Table:
         K, Z = model.mu2_table.shape
         zsum, cnt = torch.zeros(K, Z, device=self.device), torch.zeros(K, device=self.device)
         acc = _lib.fn("fhvae_mu2_accumulate")
+        err = torch.zeros(1, dtype=torch.int32, device=self.device)
         for x, lab in zip(x_batches, label_batches):
             enc = model.encode(x)
             lab = lab.to(self.device)
-            _lib.check(acc(ptr(enc["z2_mu"]), 2 * Z, ptr(lab), ptr(zsum), ptr(cnt), x.shape[0], Z, K,
+            _lib.check(acc(ptr(enc["z2_mu"]), 2 * Z, ptr(lab), ptr(zsum), ptr(cnt), x.shape[0], Z, K, ptr(err),
                            current_stream_ptr()), "fhvae_mu2_accumulate")
+        if int(err):                                   # round-level operation: one host read is fine here
+            raise IndexError("refresh: a label is outside [0, K) of the sampled cache")
         if self.world > 1:
             dist.all_reduce(zsum, group=self.group)
             dist.all_reduce(cnt, group=self.group)

@@ -63,7 +63,7 @@ def extract_posteriors(model, feats: torch.Tensor, lengths: Sequence[int], seg_s
         z1_mu[s0:s0 + nb].copy_(enc["z1_mu"])
         z2_mu[s0:s0 + nb].copy_(enc["z2_mu"])
         z2h = enc["z2_mu"]                                  # view of the (nb, 2*Z2) head: leading dim 2*Z2
-        _lib.check(accumulate(ptr(z2h), 2 * Z2, ptr(seg_utt, s0), ptr(zsum), ptr(cnt), nb, Z2, U,
+        _lib.check(accumulate(ptr(z2h), 2 * Z2, ptr(seg_utt, s0), ptr(zsum), ptr(cnt), nb, Z2, U, None,
                               current_stream_ptr()), "fhvae_mu2_accumulate")
     mu2 = torch.zeros(U, Z2, device=dev)
     _lib.check(_lib.fn("fhvae_mu2_estimate_finish")(ptr(zsum), ptr(cnt), ptr(mu2), R_MU2, U, Z2,

@@ -26,7 +26,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import ColsumProblem, SplitProblem, WgradProblem
-from .plan import CallList, current_stream_ptr, gemm_nn, gemm_nt, gemm_tn, ptr
+from .plan import CallList, _side_stream, current_stream_ptr, gemm_nn, gemm_nt, gemm_tn, ptr
 
 PZ2_LOGVAR = math.log(0.5 ** 2)      # simple_fhvae.py:88
 PMU2_LOGVAR = math.log(1.0 ** 2)     # simple_fhvae.py:23
@@ -207,11 +207,7 @@ class _FHVAECore(nn.Module):
         if int(num_seqs) != self.mu2_table.shape[0]:
             raise ValueError(f"num_seqs={num_seqs} but the mu2 table has {self.mu2_table.shape[0]} rows")
         B, T, F = x.shape
-        if not mu_idx.is_cuda:
-            # the reference keeps idxs on the CPU (train_model.py:445); torch.gather would raise on
-            # out-of-range rows (simple_fhvae.py:53) -- same error behaviour, checked on the host
-            if mu_idx.numel() != B or int(mu_idx.min()) < 0 or int(mu_idx.max()) >= int(num_seqs):
-                raise IndexError("mu_idx out of range for the mu2 table")
+        self._check_ids(mu_idx, num_segs, B, num_seqs)
         plan = self._plan(B, T, F)
         plan.load_inputs(x, mu_idx, num_segs, eps)
         grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in self._plist)
@@ -237,9 +233,34 @@ class _FHVAECore(nn.Module):
         if not x.is_cuda and not x.is_pinned():
             raise RuntimeError("train_step takes a CUDA or pinned-host batch (no CPU path)")
         B, T, F = x.shape
+        self._check_ids(mu_idx, num_segs, B, self.mu2_table.shape[0])
         plan = self._plan(B, T, F)
         plan.load_inputs(x, mu_idx, num_segs, eps)
         return plan.run_train_step(optimizer, float(alpha), allreduce)
+
+    @staticmethod
+    def _check_ids(mu_idx, num_segs, B, N):
+        """torch.gather's error behaviour (simple_fhvae.py:53).  Host-resident ids (the reference keeps them on the
+        CPU, train_model.py:445) are range-checked here; device-resident ids cannot be checked without a sync: the
+        kernels never touch memory outside the table for them, poison the segment's lower bound with NaN and set
+        FHVAE_FLAG_BAD_INDEX in ``model.nan_flag`` (``check_flags()`` reads it)."""
+        if mu_idx.numel() != B:
+            raise IndexError(f"mu_idx has {mu_idx.numel()} entries for a batch of {B} segments")
+        if torch.is_tensor(num_segs) and num_segs.numel() != B:
+            raise IndexError(f"num_segs has {num_segs.numel()} entries for a batch of {B} segments")
+        if not mu_idx.is_cuda and B and (int(mu_idx.min()) < 0 or int(mu_idx.max()) >= int(N)):
+            raise IndexError("mu_idx out of range for the mu2 table")
+
+    def check_flags(self):
+        """Host read (one sync) of the device status word: raises like the reference would have
+        (IndexError of torch.gather, simple_fhvae.py:53; NaN lower bound, train_model.py:464-466)."""
+        flag = int(self.nan_flag) if "nan_flag" in self.__dict__ else 0
+        for plan in self._plans.values():
+            flag |= int(plan.nan_flag)
+        if flag & _lib.FLAG_BAD_INDEX:
+            raise IndexError("mu_idx out of range for the mu2 table (device-side check)")
+        if flag & _lib.FLAG_NAN:
+            raise FloatingPointError("NaN in the lower bound (train_model.py:464)")
 
     @torch.no_grad()
     def encode(self, x: torch.Tensor, eps=None):
@@ -283,6 +304,7 @@ class _StepFn(torch.autograd.Function):
     def forward(ctx, model, plan, anchor, *params):
         plan.run_forward()
         ctx.model, ctx.plan, ctx.n_params = model, plan, len(params)
+        ctx.generation = plan.generation
         ctx.set_materialize_grads(False)      # unused outputs arrive as None instead of zero tensors
         # rows of the (6,B) buffer: lb, log_px, nk1, nk2, log_pmu2, log_qy -- returned as six outputs so that
         # autograd hands their gradients straight back (no per-row SelectBackward zeros + copy)
@@ -291,6 +313,16 @@ class _StepFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         model, plan = ctx.model, ctx.plan
+        if plan.generation != ctx.generation:
+            # the backward replays on the plan's static activation buffers: a later forward / encode / train_step of
+            # the same (B,T,F) has overwritten what this node saved (INTEGRATION.md "one step in flight")
+            raise RuntimeError(
+                "pytorch_scalablefhvae_b200: backward() of a forward whose activations were overwritten by a later "
+                "forward/encode/train_step of the same batch shape; call backward() before the next forward "
+                "(one step in flight per batch shape, INTEGRATION.md)")
+        if getattr(ctx, "consumed", False):
+            raise RuntimeError("pytorch_scalablefhvae_b200: double backward through one step is not supported")
+        ctx.consumed = True
         k = model._free_grad_slot()
         plan.run_backward(gouts, k)
         if ctx.n_params == 0:                 # direct delivery (see _FHVAECore.direct_grads)
@@ -356,11 +388,13 @@ class _Plan:
         self.gout = f(6, B)
         self._graph_fwd = None
         self._graph_bwd = [None, None]
+        self.generation = 0          # bumped by everything that overwrites the saved activations (see _StepFn.backward)
 
     # ---- inputs / outputs
     def set_x(self, x, mu_idx=None, num_segs=None):
         """x -> the plan's static (B,T,F) buffer and, where the plan keeps one, its time-major copy; optionally the
         two id vectors in the same launch.  Every entry (forward, train_step, encode) loads x through here."""
+        self.generation += 1
         x_tm = self.__dict__.get("x_tm")
         if (x.device == self.dev and x.dtype == torch.float32 and x.is_contiguous() and x.shape == self.x.shape
                 and self.F % 4 == 0 and x.data_ptr() % 16 == 0):
@@ -471,8 +505,12 @@ class _Plan:
 
         def fwd_bwd():
             fwd_list.run(current_stream_ptr())
-            loss_call.run(current_stream_ptr(), join=False)   # side stream 1; joined by the backward list
+            loss_call.run(current_stream_ptr(), join=False)   # side stream 1, beside the backward list ...
             bwd_list.run(current_stream_ptr())
+            main = torch.cuda.current_stream()                # ... and joined explicitly: not every plan's backward
+            ev = torch.cuda.Event()                           # list uses (hence joins) side stream 1
+            ev.record(_side_stream(None, 1))
+            main.wait_event(ev)
 
         def adam():
             optimizer.step_flat(m, gflat)
@@ -483,7 +521,9 @@ class _Plan:
                 allreduce(gflat)
             adam()
         else:
-            key = ("train", alpha, id(optimizer), allreduce is None)
+            # the captured Adam launch bakes its hyper-parameters in: a changed lr / betas / eps / grad_scale
+            # (LR scheduler, load_state_dict, a DataParallel wrapper created later) re-captures
+            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key())
             graphs = self.__dict__.setdefault("_train_graphs", {})
             if key not in graphs:
                 optimizer._state_for(m)               # allocate Adam state outside capture
@@ -553,7 +593,7 @@ class _Plan:
     def _disc_fwd(self):
         c, m, B = self.fwd, self.m, self.B
         tab = ptr(m.mu2_table)
-        c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N, side=2)
+        c.add("fhvae_mu2_gather", tab, ptr(self.idx), ptr(self.mu2), B, self.Z2, self.N, ptr(self.nan_flag), side=2)
         c.add("fhvae_disc_fwd_partial", ptr(self.z2head), 2 * self.Z2, tab, self.N, self.Z2,
               ptr(self.part), self.nsplit, B, side=2)
         c.add("fhvae_disc_target", ptr(self.z2head), 2 * self.Z2, ptr(self.mu2), ptr(self.tgt), B, self.Z2, side=2)
@@ -1081,6 +1121,12 @@ def _gauss_specs(prefix, in_dim, z):
             (f"{prefix}.mulayer.bias", (z,)), (f"{prefix}.logvar_layer.bias", (z,))]
 
 
+def _check_z2(z2_dim):
+    if z2_dim not in (8, 16, 32):
+        raise ValueError(f"z2_dim={z2_dim}: the discriminative kernels (csrc/disc.cu) are built for z2_dim in "
+                         "{8, 16, 32} (reference default 16, train_model.py:157-162; upstream 32)")
+
+
 def _check_adjacent(off, shape, a, b):
     assert off[b] == off[a] + _prod(shape[a]), f"{a} and {b} must be adjacent in the flat buffer"
 
@@ -1107,6 +1153,7 @@ class SimpleFHVAE(_FHVAECore):
         self.gemm_mode, self.use_cuda_graphs = gemm_mode, use_cuda_graphs
         assert len(self.z1_hus) == len(self.z2_hus) == len(self.x_hus) == 2, "two FC layers per block"
         assert self.z1_dim % 4 == 0 and self.z2_dim % 4 == 0
+        _check_z2(self.z2_dim)
         I, Z1, Z2 = self.input_size, self.z1_dim, self.z2_dim
         # default nn.Linear init drawn in the reference's construction order (simple_fhvae.py:31-36)
         init, specs = {}, []
@@ -1170,6 +1217,7 @@ class FHVAE(_FHVAECore):
             assert len(set(hus)) == 1 and hus[0] % 8 == 0, "one width per LSTM stack, multiple of 8"
         F, Z1, Z2 = self.feat_dim, self.z1_dim, self.z2_dim
         assert F % 4 == 0 and Z1 % 4 == 0 and Z2 % 4 == 0
+        _check_z2(Z2)
         nets = [("z1_pre_encoder", "z1", F + Z2, self.z1_hus), ("z2_pre_encoder", "z2", F, self.z2_hus),
                 ("pre_decoder", "dec", Z1 + Z2, self.x_hus)]
         init: Dict[str, torch.Tensor] = {}

@@ -15,6 +15,9 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, grad_scale=1.0):
         defaults = dict(lr=lr, betas=betas, eps=eps)
         super().__init__(params, defaults)
+        if len(self.param_groups) != 1:
+            raise ValueError("FusedAdam runs ONE flat kernel per model: a single param group (model.parameters(), "
+                             "train_model.py:409-411) is required")
         self.grad_scale = float(grad_scale)
         self._flat_state: Dict[int, dict] = {}
         self._modules = []
@@ -32,6 +35,17 @@ class FusedAdam(torch.optim.Optimizer):
             if len([p for g in self.param_groups for p in g["params"] if p._fhvae[0]() is mod]) != len(mod._plist):
                 raise ValueError("FusedAdam needs all parameters of a model (model.parameters())")
 
+    def _hyper(self):
+        g = self.param_groups[0]
+        if g.get("weight_decay", 0) or g.get("amsgrad", False) or g.get("maximize", False):
+            raise ValueError("FusedAdam implements plain Adam (train_model.py:409-411): weight_decay / amsgrad / "
+                             "maximize are not supported")
+        return float(g["lr"]), float(g["betas"][0]), float(g["betas"][1]), float(g["eps"])
+
+    def hyper_key(self):
+        """What a captured step bakes in (model.train_step re-captures its graph when this changes)."""
+        return self._hyper() + (float(self.grad_scale),)
+
     def _state_for(self, mod):
         flat = mod._ensure_flat()
         st = self._flat_state.get(id(mod))
@@ -48,19 +62,18 @@ class FusedAdam(torch.optim.Optimizer):
     @torch.no_grad()
     def step(self, closure=None):
         loss = closure() if closure is not None else None
-        g = self.param_groups[0]
-        lr, (b1, b2), eps = g["lr"], g["betas"], g["eps"]
+        lr, b1, b2, eps = self._hyper()
         for mod in self._modules:
             self.step_flat(mod, mod.packed_grads(), lr, b1, b2, eps)
         return loss
 
     def step_flat(self, mod, gflat, lr=None, b1=None, b2=None, eps=None):
         """Adam on the model's flat parameter buffer given a flat gradient buffer (graph-capturable)."""
-        g = self.param_groups[0]
-        lr = g["lr"] if lr is None else lr
-        b1 = g["betas"][0] if b1 is None else b1
-        b2 = g["betas"][1] if b2 is None else b2
-        eps = g["eps"] if eps is None else eps
+        h = self._hyper()
+        lr = h[0] if lr is None else lr
+        b1 = h[1] if b1 is None else b1
+        b2 = h[2] if b2 is None else b2
+        eps = h[3] if eps is None else eps
         st = self._state_for(mod)
         flat = mod._flat
         rc = _lib.fn("fhvae_adam_flat")(ptr(flat), ptr(gflat), ptr(st["m"]), ptr(st["v"]), flat.numel(),

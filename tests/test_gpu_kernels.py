@@ -606,7 +606,7 @@ def test_disc_fwd_bwd(B, N, Z):
     ns = _lib.fn("fhvae_disc_nsplit")(B, N)
     f = lambda *s: torch.zeros(*s, device=DEV)
     part, tgt, lqd, lse, mu2 = f(ns, B, 2), f(B), f(B), f(B), f(B, Z)
-    call("fhvae_mu2_gather", ptr(td), ptr(idd), ptr(mu2), B, Z, N)
+    call("fhvae_mu2_gather", ptr(td), ptr(idd), ptr(mu2), B, Z, N, None)
     assert torch.equal(mu2, td[idd])
     call("fhvae_disc_fwd_partial", ptr(zd), 2 * Z, ptr(td), N, Z, ptr(part), ns, B)
     call("fhvae_disc_target", ptr(zd), 2 * Z, ptr(mu2), ptr(tgt), B, Z)
@@ -655,8 +655,8 @@ def test_mu2_estimate_matches_reference_dict_loop():
     zsum, cnt = torch.zeros(K, Z, device=DEV), torch.zeros(K, device=DEV)
     table = torch.full((K, Z), 7.0, device=DEV)
     zd, idd = z2h.to(DEV), idx.to(DEV)
-    call("fhvae_mu2_accumulate", ptr(zd), 2 * Z, ptr(idd), ptr(zsum), ptr(cnt), 100, Z, K)
-    call("fhvae_mu2_accumulate", ptr(zd, 100 * 2 * Z), 2 * Z, ptr(idd, 100), ptr(zsum), ptr(cnt), B - 100, Z, K)
+    call("fhvae_mu2_accumulate", ptr(zd), 2 * Z, ptr(idd), ptr(zsum), ptr(cnt), 100, Z, K, None)
+    call("fhvae_mu2_accumulate", ptr(zd, 100 * 2 * Z), 2 * Z, ptr(idd, 100), ptr(zsum), ptr(cnt), B - 100, Z, K, None)
     call("fhvae_mu2_estimate_finish", ptr(zsum), ptr(cnt), ptr(table), 0.25, K, Z)
     for y, v in d.items():
         assert_close(table[y], v, 1e-5, f"mu2[{y}]")

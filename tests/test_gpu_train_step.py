@@ -1,0 +1,238 @@
+"""GPU: parity of the BENCHMARKED entry point -- ``model.train_step`` (one replayed launch sequence: forward, the
+fused ELBO forward+backward seam, BPTT, weight gradients, Adam; captured in one CUDA graph) -- against the CPU
+oracle's loop body of train_model.py:446-454.  bench.py times exactly this call at config 1 in bf16x3 mode."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import pytorch_scalablefhvae_b200 as P
+from oracle import fhvae_oracle as O
+from test_gpu_model import CFGS, DEV, _eps, _pair
+from util import FP32_RTOL, assert_close, relerr, synth_batch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _check_params(m, o, steps, lr=1e-3, what=""):
+    """Adam's m/sqrt(v) is sign-like where |g| ~ fp32 noise: bounded worst case + >= 99.9 % of elements within 1e-4
+    (same criterion as test_train_steps_match_oracle_adam; the kernel itself is pinned to 1e-6 elsewhere)."""
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        ref = po[k].detach()
+        diff = (p.detach().cpu() - ref).abs()
+        assert float(diff.max()) <= 2 * steps * lr, f"{what}{k}: {float(diff.max()):.3e}"
+        frac_ok = float((diff <= FP32_RTOL * float(ref.abs().max())).float().mean())
+        assert frac_ok >= 0.999, f"{what}param {k} after {steps} Adam steps: only {frac_ok:.5f} of elements within 1e-4"
+
+
+@pytest.mark.parametrize("name,mode,graphs", [
+    ("fhvae_c1", P.MODE_BF16X3, True),          # <- the bench.py configuration
+    ("fhvae_c1", P.MODE_BF16X3, False),
+    ("fhvae_c1", P.MODE_F32_SIMT, True),
+    ("fhvae_small", P.MODE_F32_SIMT, True),
+    ("fhvae_1layer_3layer", P.MODE_BF16X3, True),
+    ("simple_c0", P.MODE_BF16X3, True),
+    ("simple_c0", P.MODE_F32_SIMT, True),
+    ("simple_c0", P.MODE_F32_SIMT, False),
+    ("simple_ragged", P.MODE_F32_SIMT, True),
+])
+def test_train_step_matches_oracle(name, mode, graphs):
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg, gemm_mode=mode, use_cuda_graphs=graphs)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    oopt = O.make_adam(o.parameters())
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    steps = 3
+    for step in range(steps):
+        x, idx, nsegs = synth_batch(B, T, F, N, seed=100 + step)
+        eps = _eps(B, m.z1_dim, m.z2_dim, seed=step)
+        # device-resident ids: the fast path bench.py uses (one load_inputs launch)
+        loss = m.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), opt, 10.0, eps=eps)
+        rl, rout = O.train_step(o, oopt, x, idx, N, nsegs, 10.0, eps=eps)
+        assert_close(loss, rl, FP32_RTOL, f"{name}: loss step {step}")
+        # the five per-segment ELBO vectors + log q(i|z2) of the fused seam (rows of the (6,B) out buffer)
+        plan = m._plan(B, T, F)
+        lb, log_qy, log_px, nk1, nk2, log_pmu2 = rout
+        for row, ref, nm in ((0, lb, "lower_bound"), (1, log_px, "log_px_z"), (2, nk1, "neg_kld_z1"),
+                             (3, nk2, "neg_kld_z2"), (4, log_pmu2, "log_pmu2"), (5, log_qy, "log_qy")):
+            assert_close(plan.out[row], ref, FP32_RTOL, f"{name}: {nm} step {step}")
+    assert opt.steps_taken() == steps
+    m.check_flags()
+    _check_params(m, o, steps, what=f"{name}: ")
+
+
+def test_train_step_gradients_match_oracle_c1():
+    """One fused step at config 1 in the benchmarked mode: the flat gradient buffer the Adam launch consumed equals
+    the oracle's gradients (1e-4 max-norm relative), incl. the mu2 table."""
+    cfg = CFGS["fhvae_c1"]
+    m, o = _pair("fhvae", cfg, gemm_mode=P.MODE_BF16X3, use_cuda_graphs=True)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    eps = _eps(B, 32, 32)
+    m.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), opt, 10.0, eps=eps)
+    ref = o(x, idx, N, nsegs, eps=eps)
+    O.loss_function(ref[0], ref[1], 10.0).backward()
+    gflat = m._grad_buffer(0)
+    worst = 0.0
+    for k, q in o.named_parameters():
+        g = gflat[m._off[k]:m._off[k] + q.numel()].view(q.shape)
+        e = relerr(g, q.grad)
+        worst = max(worst, e)
+        assert e <= FP32_RTOL, f"grad {k}: {e:.3e}"
+    print(f"train_step c1 bf16x3: worst gradient max-norm relative error {worst:.2e}")
+
+
+def _run_seam(fused: str):
+    """Fresh process (the env switch is read when the call lists are built): ELBO outputs + seam gradients of one step."""
+    code = f"""
+import os, sys, torch
+os.environ["FHVAE_FUSED_ELBO"] = "{fused}"
+sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {os.path.join(ROOT, 'tests')!r})
+import pytorch_scalablefhvae_b200 as P
+from util import synth_batch
+torch.manual_seed(0)
+m = P.FHVAE(1600, [256, 256], [256, 256], 32, 32, [256, 256], seg_len=20, num_seqs=1000, gemm_mode=P.MODE_BF16X3,
+            use_cuda_graphs=True).to("cuda")
+opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+x, idx, nsegs = synth_batch(256, 20, 80, 1000)
+g = torch.Generator().manual_seed(2)
+eps = {{"z2": torch.randn(256, 32, generator=g), "z1": torch.randn(256, 32, generator=g)}}
+loss = m.train_step(x.cuda(), idx.cuda(), nsegs.cuda(), opt, 10.0, eps=eps)
+plan = m._plan(256, 20, 80)
+names = [c[1] for c in plan._train_lists(0)[0].calls]
+torch.save({{"loss": loss.cpu(), "out": plan.out.cpu(), "dxhead": plan.dxhead.cpu(), "dz1head": plan.dz1head.cpu(),
+            "dmu2": plan.dmu2.cpu(), "fused": "fhvae_elbo_fwd_bwd" in names}}, sys.argv[1])
+"""
+    path = f"/tmp/fhvae_seam_{fused}.pt"
+    r = subprocess.run([sys.executable, "-c", code, path], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return torch.load(path)
+
+
+def test_fused_elbo_seam_is_bit_identical():
+    """FHVAE_FUSED_ELBO=0 (elbo_fwd -> step_coef -> elbo_bwd) vs 1 (one fhvae_elbo_fwd_bwd launch) inside the
+    graph-captured train step at config 1: loss, the (6,B) output rows and the seam's gradients are bit-equal."""
+    a, b = _run_seam("0"), _run_seam("1")
+    assert not a["fused"] and b["fused"]
+    for k in ("loss", "out", "dxhead", "dz1head", "dmu2"):
+        assert torch.equal(a[k], b[k]), k
+
+
+def test_simple_c0_kat_on_gpu(golden_dir):
+    """SURVEY.md §4 known-answer scalars of the UNMODIFIED reference at config 0 (tests/golden/
+    simple_fhvae_c0_kat.json, generated by oracle/make_golden.py), reproduced by the CUDA path."""
+    kat = json.load(open(os.path.join(golden_dir, "simple_fhvae_c0_kat.json")))
+    if kat["torch"] != torch.__version__:
+        pytest.skip("RNG streams / default init pinned to torch " + kat["torch"])
+    torch.manual_seed(0)
+    o = O.SimpleFHVAEOracle(1600, num_seqs=1000)          # the reference's construction order -> same default init
+    m = P.SimpleFHVAE(1600, num_seqs=1000, detach_px=True, prior_grad=False, ref_log_qy=True)
+    gen = torch.Generator().manual_seed(1)
+    x = torch.randn(64, 20, 80, generator=gen)
+    idx = torch.randint(0, 1000, (64,), generator=gen)
+    nsegs = torch.randint(1, 200, (64,), generator=gen)
+    assert idx[:8].tolist() == kat["idx_head"]
+    torch.manual_seed(2)                                   # simple_fhvae.py:51 then :215 x3 (z2, z1, x)
+    table = torch.empty(1000, 16).normal_(mean=0, std=1.0)
+    eps = {"z2": torch.randn(64, 16), "z1": torch.randn(64, 16)}
+    sd = o.state_dict()
+    sd["mu2_table"] = table
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV)
+    out = m(x.to(DEV), idx, 1000, nsegs, eps=eps)
+    loss = P.loss_function(out[0], out[1], 10.0)
+    loss.backward()
+    got = {"mean_lower_bound": out[0].mean(), "log_qy": out[1], "mean_log_px_z": out[2].mean(),
+           "mean_neg_kld_z1": out[3].mean(), "mean_neg_kld_z2": out[4].mean(),
+           "mean_log_pmu2": out[5].mean(), "loss_alpha10": loss,
+           "gnorm_z2_pre_encoder_fc1_w": m.z2_pre_encoder.fc1.linear.weight.grad.norm(),
+           "gnorm_z1_gauss_mulayer_w": m.z1_gauss_layer.mulayer.weight.grad.norm()}
+    for k, v in got.items():
+        assert float(v) == pytest.approx(kat[k], rel=FP32_RTOL), k
+
+
+def test_fhvae_o3_golden_on_gpu(golden_dir):
+    """The committed O3 golden (tests/golden/fhvae_o3_small.npz, oracle/make_golden.py): the GPU box provably
+    checks against the same oracle values the authoring box produced."""
+    d = np.load(os.path.join(golden_dir, "fhvae_o3_small.npz"))
+    g = {k: torch.from_numpy(d[k]) for k in d.files if k != "meta"}
+    T, F, B, N, Z1, Z2, H = [int(v) for v in d["meta"]]
+    m = P.FHVAE(T * F, [H, H], [H, H], Z1, Z2, [H, H], seg_len=T, num_seqs=N)
+    m.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("w:")}, strict=True)
+    m.to(DEV)
+    out = m(g["x"].to(DEV), g["idx"], N, g["nsegs"], eps={"z1": g["eps_z1"], "z2": g["eps_z2"]})
+    for n, a in zip(["lower_bound", "log_qy", "log_px_z", "neg_kld_z1", "neg_kld_z2", "log_pmu2"], out):
+        assert_close(a, g["out_" + n], FP32_RTOL, n)
+    loss = P.loss_function(out[0], out[1], 10.0)
+    assert_close(loss, g["loss"], FP32_RTOL, "loss")
+    loss.backward()
+    for k, p in m.named_parameters():
+        assert_close(p.grad, g["g:" + k], FP32_RTOL, "grad " + k)
+
+
+def test_device_index_out_of_range_is_flagged_not_oob():
+    """A device-resident mu_idx outside [0,N) (torch.gather raises, simple_fhvae.py:53): no out-of-bounds access,
+    the segment's lower bound is NaN (the reference's own guard, train_model.py:464) and check_flags() raises."""
+    cfg = CFGS["fhvae_small"]
+    m, _ = _pair("fhvae", cfg)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    before = m.mu2_table.detach().clone()
+    bad = idx.clone(); bad[3] = N + 5; bad[4] = -1
+    with pytest.raises(IndexError):
+        m.train_step(x.to(DEV), bad, nsegs, opt)                       # host-resident ids: checked on the host
+    with pytest.raises(IndexError):
+        m.train_step(x.to(DEV), idx[:-1].to(DEV), nsegs.to(DEV), opt)  # wrong length
+    with torch.no_grad():
+        out = m(x.to(DEV), bad.to(DEV), N, nsegs.to(DEV), eps=_eps(B, m.z1_dim, m.z2_dim))
+    assert torch.isnan(out[0][3]) and torch.isnan(out[0][4]) and not torch.isnan(out[0][0])
+    with pytest.raises(IndexError):
+        m.check_flags()
+    assert torch.equal(m.mu2_table.detach(), before)
+
+
+def test_backward_after_overwritten_forward_raises():
+    """the backward replays on the plan's static activations; a second forward of the same shape before
+    backward() must raise instead of silently producing gradients of the wrong batch."""
+    cfg = CFGS["fhvae_small"]
+    m, _ = _pair("fhvae", cfg)
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    out1 = m(x.to(DEV), idx, N, nsegs)
+    with torch.no_grad():
+        m(x.to(DEV) * 2, idx, N, nsegs)
+    with pytest.raises(RuntimeError, match="overwritten"):
+        P.loss_function(out1[0], out1[1]).backward()
+    out2 = m(x.to(DEV), idx, N, nsegs)
+    m.encode(x.to(DEV))
+    with pytest.raises(RuntimeError, match="overwritten"):
+        P.loss_function(out2[0], out2[1]).backward()
+    out3 = m(x.to(DEV), idx, N, nsegs)           # the normal pattern still works
+    P.loss_function(out3[0], out3[1]).backward()
+
+
+def test_lr_change_recaptures_train_graph():
+    """the captured Adam launch bakes lr in; changing param_groups[0]['lr'] must take effect."""
+    cfg = CFGS["fhvae_small"]
+    m, o = _pair("fhvae", cfg, use_cuda_graphs=True)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    oopt = O.make_adam(o.parameters())
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    for step, lr in enumerate([1e-3, 1e-3, 5e-4, 5e-4]):
+        opt.param_groups[0]["lr"] = lr
+        oopt.param_groups[0]["lr"] = lr
+        x, idx, nsegs = synth_batch(B, T, F, N, seed=7 + step)
+        eps = _eps(B, m.z1_dim, m.z2_dim, seed=step)
+        m.train_step(x.to(DEV), idx, nsegs, opt, 10.0, eps=eps)
+        O.train_step(o, oopt, x, idx, N, nsegs, 10.0, eps=eps)
+    _check_params(m, o, 4)
+    with pytest.raises(ValueError):
+        P.FusedAdam([{"params": list(m.parameters())[:3]}, {"params": list(m.parameters())[3:]}])

@@ -131,3 +131,82 @@ def test_fhvae_oracle_runs_and_shapes():
 def test_segment_arithmetic():
     assert O.segment_starts(200).tolist() == list(range(0, 184, 8))   # (200-20)//8+1 = 23 segments
     assert len(O.segment_starts(20)) == 1 and len(O.segment_starts(19)) == 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# O3 (FHVAE, LSTM): the reference's fhvae.py:4-14 is a stub, so O3 is "parity unpinned" by the reference.  It is
+# pinned twice by us instead: (1) against a hand-written fp64 numpy LSTM cell + closed-form loss / BPTT (SURVEY.md
+# Appendix C) that shares no code with torch.nn.LSTM or autograd, (2) against a committed golden of itself.
+# ---------------------------------------------------------------------------------------------------------------
+def _o3_small(seed=21):
+    T, F, B, N, Z1, Z2, H = 6, 8, 10, 13, 8, 16, 32
+    torch.manual_seed(seed)
+    m = O.FHVAEOracle(T * F, [H, H], [H, H], Z1, Z2, [H, H], seg_len=T, num_seqs=N).double()
+    g = torch.Generator().manual_seed(seed + 1)
+    x = torch.randn(B, T, F, generator=g)
+    idx = torch.randint(0, N, (B,), generator=g)
+    nsegs = torch.randint(1, 120, (B,), generator=g)
+    eps = {"z2": torch.randn(B, Z2, generator=g), "z1": torch.randn(B, Z1, generator=g)}
+    return m, x, idx, nsegs, eps, N
+
+
+def test_o3_forward_matches_handwritten_fp64_cell():
+    m, x, idx, nsegs, eps, N = _o3_small()
+    out = m(x.double(), idx, N, nsegs, eps=eps)
+    loss = O.loss_function(out[0], out[1], 10.0)
+    ref = O.fhvae_forward_fp64(m, x, idx, nsegs, eps)
+    names = ["lower_bound", "log_qy", "log_px_z", "neg_kld_z1", "neg_kld_z2", "log_pmu2"]
+    for n, o in zip(names, out):
+        np.testing.assert_allclose(o.detach().numpy(), ref[n], rtol=1e-10, atol=1e-10, err_msg=n)
+    assert float(loss) == pytest.approx(float(ref["loss"]), rel=1e-12)
+
+
+@pytest.mark.parametrize("layers", [1, 2, 3])
+def test_nn_lstm_matches_handwritten_cell_and_bptt(layers):
+    """nn.LSTM forward + autograd == hand-written cell + closed-form BPTT (outputs, final h of every layer, dx, every
+    weight / bias gradient), fp64, 1e-10."""
+    B, T, In, H = 5, 7, 6, 12
+    torch.manual_seed(3)
+    lstm = torch.nn.LSTM(In, H, num_layers=layers, batch_first=True).double()
+    x = torch.randn(B, T, In, dtype=torch.float64, requires_grad=True)
+    out, (hn, _) = lstm(x)
+    g = torch.Generator().manual_seed(4)
+    d_out = torch.randn(B, T, H, generator=g, dtype=torch.float64)
+    d_fin = torch.randn(layers, B, H, generator=g, dtype=torch.float64)
+    ((out * d_out).sum() + (hn * d_fin).sum()).backward()
+    w = [tuple(getattr(lstm, f"{n}_l{l}").detach().numpy() for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh"))
+         for l in range(layers)]
+    o2, fin, cache = O.lstm_stack_fp64(x.detach().numpy(), w)
+    np.testing.assert_allclose(out.detach().numpy(), o2, rtol=1e-10, atol=1e-12)
+    for l in range(layers):
+        np.testing.assert_allclose(hn[l].detach().numpy(), fin[l], rtol=1e-10, atol=1e-12)
+    dx, grads = O.lstm_stack_bwd_fp64(d_out.numpy(), [d_fin[l].numpy() for l in range(layers)], w, cache)
+    np.testing.assert_allclose(x.grad.numpy(), dx, rtol=1e-9, atol=1e-12)
+    for l in range(layers):
+        for n, gr in zip(("weight_ih", "weight_hh", "bias_ih", "bias_hh"), grads[l]):
+            np.testing.assert_allclose(getattr(lstm, f"{n}_l{l}").grad.numpy(), gr, rtol=1e-9, atol=1e-12,
+                                       err_msg=f"{n}_l{l}")
+
+
+def test_o3_reproduces_its_golden(golden_dir):
+    """tests/golden/fhvae_o3_small.npz (oracle/make_golden.py): the oracle on THIS box gives the committed values."""
+    d = np.load(os.path.join(golden_dir, "fhvae_o3_small.npz"))
+    g = {k: torch.from_numpy(d[k]) for k in d.files if k != "meta"}
+    T, F, B, N, Z1, Z2, H = [int(v) for v in d["meta"]]
+    m = O.FHVAEOracle(T * F, [H, H], [H, H], Z1, Z2, [H, H], seg_len=T, num_seqs=N)
+    m.load_state_dict({k[2:]: v for k, v in g.items() if k.startswith("w:")}, strict=True)
+    eps = {"z1": g["eps_z1"], "z2": g["eps_z2"]}
+    out = m(g["x"], g["idx"], N, g["nsegs"], eps=eps)
+    names = ["lower_bound", "log_qy", "log_px_z", "neg_kld_z1", "neg_kld_z2", "log_pmu2"]
+    for n, o in zip(names, out):
+        torch.testing.assert_close(o.detach(), g["out_" + n], rtol=2e-5, atol=1e-5, msg=n)
+    loss = O.loss_function(out[0], out[1], 10.0)
+    loss.backward()
+    torch.testing.assert_close(loss.detach(), g["loss"], rtol=2e-5, atol=1e-5)
+    for k, p in m.named_parameters():
+        e = float((p.grad - g["g:" + k]).abs().max()) / (float(g["g:" + k].abs().max()) + 1e-30)
+        assert e < 2e-5, (k, e)
+    # and the golden itself agrees with the hand-written fp64 cell (fp32 oracle vs fp64 numpy: 1e-5)
+    ref = O.fhvae_forward_fp64(m, g["x"], g["idx"], g["nsegs"], eps)
+    for n in names:
+        np.testing.assert_allclose(g["out_" + n].numpy(), ref[n], rtol=2e-5, atol=2e-5, err_msg=n)
