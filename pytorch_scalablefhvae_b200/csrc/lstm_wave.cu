@@ -44,6 +44,29 @@ constexpr int WHDR = 512;          // header of the exchange buffer in uint4 (8 
 constexpr int WMAXG = 32;          // counters for up to 32 groups per layer
 constexpr int WMAXT = 63;          // flag = epoch * 64 + t + 1
 
+// ---- experiment switches (tools/build_variant.sh + tools/wave_bench.py); the defaults are the measured best
+#ifndef WAVE_POLL_SEQ_FWD
+#define WAVE_POLL_SEQ_FWD 1  // forward h gather: wait word by word (measured: 116 us/launch vs 173 us with the parallel wait,
+#endif                       // whose retry loads need 28 more registers -> spills in the 112-register compute warps)
+#ifndef WAVE_POLL_SEQ_BWD
+#define WAVE_POLL_SEQ_BWD 0  // BPTT reduce-scatter: all outstanding words per retry round (measured: 111 vs 134 us/launch)
+#endif
+#ifndef WAVE_P_FIRST
+#define WAVE_P_FIRST 0       // 1: request this step's input projection before the exchange instead of after it
+#endif
+#ifndef WAVE_SENTINEL
+#define WAVE_SENTINEL 0      // 1: spin on ONE word of the last peer slice before the bulk loads of the exchange
+#endif
+#ifndef WAVE_FLAGPOLL
+#define WAVE_FLAGPOLL 0      // 1: ONE warp polls one sentinel word per producer; the other warps sleep at a named barrier
+#endif                       //    and read the LL words once they are (almost surely) there -- no poll spam in L2
+#ifndef WAVE_TMA
+#define WAVE_TMA 0           // 1: forward h exchange = plain payload + release/acquire flag + cp.async.bulk straight into the
+#endif                       //    MMA operand buffer (half the bytes of LL words, no register staging, no compute-warp work)
+#ifndef WAVE_SAVE_FIRST
+#define WAVE_SAVE_FIRST 0    // 1: the HBM stores of the previous step are issued before the exchange loads
+#endif
+
 __device__ __forceinline__ uint4 ld_ll(const uint4* p) {
     uint4 v;
     asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
@@ -61,13 +84,42 @@ __device__ __forceinline__ uint32_t wait_ll(uint4& v, const uint4* p, uint32_t f
     return spins;
 }
 
+// ---- flag + bulk-copy exchange (WAVE_TMA) ------------------------------------------------------------------
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void wait_flag(const uint32_t* p, uint32_t flag) {
+    uint32_t spins = 0;
+    while (ld_acquire_gpu(p) != flag)
+        if (++spins > FHVAE_SPIN_LIMIT) __trap();
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy (TMA engine, async proxy); completion is counted in bytes on `bar`
+__device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
 // Wait for N LL words at once: every retry round re-issues ALL still-invalid loads back to back, so a round costs
 // one L2 round trip (~260 cycles) however many words are outstanding.  (Waiting word by word -- wait_ll in a loop --
 // serialises the round trips: 7 peer slices that all miss their first poll cost 7 dependent trips, which was
 // 2900-3700 of the 10600 cycles of a forward wavefront step in round 1.)
-template <int N, typename AddrFn>
+template <int N, bool SEQ, typename AddrFn>
 __device__ __forceinline__ uint32_t wait_ll_all(uint4 (&v)[N], AddrFn addr, uint32_t flag) {
     uint32_t spins = 0;
+    if (SEQ) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) spins += wait_ll(v[i], addr(i), flag);
+        return spins;
+    }
     for (;;) {
         uint32_t bad = 0;
 #pragma unroll
@@ -83,9 +135,11 @@ __device__ __forceinline__ uint32_t wait_ll_all(uint4 (&v)[N], AddrFn addr, uint
 #ifdef FHVAE_TIMELINE
 __device__ long long g_wave_tl[2][32][16];
 #define WTL(step, slot) do { if (rank == 0 && grp == 0 && threadIdx.x == 0 && (step) < 32) g_wave_tl[layer][step][slot] = clock64(); } while (0)
+#define WTL1(step, slot) do { if (rank == 0 && grp == 0 && (step) < 32) g_wave_tl[layer][step][slot] = clock64(); } while (0)   // caller = one thread
 extern "C" int fhvae_debug_wave_timeline(long long* out) { return (int)cudaMemcpyFromSymbol(out, g_wave_tl, sizeof(g_wave_tl)); }
 #else
 #define WTL(step, slot) do { } while (0)
+#define WTL1(step, slot) do { } while (0)
 #endif
 
 struct WaveFwdArgs {
@@ -113,9 +167,17 @@ struct WaveFwdSmem {
 
 // pull NS slices (all 8, or the 7 peers) of one published step into an MMA operand buffer
 template <bool X3, int NS, bool SKIP_OWN>
-__device__ __forceinline__ void wave_load(const uint4* slot, int rank, uint4 (&v)[NS]) {
+__device__ __forceinline__ void wave_load(const uint4* slot, int rank, uint4 (&v)[NS], uint32_t flag) {
     constexpr int NW = (X3 ? 2 : 1) * 256;
     if ((int)threadIdx.x < NW) {
+#if WAVE_SENTINEL
+        {   // one word of the LAST slice first: when it has landed the others almost surely have too, so the bulk
+            // pass below is not a wasted 57-KB read of words that are still in flight
+            const int src = SKIP_OWN ? (NS - 1) + ((NS - 1) >= rank ? 1 : 0) : NS - 1;
+            uint4 s = ld_ll(slot + src * WSLICE + threadIdx.x);
+            wait_ll(s, slot + src * WSLICE + threadIdx.x, flag);
+        }
+#endif
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int src = SKIP_OWN ? i + (i >= rank ? 1 : 0) : i;
@@ -131,7 +193,7 @@ __device__ __forceinline__ void wave_store(const uint4* slot, int rank, uint32_t
     if (tid < NW) {
         const int part = tid >> 8, rem = tid & 255, chunk = rem >> 1, half = rem & 1;
         const int kcl = chunk / WNB, row = chunk % WNB;
-        wait_ll_all<NS>(v, [&](int i) { return slot + (SKIP_OWN ? i + (i >= rank ? 1 : 0) : i) * WSLICE + tid; }, flag);
+        wait_ll_all<NS, WAVE_POLL_SEQ_FWD != 0>(v, [&](int i) { return slot + (SKIP_OWN ? i + (i >= rank ? 1 : 0) : i) * WSLICE + tid; }, flag);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int src = SKIP_OWN ? i + (i >= rank ? 1 : 0) : i;
@@ -167,6 +229,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     uint64_t* p1_done = rec_done + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p1_done + 1);
     uint32_t* epoch_slot = tmem_slot + 1;
+    volatile uint32_t* p1_safe = epoch_slot + 1;    // WAVE_TMA: last step whose projection MMAs are known complete
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = (warp >> 2) & 3;   // gate (= TMEM lane quarter), column group
@@ -196,10 +259,12 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     constexpr int TCOLS = (ACOL + 2 * NACC * NB) <= 256 ? 256 : 512;
     if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) {
-        mbar_init(&hb_full[0], NT / 32); mbar_init(&hb_full[1], NT / 32);
+        // WAVE_TMA: + one arrive.expect_tx per peer slice (issued by the pull lanes of warp 17)
+        mbar_init(&hb_full[0], NT / 32 + (WAVE_TMA ? WG - 1 : 0)); mbar_init(&hb_full[1], NT / 32 + (WAVE_TMA ? WG - 1 : 0));
         mbar_init(rec_done, 1); mbar_init(p1_done, 1);
         fence_mbar_init();
         *epoch_slot = *cnt;
+        *p1_safe = 0;
     }
     tc_fence_before();
     __syncthreads();
@@ -224,6 +289,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 const uint64_t dhh0 = make_smem_desc(hbt, H_LBO, SBO_);
                 const uint64_t dhl0 = make_smem_desc(hbt + S::H_PART, H_LBO, SBO_);
                 mbar_wait(&hb_full[t & 1], ((t - 1) >> 1) & 1);        // h_{t-1} gathered in buffer t&1
+                WTL1(t, 13);
                 tc_fence_after();
                 if (t < T) {
                     // rolled over the 8 slices (this warp runs on 32 registers)
@@ -247,6 +313,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                     }
                 }
                 if (t < T) umma_commit(rec_done);
+                WTL1(t, 14);
                 if (p1_duty) {
                     uint64_t dh = dhh0, dl = dhl0;
                     uint64_t dwh = make_smem_desc(wih_u, W_LBO, SBO_), dwl = make_smem_desc(wih_u + S::W_PART, W_LBO, SBO_);
@@ -268,6 +335,34 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
             }
         }
+#if WAVE_TMA
+        else if (warp == NT / 32 + 1 && lane < WG - 1) {
+            // ---- pull lanes: lane i owns peer slice src(i).  Poll the slice's flag (acquire), then bulk-copy the
+            // payload (already in the UMMA operand layout) straight into the operand buffer of step t; the issuer's
+            // hb_full barrier counts the bytes.  No compute warp touches the exchange.
+            const int src = lane + (lane >= rank ? 1 : 0);
+            constexpr uint32_t PART_BYTES = 4 * H_LBO;                       // 4 K-chunks x 32 rows x 16 B = 2 KB
+            for (int t = 1; t < nsteps; ++t) {
+                const uint4* sl = own + (size_t)(t - 1) * (WG * WSLICE) + src * WSLICE;
+                // buffer t&1 was last read by the projection MMAs of step t-2 (p1_duty only; the recurrent MMAs of
+                // step t-2 are complete by causality: no peer can publish h_{t-1} before it received our h_{t-2})
+                if (p1_duty && t >= 3) {
+                    uint32_t spins = 0;
+                    while (*p1_safe < (uint32_t)(t - 2))
+                        if (++spins > FHVAE_SPIN_LIMIT) __trap();
+                }
+                wait_flag(reinterpret_cast<const uint32_t*>(sl + 256), fbase + t);
+                if (lane == WG - 2) WTL1(t, 11);
+                fence_proxy_async_all();
+                uint64_t* bar = &hb_full[t & 1];
+                mbar_arrive_expect_tx(bar, (X3 ? 2u : 1u) * PART_BYTES);
+                const uint32_t dst = hb_u + (t & 1) * S::H_BUF + (uint32_t)src * PART_BYTES;
+                bulk_g2s(dst, sl, PART_BYTES, bar);
+                if (X3) bulk_g2s(dst + S::H_PART, reinterpret_cast<const uint8_t*>(sl) + PART_BYTES, PART_BYTES, bar);
+                if (lane == WG - 2) WTL1(t, 12);
+            }
+        }
+#endif
         __syncwarp();
     } else {
         // ================= compute warps =================
@@ -357,25 +452,45 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             const bool real = t < T;
             WTL(t, 0);
             uint8_t* hbt = smem + S::H_OFF + (t & 1) * S::H_BUF;
-            // this step's input projection is requested FIRST (layer 0: the GEMM-produced P0 from HBM, layer 1: layer 0's
-            // LL words): its latency then hides behind the exchange below instead of following it
             float pv[CPW];
             uint4 pl[CPW / 2];
-            if (real) {
-                if (layer == 0) {
-                    const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
+            auto request_p = [&]() {
+                if (real) {
+                    if (layer == 0) {
+                        const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
 #pragma unroll
-                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
-                } else {
+                        for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+                    } else {
 #pragma unroll
-                    for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
+                        for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
+                    }
                 }
-            }
+            };
+#if WAVE_P_FIRST
+            request_p();
+#endif
+#if WAVE_TMA
+            if (t > 0) store_saved(t - 1);   // (the pull lanes of warp 17 gather h_{t-1}; nothing to do here)
+#else
             if (t > 0) {
                 // h_{t-1}: the 7 peer slices (own slice was written locally by the cell phase)
                 const uint4* slot = own + (size_t)(t - 1) * (WG * WSLICE);
                 uint4 hv[7];
-                wave_load<X3, 7, true>(slot, rank, hv);
+#if WAVE_SAVE_FIRST
+                store_saved(t - 1);
+#endif
+#if WAVE_FLAGPOLL
+                if (warp == 0) {
+                    if (lane < WG - 1) {
+                        const uint4* sp = slot + (lane + (lane >= rank ? 1 : 0)) * WSLICE + (NW - 1);
+                        uint4 sv = ld_ll(sp);
+                        wait_ll(sv, sp, fbase + t);
+                    }
+                    __syncwarp();
+                }
+                bar_compute();
+#endif
+                wave_load<X3, 7, true>(slot, rank, hv, fbase + t);
                 WTL(t, 6);
                 wave_store<X3, 7, true>(slot, rank, fbase + t, hv, hbt);
                 WTL(t, 7);
@@ -383,8 +498,14 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&hb_full[t & 1]);
+#if !WAVE_SAVE_FIRST
                 store_saved(t - 1);          // HBM stores of the previous step ride in the shadow of this step's MMAs
+#endif
             }
+#endif
+#if !WAVE_P_FIRST
+            request_p();                     // this step's input projection: layer 0 from the GEMM-produced P0, layer 1 from layer 0's LL words
+#endif
             WTL(t, 1);
             if (real) {
                 float acc[CPW];
@@ -406,7 +527,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
                 WTL(t, 3);
                 if (layer == 1) {
-                    wait_ll_all<CPW / 2>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
+                    wait_ll_all<CPW / 2, WAVE_POLL_SEQ_FWD != 0>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
 #pragma unroll
                     for (int j = 0; j < CPW / 2; ++j) {
                         pv[2 * j] = __uint_as_float(pl[j].x);
@@ -437,6 +558,30 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                     if (X3)
                         *reinterpret_cast<__nv_bfloat16*>(hbn + S::H_PART + hoff_k + b * 16) = __float2bfloat16_rn(h - __bfloat162float(hh));
                 }
+#if WAVE_TMA
+                // own slice of h_t is in operand buffer (t+1)&1: visible to the async proxy, then counted on its barrier
+                fence_proxy_async();
+                bar_compute();
+                WTL(t, 5);
+                if (t + 1 < nsteps) {
+                    if (lane == 0) mbar_arrive(&hb_full[(t + 1) & 1]);
+                    // publish: payload = the slice exactly as it sits in the operand buffer (2 KB per bf16 part), plain
+                    // coalesced 8-byte stores; then ONE release store of the flag (cumulative over the CTA barrier)
+                    if (tid < NW) {
+                        const int part = tid >> 8, rem = tid & 255;
+                        const uint2 d = *reinterpret_cast<const uint2*>(hbn + part * S::H_PART + (uint32_t)(rank * 4) * H_LBO + rem * 8);
+                        uint2* dst = reinterpret_cast<uint2*>(own + (size_t)t * (WG * WSLICE) + rank * WSLICE) + tid;
+                        asm volatile("st.global.v2.u32 [%0], {%1, %2};" ::"l"(dst), "r"(d.x), "r"(d.y) : "memory");
+                    }
+                    WTL(t, 8);
+                    bar_compute();
+                    WTL(t, 9);
+                    if (tid == 0)
+                        st_release_gpu(reinterpret_cast<uint32_t*>(own + (size_t)t * (WG * WSLICE) + rank * WSLICE + 256), fbase + t + 1);
+                    WTL(t, 10);
+                }
+            }
+#else
                 bar_compute();
                 WTL(t, 5);
                 // publish this CTA's slice of h_t: peers need it for step t+1 (and the P1 duty for its extra step)
@@ -447,10 +592,14 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                     st_ll(own + (size_t)t * (WG * WSLICE) + rank * WSLICE + tid, d.x, d.y, fbase + t + 1);
                 }
             }
+#endif
             if (p1_duty && t > 0) {
                 // P1[t-1] = W_ih1_slice * h0_{t-1}^T has been accumulating behind this step's recurrent MMAs
                 mbar_wait(p1_done, (t - 1) & 1);
                 tc_fence_after();
+#if WAVE_TMA
+                if (tid == 0) *p1_safe = (uint32_t)t;      // the projection MMAs of step t (operand buffer t&1) are complete
+#endif
                 float pa[CPW];
                 tmem_ld_nb<CPW>(tmem_p + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * CPW), pa);
 #pragma unroll
@@ -698,9 +847,19 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
             uint8_t* dst = smem + S::G1_OFF + buf * S::G_BUF;
             constexpr int PER = NPARTW / NT;
             uint4 v[PER];
+#if WAVE_FLAGPOLL
+            if (warp == 0) {
+                if (lane == 0) {
+                    uint4 sv = ld_ll(src + NPARTW - 1);
+                    wait_ll(sv, src + NPARTW - 1, fbase + (uint32_t)(T - t));
+                }
+                __syncwarp();
+            }
+            bar_compute();
+#endif
 #pragma unroll
             for (int i = 0; i < PER; ++i) v[i] = ld_ll(src + tid + i * NT);
-            wait_ll_all<PER>(v, [&](int i) { return src + tid + i * NT; }, fbase + (uint32_t)(T - t));
+            wait_ll_all<PER, WAVE_POLL_SEQ_BWD != 0>(v, [&](int i) { return src + tid + i * NT; }, fbase + (uint32_t)(T - t));
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int w = tid + i * NT;
@@ -788,9 +947,20 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 // ---- the 8 partial tiles of this CTA's units (fixed summation order: deterministic)
                 const uint4* rd = wr + ((size_t)rank * WG) * WRS + warp * 32 + lane;
                 uint4 pr[WG];
+#if WAVE_FLAGPOLL
+                if (warp == 0) {
+                    if (lane < WG) {
+                        const uint4* sp = wr + ((size_t)rank * WG + lane) * WRS + (WRS - 1);
+                        uint4 sv = ld_ll(sp);
+                        wait_ll(sv, sp, fbase + k + 1);
+                    }
+                    __syncwarp();
+                }
+                bar_compute();
+#endif
 #pragma unroll
                 for (int src = 0; src < WG; ++src) pr[src] = ld_ll(rd + src * WRS);
-                wait_ll_all<WG>(pr, [&](int src) { return rd + src * WRS; }, fbase + k + 1);
+                wait_ll_all<WG, WAVE_POLL_SEQ_BWD != 0>(pr, [&](int src) { return rd + src * WRS; }, fbase + k + 1);
 #pragma unroll
                 for (int src = 0; src < WG; ++src) {                      // fixed summation order: deterministic
                     dh[0] += __uint_as_float(pr[src].x);

@@ -41,8 +41,9 @@ def test_gather_property(case):
     table = torch.randn(N, Z, generator=g).to(DEV)
     out = torch.full((B, Z), -1.0, device=DEV)
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
-    call("fhvae_mu2_gather", ptr(table), ptr(idx.to(DEV)), ptr(out), B, Z, N, ptr(flag))
-    assert torch.equal(out, table[idx.to(DEV)]) and int(flag) == 0
+    idd = idx.to(DEV)                      # (device temporaries must outlive the launch: keep references)
+    call("fhvae_mu2_gather", ptr(table), ptr(idd), ptr(out), B, Z, N, ptr(flag))
+    assert torch.equal(out, table[idd]) and int(flag) == 0
 
 
 @SET
@@ -56,10 +57,11 @@ def test_scatter_reduce_property(case):
     base = torch.randint(-3, 4, (N, Z), generator=g).float()
     ref = base.clone().index_add_(0, idx, src)
     outs = []
+    sd, idd = src.to(DEV), idx.to(DEV)
     for _ in range(2):
         dst = base.clone().to(DEV)
         touched = torch.full((B,), -1, dtype=torch.int32, device=DEV)
-        call("fhvae_mu2_scatter_reduce", ptr(src.to(DEV)), ptr(idx.to(DEV)), ptr(dst), ptr(touched), B, Z, N)
+        call("fhvae_mu2_scatter_reduce", ptr(sd), ptr(idd), ptr(dst), ptr(touched), B, Z, N)
         outs.append(dst.cpu())
     assert torch.equal(outs[0], ref) and torch.equal(outs[0], outs[1])
     first, seen = torch.zeros(B, dtype=torch.int32), set()
@@ -80,7 +82,8 @@ def test_accumulate_property(case):
     z = torch.randint(-8, 9, (B, 2 * Z), generator=g).float()        # (B, 2Z) head layout: ld = 2Z, first Z columns used
     zsum, cnt = torch.zeros(N, Z, device=DEV), torch.zeros(N, device=DEV)
     flag = torch.zeros(1, dtype=torch.int32, device=DEV)
-    call("fhvae_mu2_accumulate", ptr(z.to(DEV)), 2 * Z, ptr(idx.to(DEV)), ptr(zsum), ptr(cnt), B, Z, N, ptr(flag))
+    zd, idd = z.to(DEV), idx.to(DEV)
+    call("fhvae_mu2_accumulate", ptr(zd), 2 * Z, ptr(idd), ptr(zsum), ptr(cnt), B, Z, N, ptr(flag))
     assert torch.equal(zsum.cpu(), torch.zeros(N, Z).index_add_(0, idx, z[:, :Z]))
     assert torch.equal(cnt.cpu().long(), torch.bincount(idx, minlength=N)) and int(flag) == 0
 
@@ -99,7 +102,8 @@ def test_rows_copy_property(n, Z, seed):
     skip = torch.rand(n, generator=g) < 0.2
     d_rows = torch.where(skip, torch.full_like(d_rows, -1), d_rows)
     dst = dst0.clone().to(DEV)
-    call("fhvae_rows_copy", ptr(src.to(DEV)), ptr(s_rows.to(DEV)), ptr(dst), ptr(d_rows.to(DEV)), n, Z)
+    sd, srd, drd = src.to(DEV), s_rows.to(DEV), d_rows.to(DEV)
+    call("fhvae_rows_copy", ptr(sd), ptr(srd), ptr(dst), ptr(drd), n, Z)
     ref = dst0.clone()
     for i in range(n):
         if int(d_rows[i]) >= 0:
