@@ -298,17 +298,25 @@ int fhvae_split_planes_batch(const fhvae_split_problem* problems, int n_problems
 /* The wavefront recurrence with bf16 hi/lo planes as additional (fwd) or alternative (bwd) outputs: the planes are
  * the TMA operands of fhvae_wgrad_planes_batch, written by the kernel that produces the tensor instead of by a
  * separate fhvae_split_planes_batch pass.  *_planes: bf16 [2][T*B*width], hi at element i, lo at plane_stride + i
- * (may be NULL).  In the backward the fp32 dgates_* may be NULL when the corresponding planes are given. */
+ * (may be NULL).  In the backward the fp32 dgates_* may be NULL when the corresponding planes are given.
+ * packed (may be NULL): the stack's pre-packed weight operands written by fhvae_lstm_wave_pack from the SAME weights
+ * and mode -- the kernels then fill TMEM / shared memory with coalesced loads and bulk copies instead of converting
+ * the fp32 weights in every launch (9-15 us of each of the six recurrent launches of a step). */
+long long fhvae_lstm_wave_pack_bytes(int H, int nlayers, int mode);
+/* W_hh0: layer 0 (or the only layer); W_ih1, W_hh1: layer 1 of a 2-layer stack (else NULL).  packed: 128-byte aligned,
+ * fhvae_lstm_wave_pack_bytes bytes.  Must be re-run whenever the weights change (once per optimizer step). */
+int fhvae_lstm_wave_pack(const float* W_hh0, const float* W_ih1, const float* W_hh1, void* packed, int H, int nlayers,
+                         int mode, void* stream);
 int fhvae_lstm_wave_fwd_planes(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0, float* acts0,
                                const float* W_ih1, const float* bias1, const float* W_hh1, float* h1, float* c1,
-                               float* acts1, void* xchg, void* h0_planes, void* h1_planes, int64_t plane_stride, int T,
-                               int B, int H, int nlayers, int mode, void* stream);
+                               float* acts1, void* xchg, void* h0_planes, void* h1_planes, int64_t plane_stride,
+                               const void* packed, int T, int B, int H, int nlayers, int mode, void* stream);
 int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* dh_last_top, const float* dh_last_bot,
                                const float* W_hh_top, const float* c_top, const float* acts_top, float* dgates_top,
                                float* dgsum_top, const float* W_ih_top, const float* W_hh_bot, const float* c_bot,
                                const float* acts_bot, float* dgates_bot, float* dgsum_bot, void* xchg,
-                               void* dg_top_planes, void* dg_bot_planes, int64_t plane_stride, int T, int B, int H,
-                               int nlayers, int mode, void* stream);
+                               void* dg_top_planes, void* dg_bot_planes, int64_t plane_stride, const void* packed,
+                               int T, int B, int H, int nlayers, int mode, void* stream);
 
 /* x (B,T,F), mu_idx (B int64, may be NULL), num_segs (B int64, may be NULL) -> the step's static input buffers, one
  * launch (device-to-device; the batch of train_model.py:444-445 into CUDA-graph-stable storage).  x is also written

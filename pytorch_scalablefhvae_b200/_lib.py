@@ -60,8 +60,10 @@ PROTOTYPES = {
     "fhvae_lstm_wave_xchg_bytes": [_i, _i, _i, _i],
     "fhvae_lstm_wave_fwd": [_p] * 13 + [_i, _i, _i, _i, _i, _p],
     "fhvae_lstm_wave_bwd_xchg_bytes": [_i, _i, _i, _i],
-    "fhvae_lstm_wave_fwd_planes": [_p] * 15 + [_l, _i, _i, _i, _i, _i, _p],
-    "fhvae_lstm_wave_bwd_planes": [_p] * 17 + [_l, _i, _i, _i, _i, _i, _p],
+    "fhvae_lstm_wave_fwd_planes": [_p] * 15 + [_l, _p, _i, _i, _i, _i, _i, _p],
+    "fhvae_lstm_wave_bwd_planes": [_p] * 17 + [_l, _p, _i, _i, _i, _i, _i, _p],
+    "fhvae_lstm_wave_pack_bytes": [_i, _i, _i],
+    "fhvae_lstm_wave_pack": [_p, _p, _p, _p, _i, _i, _i, _p],
     "fhvae_lstm_wave_bwd": [_p] * 15 + [_i, _i, _i, _i, _i, _p],
     "fhvae_reparam_fwd": [_p, _l, _p, _p, _l, _i, _i, _p],
     "fhvae_reparam_bwd": [_p, _l, _p, _p, _l, _p, _l, _i, _i, _i, _p],
@@ -98,7 +100,7 @@ PROTOTYPES = {
     "fhvae_built_for_sm": [],
     "fhvae_launch_count": [],
 }
-NO_STATUS = {"fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
+NO_STATUS = {"fhvae_lstm_wave_pack_bytes", "fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
 EXPORTS = sorted(list(PROTOTYPES) + ["fhvae_last_error_string"])
 
 _lib = None
@@ -137,7 +139,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if the .so lacks a declared symbol
         fn.argtypes = args
         fn.restype = (C.c_ulonglong if name == "fhvae_launch_count" else
-                      C.c_longlong if name.endswith("xchg_bytes") else C.c_int)
+                      C.c_longlong if name.endswith("_bytes") else C.c_int)
     _lib = lib
     return lib
 

@@ -37,12 +37,14 @@ size_t lstm_wave_xchg_bytes(int T, int B, int L);
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
                   void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0 = nullptr, void* hp1 = nullptr,
-                  long long hps = 0);
+                  long long hps = 0, const void* packed = nullptr);
+size_t lstm_wave_pack_bytes(int L, int mode);
+int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int L, int mode, cudaStream_t st);
 size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L);
 int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
                   const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
                   const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st,
-                  void* dgp1 = nullptr, void* dgp0 = nullptr, long long dgps = 0);
+                  void* dgp1 = nullptr, void* dgp0 = nullptr, long long dgps = 0, const void* packed = nullptr);
 
 }  // namespace fhvae
 
@@ -97,6 +99,8 @@ extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const f
                          as_stream(stream));
 }
 
+static constexpr int WAVE_MIN_B = 32;
+
 extern "C" int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int mode) {
     return (mode == FHVAE_MODE_BF16X3 || mode == FHVAE_MODE_BF16) && lstm_wave_supported(T, B, H, nlayers) ? 1 : 0;
 }
@@ -121,14 +125,28 @@ extern "C" int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float
 extern "C" int fhvae_lstm_wave_fwd_planes(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0,
                                           float* acts0, const float* W_ih1, const float* bias1, const float* W_hh1,
                                           float* h1, float* c1, float* acts1, void* xchg, void* h0_planes,
-                                          void* h1_planes, int64_t plane_stride, int T, int B, int H, int nlayers,
-                                          int mode, void* stream) {
+                                          void* h1_planes, int64_t plane_stride, const void* packed, int T, int B, int H,
+                                          int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
                     "lstm_wave_fwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh0 && h0 && c0 && acts0 && xchg && (P0 || Q0), "lstm_wave_fwd: null pointer (layer 0)");
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih1 && W_hh1 && h1 && c1 && acts1), "lstm_wave_fwd: null pointer (layer 1)");
     return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, nlayers,
-                         mode, as_stream(stream), h0_planes, nlayers == 2 ? h1_planes : nullptr, plane_stride);
+                         mode, as_stream(stream), h0_planes, nlayers == 2 ? h1_planes : nullptr, plane_stride, packed);
+}
+
+extern "C" long long fhvae_lstm_wave_pack_bytes(int H, int nlayers, int mode) {
+    if (!fhvae_lstm_wave_supported(1, WAVE_MIN_B, H, nlayers, mode)) return 0;
+    return (long long)lstm_wave_pack_bytes(nlayers, mode);
+}
+
+extern "C" int fhvae_lstm_wave_pack(const float* W_hh0, const float* W_ih1, const float* W_hh1, void* packed, int H,
+                                    int nlayers, int mode, void* stream) {
+    FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(1, WAVE_MIN_B, H, nlayers, mode),
+                    "lstm_wave_pack: needs a tensor-core mode, H == 256, 1 or 2 layers");
+    FHVAE_CHECK_ARG(W_hh0 && packed && (nlayers == 1 || (W_ih1 && W_hh1)), "lstm_wave_pack: null pointer");
+    FHVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "lstm_wave_pack: the image buffer must be 128-byte aligned");
+    return lstm_wave_pack(W_hh0, W_ih1, W_hh1, packed, nlayers, mode, as_stream(stream));
 }
 
 extern "C" long long fhvae_lstm_wave_bwd_xchg_bytes(int T, int B, int H, int nlayers) {
@@ -156,8 +174,8 @@ extern "C" int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* 
                                           float* dgates_top, float* dgsum_top, const float* W_ih_top,
                                           const float* W_hh_bot, const float* c_bot, const float* acts_bot,
                                           float* dgates_bot, float* dgsum_bot, void* xchg, void* dg_top_planes,
-                                          void* dg_bot_planes, int64_t plane_stride, int T, int B, int H, int nlayers,
-                                          int mode, void* stream) {
+                                          void* dg_bot_planes, int64_t plane_stride, const void* packed, int T, int B, int H,
+                                          int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
                     "lstm_wave_bwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh_top && c_top && acts_top && (dgates_top || dg_top_planes) && xchg,
@@ -167,5 +185,5 @@ extern "C" int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* 
     FHVAE_CHECK_ARG(dh_all_top || dh_last_top || (nlayers == 2 && dh_last_bot), "lstm_wave_bwd: no incoming gradient");
     return lstm_wave_bwd(dh_all_top, dh_last_top, dh_last_bot, W_hh_top, c_top, acts_top, dgates_top, dgsum_top, W_ih_top,
                          W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, nlayers, mode, as_stream(stream),
-                         dg_top_planes, nlayers == 2 ? dg_bot_planes : nullptr, plane_stride);
+                         dg_top_planes, nlayers == 2 ? dg_bot_planes : nullptr, plane_stride, packed);
 }

@@ -106,7 +106,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void* src, uin
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+#ifndef WAVE_TMA_FENCE
+#define WAVE_TMA_FENCE 1     // consumer-side proxy fence before the bulk copies: 0 none, 1 .global, 2 all state spaces
+#endif
+__device__ __forceinline__ void fence_proxy_async_all() {
+#if WAVE_TMA_FENCE == 2
+    asm volatile("fence.proxy.async;" ::: "memory");
+#elif WAVE_TMA_FENCE == 1
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+#endif
+}
 
 // Wait for N LL words at once: every retry round re-issues ALL still-invalid loads back to back, so a round costs
 // one L2 round trip (~260 cycles) however many words are outstanding.  (Waiting word by word -- wait_ll in a loop --
@@ -115,20 +124,21 @@ __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.pr
 template <int N, bool SEQ, typename AddrFn>
 __device__ __forceinline__ uint32_t wait_ll_all(uint4 (&v)[N], AddrFn addr, uint32_t flag) {
     uint32_t spins = 0;
-    if (SEQ) {
+    if constexpr (SEQ) {
 #pragma unroll
         for (int i = 0; i < N; ++i) spins += wait_ll(v[i], addr(i), flag);
         return spins;
-    }
-    for (;;) {
-        uint32_t bad = 0;
+    } else {
+        for (;;) {
+            uint32_t bad = 0;
 #pragma unroll
-        for (int i = 0; i < N; ++i) bad |= (v[i].y != flag || v[i].w != flag) ? (1u << i) : 0u;
-        if (!bad) return spins;
-        if (++spins > FHVAE_SPIN_LIMIT) __trap();
+            for (int i = 0; i < N; ++i) bad |= (v[i].y != flag || v[i].w != flag) ? (1u << i) : 0u;
+            if (!bad) return spins;
+            if (++spins > FHVAE_SPIN_LIMIT) __trap();
 #pragma unroll
-        for (int i = 0; i < N; ++i)
-            if ((bad >> i) & 1u) v[i] = ld_ll(addr(i));
+            for (int i = 0; i < N; ++i)
+                if ((bad >> i) & 1u) v[i] = ld_ll(addr(i));
+        }
     }
 }
 
@@ -142,12 +152,167 @@ extern "C" int fhvae_debug_wave_timeline(long long* out) { return (int)cudaMemcp
 #define WTL1(step, slot) do { } while (0)
 #endif
 
+// ================================================================================================
+// Pre-packed weight operands.  Staging a CTA's W_hh slice into TMEM (and, for the cross-layer products, its W_ih1
+// slice into shared memory) from the fp32 weights costs 17-30 k cycles per launch (strided 16-byte loads of rows
+// 1 KB apart + fp32 -> bf16 hi/lo conversion, by 128 CTAs at once): 9-15 us of every one of the six recurrent
+// launches of a step.  wave_pack_kernel does the conversion ONCE per step (the weights only change in Adam) into
+// images laid out exactly as the kernels consume them:
+//   T images (128 x 256 bf16 per part, for tcgen05.st): uint4 [warp 16][v 8*parts][lane 32] -- a warp's load
+//            instruction reads 512 contiguous bytes; v = part*8 + hf*4 + i holds the 4 words {4i..4i+3} of the
+//            16-word tcgen05.st of half hf.
+//   S images (the UMMA no-swizzle K-major shared-memory operand, 64 KB per part): copied verbatim by cp.async.bulk.
+// Order in the buffer: fwdT[layer][rank], fwdS[rank] (2-layer stacks), bwdT[layer][rank], bwdS[rank].
+// ================================================================================================
+template <bool X3> struct WavePack {
+    static constexpr size_t IMG = (X3 ? 2 : 1) * 65536;
+    __host__ __device__ static constexpr int n_images(int L) { return 16 * L + (L == 2 ? 16 : 0); }
+    __host__ __device__ static constexpr size_t fwdT(int L, int layer, int rank) { return (size_t)(layer * WG + rank) * IMG; }
+    __host__ __device__ static constexpr size_t fwdS(int L, int rank) { return (size_t)(L * WG + rank) * IMG; }
+    __host__ __device__ static constexpr size_t bwdT(int L, int layer, int rank) {
+        return (size_t)(L * WG + (L == 2 ? WG : 0) + layer * WG + rank) * IMG;
+    }
+    __host__ __device__ static constexpr size_t bwdS(int L, int rank) { return (size_t)(2 * L * WG + WG + rank) * IMG; }
+};
+
+struct WavePackArgs { const float* Whh[2]; const float* Wih1; uint8_t* out; int L; };
+
+template <bool X3>
+__global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ WavePackArgs a) {
+    using PK = WavePack<X3>;
+    constexpr int CH = WH, UC = WU, NC = WNC, NT = WNT;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = (warp >> 2) & 3;
+    const int L = a.L;
+    int img = blockIdx.x;
+    const int nT = L * WG, nS = (L == 2) ? WG : 0;
+    auto store_T = [&](uint8_t* dst, const uint32_t (&w)[32], int part) {     // 32 words: [hf 2][16]
+        uint4* o = reinterpret_cast<uint4*>(dst) + (size_t)(warp * (X3 ? 16 : 8) + part * 8) * 32 + lane;
+#pragma unroll
+        for (int v = 0; v < 8; ++v) o[v * 32] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+    };
+    if (img < nT) {
+        // ---- forward TMEM image: lane n = gate q * 32 + unit, 32-bit column c = (k, k+1) pair, k = 2c
+        const int layer = img / WG, rank = img % WG;
+        const float* src = a.Whh[layer] + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const float4 w4 = __ldg(reinterpret_cast<const float4*>(src) + i);
+            const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const uint32_t h = pack_bf16(v[2 * j], v[2 * j + 1]);
+                hi[2 * i + j] = h;
+                lo[2 * i + j] = pack_bf16(v[2 * j] - __uint_as_float(h << 16), v[2 * j + 1] - __uint_as_float(h & 0xffff0000u));
+            }
+        }
+        uint8_t* dst = a.out + PK::fwdT(L, layer, rank);
+        store_T(dst, hi, 0);
+        if (X3) store_T(dst, lo, 1);
+        return;
+    }
+    img -= nT;
+    if (img < nS) {
+        // ---- forward shared-memory image of the W_ih1 slice: [part][K chunk 32][row 128] x 16 B
+        const int rank = img;
+        const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+        const int r = q * 32 + lane;
+        uint8_t* dst = a.out + PK::fwdS(L, rank);
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+            const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
+            const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
+            const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+            const uint32_t off = (uint32_t)(cg * 8 + i) * (NC * 16) + (uint32_t)r * 16;
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            *reinterpret_cast<uint4*>(dst + off) = hi;
+            if (X3) *reinterpret_cast<uint4*>(dst + 65536 + off) = lo;
+        }
+        return;
+    }
+    img -= nS;
+    if (img < nT) {
+        // ---- BPTT TMEM image of W_hh^T: lane = unit n (two halves of 128), column = pair of the CTA's 128 gate columns
+        const int layer = img / WG, rank = img % WG, g = cg;
+        const float* W = a.Whh[layer];
+        uint32_t hi[32], lo[32];
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const int n = hf * 128 + q * 32 + lane;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+                const float v0 = __ldg(W + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
+                const float v1 = __ldg(W + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
+                const uint32_t h = pack_bf16(v0, v1);
+                hi[hf * 16 + j] = h;
+                lo[hf * 16 + j] = pack_bf16(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xffff0000u));
+            }
+        }
+        uint8_t* dst = a.out + PK::bwdT(L, layer, rank);
+        store_T(dst, hi, 0);
+        if (X3) store_T(dst, lo, 1);
+        return;
+    }
+    img -= nT;
+    {
+        // ---- BPTT shared-memory image of W_ih1^T: [part][unit half 2][K chunk 16][unit 128] x 16 B
+        const int rank = img;
+        uint8_t* dst = a.out + PK::bwdS(L, rank);
+        constexpr int WIT = CH * (NC / 8) / NT;
+#pragma unroll 2
+        for (int i = 0; i < WIT; ++i) {
+            const int item = tid + i * NT;
+            const int n = item & (CH - 1), kc = item >> 8;
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = kc * 8 + j, g = k >> 5, u = k & 31;
+                v[j] = __ldg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
+            }
+            const uint32_t off = (uint32_t)(n >> 7) * (128 * NC * 2) + (uint32_t)(kc * 128 + (n & 127)) * 16;
+            uint4 hi, lo;
+            split_bf16(v, hi, lo);
+            *reinterpret_cast<uint4*>(dst + off) = hi;
+            if (X3) *reinterpret_cast<uint4*>(dst + 65536 + off) = lo;
+        }
+    }
+}
+
+// packed T image -> this thread's TMEM columns: 8 coalesced 16-byte loads + 2 tcgen05.st.x16 per bf16 part
+template <bool X3>
+__device__ __forceinline__ void wave_load_T_image(const uint8_t* img, int warp, int lane, uint32_t ta, uint32_t half_stride,
+                                                  uint32_t part_stride) {
+#pragma unroll
+    for (int part = 0; part < (X3 ? 2 : 1); ++part) {
+        const uint4* src = reinterpret_cast<const uint4*>(img) + (size_t)(warp * (X3 ? 16 : 8) + part * 8) * 32 + lane;
+        uint4 u[8];
+#pragma unroll
+        for (int v = 0; v < 8; ++v) u[v] = __ldg(src + v * 32);
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+            const uint32_t w[16] = {u[4 * hf].x,     u[4 * hf].y,     u[4 * hf].z,     u[4 * hf].w,
+                                    u[4 * hf + 1].x, u[4 * hf + 1].y, u[4 * hf + 1].z, u[4 * hf + 1].w,
+                                    u[4 * hf + 2].x, u[4 * hf + 2].y, u[4 * hf + 2].z, u[4 * hf + 2].w,
+                                    u[4 * hf + 3].x, u[4 * hf + 3].y, u[4 * hf + 3].z, u[4 * hf + 3].w};
+            tmem_st16(ta + part * part_stride + hf * half_stride, w);
+        }
+    }
+}
+// packed S image -> shared memory, 16-KB bulk copies counted on `bar` (issued by one thread)
+__device__ __forceinline__ void wave_load_S_image(const uint8_t* img, uint32_t dst_smem, uint32_t bytes, uint64_t* bar) {
+    mbar_arrive_expect_tx(bar, bytes);
+    for (uint32_t o = 0; o < bytes; o += 16384) bulk_g2s(dst_smem + o, img + o, 16384, bar);
+}
+
 struct WaveFwdArgs {
     const float* P0; const float* Q0; const float* Whh0; float* h0; float* c0; float* a0;
     const float* Wih1; const float* b1; const float* Whh1; float* h1; float* c1; float* a1;
     uint4* xchg;
     int T, B, b_off, G, Gs, L;     // B = row stride (whole batch), G groups in this launch, Gs = slot stride
     __nv_bfloat16* hp0; __nv_bfloat16* hp1; long long hps;   // optional bf16 hi/lo planes of h (lo at +hps), for gemm_wgrad.cu
+    const uint8_t* packed;          // optional pre-packed operand images of the weights (wave_pack_kernel); NULL: convert here
 };
 
 template <bool X3>
@@ -230,6 +395,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p1_done + 1);
     uint32_t* epoch_slot = tmem_slot + 1;
     volatile uint32_t* p1_safe = epoch_slot + 1;    // WAVE_TMA: last step whose projection MMAs are known complete
+    uint64_t* w_full = hb_full + 6;                 // packed W_ih1 image landed in shared memory (bulk copies)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = (warp >> 2) & 3;   // gate (= TMEM lane quarter), column group
@@ -252,6 +418,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     uint4* own = a.xchg + WHDR + ((size_t)(layer * a.Gs + grp) * T) * (WG * WSLICE);
     uint4* p1x = a.xchg + WHDR + ((size_t)(2 * a.Gs) * T) * (WG * WSLICE) + ((size_t)grp * T) * (WG * WPSLICE) + rank * WPSLICE;
 
+    WTL(0, 15);
     // ---- prologue: TMEM, barriers, W_hh slice -> TMEM (lane n = gate*32 + unit, column k/2 = bf16 pair)
     constexpr int NACC = 2;
     constexpr int WCOLS = CH / 2;
@@ -259,18 +426,21 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     constexpr int TCOLS = (ACOL + 2 * NACC * NB) <= 256 ? 256 : 512;
     if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) {
-        // WAVE_TMA: + one arrive.expect_tx per peer slice (issued by the pull lanes of warp 17)
-        mbar_init(&hb_full[0], NT / 32 + (WAVE_TMA ? WG - 1 : 0)); mbar_init(&hb_full[1], NT / 32 + (WAVE_TMA ? WG - 1 : 0));
-        mbar_init(rec_done, 1); mbar_init(p1_done, 1);
+        // WAVE_TMA: + one arrive.expect_tx for the 7 peer slices (pull lanes of warp 17)
+        mbar_init(&hb_full[0], NT / 32 + (WAVE_TMA ? 1 : 0)); mbar_init(&hb_full[1], NT / 32 + (WAVE_TMA ? 1 : 0));
+        mbar_init(rec_done, 1); mbar_init(p1_done, 1); mbar_init(w_full, 1);
         fence_mbar_init();
         *epoch_slot = *cnt;
         *p1_safe = 0;
+        if (p1_duty && a.packed)
+            wave_load_S_image(a.packed + WavePack<X3>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t fbase = (*epoch_slot) << 6;
+    WTL(3, 15);
     constexpr uint32_t W_LBO = WNC * 16, H_LBO = NB * 16, SBO_ = 128;
     const uint32_t tmem_d = tmem_base + ACOL;                  // recurrent accumulators [NACC][NB]
     const uint32_t tmem_p = tmem_d + NACC * NB;                // layer-1 projection accumulators [NACC][NB]
@@ -284,6 +454,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         __syncthreads();                                        // operands staged by the compute warps
         tc_fence_after();
         if (warp == NT / 32 && elect_one()) {
+            if (p1_duty && a.packed) mbar_wait(w_full, 0);
             for (int t = 1; t < nsteps; ++t) {
                 const uint32_t hbt = hb_u + (t & 1) * S::H_BUF;
                 const uint64_t dhh0 = make_smem_desc(hbt, H_LBO, SBO_);
@@ -342,6 +513,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             // hb_full barrier counts the bytes.  No compute warp touches the exchange.
             const int src = lane + (lane >= rank ? 1 : 0);
             constexpr uint32_t PART_BYTES = 4 * H_LBO;                       // 4 K-chunks x 32 rows x 16 B = 2 KB
+            constexpr uint32_t PULL_MASK = (1u << (WG - 1)) - 1;
             for (int t = 1; t < nsteps; ++t) {
                 const uint4* sl = own + (size_t)(t - 1) * (WG * WSLICE) + src * WSLICE;
                 // buffer t&1 was last read by the projection MMAs of step t-2 (p1_duty only; the recurrent MMAs of
@@ -351,11 +523,19 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                     while (*p1_safe < (uint32_t)(t - 2))
                         if (++spins > FHVAE_SPIN_LIMIT) __trap();
                 }
-                wait_flag(reinterpret_cast<const uint32_t*>(sl + 256), fbase + t);
+                // the 7 lanes poll in lockstep (one converged loop: no divergent re-issue of the copies)
+                const uint32_t* fp = reinterpret_cast<const uint32_t*>(sl + 256);
+                bool seen = false;
+                uint32_t spins = 0;
+                do {
+                    if (!seen) seen = ld_acquire_gpu(fp) == fbase + t;
+                    if (++spins > FHVAE_SPIN_LIMIT) __trap();
+                } while (!__all_sync(PULL_MASK, seen));
                 if (lane == WG - 2) WTL1(t, 11);
                 fence_proxy_async_all();
                 uint64_t* bar = &hb_full[t & 1];
-                mbar_arrive_expect_tx(bar, (X3 ? 2u : 1u) * PART_BYTES);
+                if (lane == 0) mbar_arrive_expect_tx(bar, (WG - 1) * (X3 ? 2u : 1u) * PART_BYTES);
+                __syncwarp(PULL_MASK);
                 const uint32_t dst = hb_u + (t & 1) * S::H_BUF + (uint32_t)src * PART_BYTES;
                 bulk_g2s(dst, sl, PART_BYTES, bar);
                 if (X3) bulk_g2s(dst + S::H_PART, reinterpret_cast<const uint8_t*>(sl) + PART_BYTES, PART_BYTES, bar);
@@ -367,30 +547,36 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     } else {
         // ================= compute warps =================
         reg_inc<112>();   // 20 warps x 96 regs at launch = 16 x 112 + 4 x 32 (setmaxnreg only moves registers inside the CTA)
-        const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
-        float4 wv[16];
-#pragma unroll
-        for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+        WTL(4, 15);
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
+        if (a.packed) {
+            wave_load_T_image<X3>(a.packed + WavePack<X3>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
+        } else {
+            const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+            float4 wv[16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-            uint32_t hi[16], lo[16];
+            for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float4 w4 = wv[hf * 8 + i];
-                const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t hi[16], lo[16];
 #pragma unroll
-                for (int j = 0; j < 2; ++j) {
-                    hi[2 * i + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
-                    lo[2 * i + j] = pack_bf16(v[2 * j] - __uint_as_float(hi[2 * i + j] << 16),
-                                              v[2 * j + 1] - __uint_as_float(hi[2 * i + j] & 0xffff0000u));
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w4 = wv[hf * 8 + i];
+                    const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        hi[2 * i + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                        lo[2 * i + j] = pack_bf16(v[2 * j] - __uint_as_float(hi[2 * i + j] << 16),
+                                                  v[2 * j + 1] - __uint_as_float(hi[2 * i + j] & 0xffff0000u));
+                    }
                 }
+                tmem_st16(ta + hf * 16, hi);
+                if (X3) tmem_st16(ta + WCOLS + hf * 16, lo);
             }
-            tmem_st16(ta + hf * 16, hi);
-            if (X3) tmem_st16(ta + WCOLS + hf * 16, lo);
         }
         tmem_wait_st();
-        if (p1_duty) {
+        WTL(5, 15);
+        if (p1_duty && !a.packed) {
             // resident W_ih1 slice as an smem A operand: row n = gate*32 + unit, K-chunk planes of W_LBO bytes
             const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
             const int r = q * 32 + lane;
@@ -411,10 +597,12 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
             }
         }
+        WTL(6, 15);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        WTL(7, 15);
         // time-invariant addend for this thread's (gate q, unit lane) column, rows cg*CPW ..
         const int col = q * CH + rank * UC + lane;
         float qv[CPW];
@@ -423,6 +611,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
 #pragma unroll
             for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
         }
+        WTL(1, 15);
         float creg[RPT];
 #pragma unroll
         for (int i = 0; i < RPT; ++i) creg[i] = 0.f;
@@ -616,6 +805,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             }
         }
         if (!p1_duty) store_saved(T - 1);
+        WTL(2, 15);
     }
     if (tid == 0) *cnt = (fbase >> 6) + 1;
     tc_fence_before();
@@ -644,6 +834,7 @@ struct WaveBwdArgs {
     uint4* xchg;
     int T, B, b_off, G, Gs, L;
     __nv_bfloat16* dgp1; __nv_bfloat16* dgp0; long long dgps;   // optional bf16 hi/lo planes of dgates (lo at +dgps)
+    const uint8_t* packed;          // optional pre-packed operand images of the weights (wave_pack_kernel)
 };
 
 template <bool X3>
@@ -677,6 +868,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     uint64_t* rec_done = g_full + 3;                                       // issuer (commit) -> compute warps
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(g_full + 4);
     uint32_t* epoch_slot = tmem_slot + 1;
+    uint64_t* w_full = g_full + 6;                                         // packed W_ih1^T image landed in shared memory
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = (warp >> 2) & 3;
@@ -708,9 +900,11 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) {
         mbar_init(&g_full[0], NT / 32); mbar_init(&g_full[1], NT / 32); mbar_init(g_pro, NT / 32);
-        mbar_init(rec_done, 1);
+        mbar_init(rec_done, 1); mbar_init(w_full, 1);
         fence_mbar_init();
         *epoch_slot = *cnt;
+        if (bottom && a.packed)
+            wave_load_S_image(a.packed + WavePack<X3>::bwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
     tc_fence_before();
     __syncthreads();
@@ -772,6 +966,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 }
             };
             if (bottom) {
+                if (a.packed) mbar_wait(w_full, 0);
                 mbar_wait(g_pro, 0);                           // dgates1_{T-1} (and _{T-2}) are in G1
                 tc_fence_after();
                 cross((uint32_t)((T - 1) & 1), (uint32_t)((T - 1) & 1));
@@ -791,7 +986,12 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     } else {
         // ================= compute warps =================
         reg_inc<112>();
-        {   // resident A operand of the recurrent product: lane = unit n (per half), column = (k, k+1) pair of the
+        if (a.packed) {
+            const int layer_of = bottom ? 0 : a.L - 1;
+            wave_load_T_image<X3>(a.packed + WavePack<X3>::bwdT(a.L, layer_of, rank), warp, lane,
+                                  tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16), WCOLS, 2 * WCOLS);
+            tmem_wait_st();
+        } else {   // resident A operand of the recurrent product: lane = unit n (per half), column = (k, k+1) pair of the
             // CTA's 128 gate columns k = g*32 + u;  A[n][k] = W_hh[(g*H + 32*rank + u) * H + n];  cg <-> gate g
             const int g = cg;
 #pragma unroll 1
@@ -811,7 +1011,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
             }
             tmem_wait_st();
         }
-        if (bottom) {
+        if (bottom && !a.packed) {
             // resident smem A operand of the cross-layer product: A2[n][k] = W_ih1[(g*H + 32*rank + u) * H + n]
             constexpr int WIT = CH * (NC / 8) / NT;
 #pragma unroll 2
@@ -1066,9 +1266,11 @@ static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
 
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
-                  void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0, void* hp1, long long hps) {
+                  void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0, void* hp1, long long hps,
+                  const void* packed) {
     WaveFwdArgs a{P0, Q0, Whh0, h0, c0, a0, Wih1, b1, Whh1, h1, c1, a1, reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
-                  reinterpret_cast<__nv_bfloat16*>(hp0), reinterpret_cast<__nv_bfloat16*>(hp1), hps};
+                  reinterpret_cast<__nv_bfloat16*>(hp0), reinterpret_cast<__nv_bfloat16*>(hp1), hps,
+                  reinterpret_cast<const uint8_t*>(packed)};
     return mode == FHVAE_MODE_BF16X3 ? launch_wave_fwd<true>(a, st) : launch_wave_fwd<false>(a, st);
 }
 
@@ -1106,11 +1308,28 @@ static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
 int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
                   const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
                   const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st,
-                  void* dgp1, void* dgp0, long long dgps) {
+                  void* dgp1, void* dgp0, long long dgps, const void* packed) {
     WaveBwdArgs a{dh_all, dh_last1, dh_last0, Whh1, c1, a1, dg1, dgsum1, Wih1, Whh0, c0, a0, dg0, dgsum0,
                   reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
-                  reinterpret_cast<__nv_bfloat16*>(dgp1), reinterpret_cast<__nv_bfloat16*>(dgp0), dgps};
+                  reinterpret_cast<__nv_bfloat16*>(dgp1), reinterpret_cast<__nv_bfloat16*>(dgp0), dgps,
+                  reinterpret_cast<const uint8_t*>(packed)};
     return mode == FHVAE_MODE_BF16X3 ? launch_wave_bwd<true>(a, st) : launch_wave_bwd<false>(a, st);
+}
+
+size_t lstm_wave_pack_bytes(int L, int mode) {
+    return mode == FHVAE_MODE_BF16X3 ? WavePack<true>::n_images(L) * WavePack<true>::IMG
+                                     : WavePack<false>::n_images(L) * WavePack<false>::IMG;
+}
+
+// layer-indexed weights: Whh_l0 (bottom / only layer), Wih1 + Whh_l1 (second layer of a 2-layer stack)
+int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int L, int mode, cudaStream_t st) {
+    WavePackArgs a{{Whh_l0, Whh_l1}, Wih1, reinterpret_cast<uint8_t*>(out), L};
+    if (mode == FHVAE_MODE_BF16X3)
+        wave_pack_kernel<true><<<WavePack<true>::n_images(L), WNT, 0, st>>>(a);
+    else
+        wave_pack_kernel<false><<<WavePack<false>::n_images(L), WNT, 0, st>>>(a);
+    FHVAE_LAUNCH_CHECK("lstm_wave_pack");
+    return 0;
 }
 
 }  // namespace fhvae

@@ -673,6 +673,14 @@ class _FHVAEPlan(_Plan):
                              _lib.fn("fhvae_lstm_wave_supported")(T, B, self.H[k], 2, self.mode))
                      for (k, _), hus in zip(self.NETS, (m.z2_hus, m.z1_hus, m.x_hus))}
         self.wave_xchg = self.wave_xchg_bwd = None
+        # pre-packed weight operands of the wavefront kernels (fhvae_lstm_wave_pack): rebuilt at the start of every
+        # forward list from the current weights, consumed by the stack's forward AND BPTT launch
+        self.wave_packed = {}
+        if os.environ.get("FHVAE_WAVE_PACK", "1") != "0":
+            for k, on in self.wave.items():
+                if on:
+                    nb = _lib.fn("fhvae_lstm_wave_pack_bytes")(self.H[k], 2, self.mode)
+                    self.wave_packed[k] = torch.zeros(nb // 4, dtype=torch.float32, device=self.dev)
         if any(self.wave.values()):
             Hw = next(self.H[k] for k in self.wave if self.wave[k])
             nbytes = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, Hw, 2)
@@ -717,6 +725,10 @@ class _FHVAEPlan(_Plan):
         pre = dict(self.NETS)
         c.add("fhvae_add2", ptr(self.bsum), m.poff(m._bias_first[0]), m.poff(m._bias_first[1]),
               m._bias_block_len, side=2)             # fused (b_ih + b_hh), beside the transpose
+        for k, buf in self.wave_packed.items():      # weight operand images: side stream 3, beside the x projection
+            _, whh0, _, _ = _lstm_names(dict(self.NETS)[k], 0)
+            wih1, whh1, _, _ = _lstm_names(dict(self.NETS)[k], 1)
+            c.add("fhvae_lstm_wave_pack", m.poff(whh0), m.poff(wih1), m.poff(whh1), ptr(buf), self.H[k], 2, mode, side=3)
         Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
         wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
         wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
@@ -739,7 +751,8 @@ class _FHVAEPlan(_Plan):
                 c.add("fhvae_lstm_wave_fwd_planes", ptr(self.P[k, 0]) if (k, 0) in self.P else None, q0, m.poff(whh0),
                       ptr(self.h[k, 0]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), m.poff(wih1), self._bs(k, 1),
                       m.poff(whh1), ptr(self.h[k, 1]), ptr(self.c[k, 1]), ptr(self.acts[k, 1]),
-                      ptr(self.wave_xchg), hp[0], hp[1], T * B * H, T, B, H, 2, mode)
+                      ptr(self.wave_xchg), hp[0], hp[1], T * B * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
+                      T, B, H, 2, mode)
                 return
             for l in range(self.L[k]):
                 wih, whh, _, _ = _lstm_names(pre[k], l)
@@ -772,6 +785,7 @@ class _FHVAEPlan(_Plan):
             c.gemm([gemm_nt(ptr(self.zcat, qoff), Z1 + Z2, Wq, ld_wq, ptr(Q), NQ, B, NQ, Kq, bias=bq or 0)], mode)
 
         # z2 encoder -> head -> sample (into zcat[:, Z1:]) -> time-invariant z2 part of the z1 encoder's input (Q)
+        c.join(3)              # packed weight operands
         stack("z2", None)
         head_stage("z2", Hz2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias", self.z2head, Z2,
                    self.eps2, Z1, m.poff(wih_z1, F), F + Z2, None, Z1, Z2, self.Q["z1"], 4 * Hz1)
@@ -879,7 +893,8 @@ class _FHVAEPlan(_Plan):
                       ptr(self.c[k, 1]), ptr(self.acts[k, 1]), None if use_tma else ptr(self.dg[k, 1]),
                       ptr(self.dgsum[k, 1]), m.poff(n1[0]), m.poff(n0[1]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]),
                       None if use_tma else ptr(self.dg[k, 0]), ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd),
-                      dgp[1], dgp[0], T * B * 4 * H, T, B, H, 2, mode)
+                      dgp[1], dgp[0], T * B * 4 * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
+                      T, B, H, 2, mode)
                 for l in (1, 0):
                     wih, whh, bih, bhh = _lstm_names(pre[k], l)
                     if T > 1:

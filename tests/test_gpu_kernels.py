@@ -269,6 +269,15 @@ def _wave_xchg(T, B, H, L):
     return torch.zeros(n // 4, device=DEV)
 
 
+def _wave_packed(W0, Wi1, W1, H, L, mode):
+    nb = _lib.fn("fhvae_lstm_wave_pack_bytes")(H, L, mode)
+    assert nb == (16 * L + (16 if L == 2 else 0)) * (2 if mode == 1 else 1) * 65536
+    buf = torch.zeros(nb // 4, device=DEV)
+    call("fhvae_lstm_wave_pack", ptr(W0), ptr(Wi1) if Wi1 is not None else None, ptr(W1) if W1 is not None else None,
+         ptr(buf), H, L, mode)
+    return buf
+
+
 @pytest.mark.parametrize("mode", [1, 2])
 @pytest.mark.parametrize("T,B,L,repeat", [(1, 32, 1, 1), (3, 64, 2, 2), (20, 256, 1, 2), (20, 256, 2, 3), (7, 320, 2, 1),
                                            (20, 608, 1, 1)])
@@ -303,8 +312,11 @@ def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
     out2 = [[f(T, B, H), f(T, B, H), f(T, B, 4 * H)] for _ in range(2)]
     hp = [torch.zeros(2, T * B * H, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
     l1 = [ptr(Wi1), ptr(b1), ptr(W1), ptr(out2[1][0]), ptr(out2[1][1]), ptr(out2[1][2])] if L == 2 else [None] * 6
+    # ... and with the weights taken from the pre-packed operand images (fhvae_lstm_wave_pack) instead of being
+    # converted in the kernel: same arithmetic, so still bit-identical
+    packed = _wave_packed(W0, Wi1 if L == 2 else None, W1 if L == 2 else None, H, L, mode)
     call("fhvae_lstm_wave_fwd_planes", ptr(P), ptr(Q), ptr(W0), ptr(out2[0][0]), ptr(out2[0][1]), ptr(out2[0][2]), *l1,
-         ptr(xchg), hp[0].data_ptr(), hp[1].data_ptr() if L == 2 else None, T * B * H, T, B, H, L, mode)
+         ptr(xchg), hp[0].data_ptr(), hp[1].data_ptr() if L == 2 else None, T * B * H, ptr(packed), T, B, H, L, mode)
     torch.cuda.synchronize()
     for l in range(L):
         assert torch.equal(out2[l][0], out[l][0]) and torch.equal(out2[l][2], out[l][2])
@@ -365,9 +377,10 @@ def test_lstm_wave_bwd_matches_simt(T, B, L, use_all, use_last, repeat, mode):
     dgp = [torch.zeros(2, T * B * 4 * H, dtype=torch.bfloat16, device=DEV) for _ in range(2)]
     dgs2 = [f(B, 4 * H), f(B, 4 * H)]
     bot = ([ptr(Wi1), ptr(W0), ptr(st[0][1]), ptr(st[0][2]), None, ptr(dgs2[0])] if L == 2 else [None] * 6)
+    packed = _wave_packed(W0, Wi1 if L == 2 else None, W1 if L == 2 else None, H, L, mode)   # pre-packed weight operands
     call("fhvae_lstm_wave_bwd_planes", pa, pl, ptr(dh_last0) if L == 2 else None, ptr(Wtop), ptr(st[top][1]),
          ptr(st[top][2]), None, ptr(dgs2[top]), *bot, ptr(xchg), dgp[top].data_ptr(),
-         dgp[0].data_ptr() if L == 2 else None, T * B * 4 * H, T, B, H, L, mode)
+         dgp[0].data_ptr() if L == 2 else None, T * B * 4 * H, ptr(packed), T, B, H, L, mode)
     torch.cuda.synchronize()
     for l in range(L):
         hi = dg[l].reshape(-1).to(torch.bfloat16)

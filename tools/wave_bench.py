@@ -14,6 +14,7 @@ import torch
 T, B, H, L = 20, 256, 256, 2
 REPS = 10
 STRESS = 0
+PACK = True
 
 
 def vp(t, off=0):
@@ -48,6 +49,7 @@ def graph_us(fn):
 
 
 def run(lib, mode, timeline=False):
+    NEWABI = hasattr(lib, "fhvae_lstm_wave_pack")
     g = torch.Generator(device="cuda").manual_seed(0)
     z = lambda *s, sc=0.3: torch.randn(*s, device="cuda", generator=g) * sc
     P, Q = z(T, B, 4 * H), z(B, 4 * H)
@@ -55,13 +57,21 @@ def run(lib, mode, timeline=False):
     f = lambda *s: torch.zeros(*s, device="cuda")
     h, c, a = [f(T, B, H), f(T, B, H)], [f(T, B, H), f(T, B, H)], [f(T, B, 4 * H), f(T, B, 4 * H)]
     hp = [torch.zeros(2, T * B * H, dtype=torch.bfloat16, device="cuda") for _ in range(2)]
+    packed = None
+    if PACK and hasattr(lib, "fhvae_lstm_wave_pack"):
+        lib.fhvae_lstm_wave_pack_bytes.restype = ctypes.c_longlong
+        packed = torch.zeros(lib.fhvae_lstm_wave_pack_bytes(H, L, mode) // 4, device="cuda")
+        assert lib.fhvae_lstm_wave_pack(vp(W0), vp(Wi1), vp(W1), vp(packed), H, L, mode, None) == 0
+        t_pack = graph_us(lambda st: lib.fhvae_lstm_wave_pack(vp(W0), vp(Wi1), vp(W1), vp(packed), H, L, mode, ctypes.c_void_p(st)))
+        print(f"     pack kernel {t_pack:.1f} us", flush=True)
     xf = torch.zeros(lib.fhvae_lstm_wave_xchg_bytes(T, B, H, L) // 4, device="cuda")
     xb = torch.zeros(lib.fhvae_lstm_wave_bwd_xchg_bytes(T, B, H, L) // 4, device="cuda")
 
     def fwd(st):
         r = lib.fhvae_lstm_wave_fwd_planes(vp(P), vp(Q), vp(W0), vp(h[0]), vp(c[0]), vp(a[0]), vp(Wi1), vp(b1), vp(W1),
                                            vp(h[1]), vp(c[1]), vp(a[1]), vp(xf), vp(hp[0]), vp(hp[1]),
-                                           ctypes.c_longlong(T * B * H), T, B, H, L, mode, ctypes.c_void_p(st))
+                                           ctypes.c_longlong(T * B * H), *([vp(packed)] if NEWABI else []), T, B, H, L, mode,
+                                           ctypes.c_void_p(st))
         assert r == 0, lib.fhvae_last_error_string()
     t_f = graph_us(fwd)
     dh_all, dhl1, dhl0 = z(T, B, H), z(B, H), z(B, H)
@@ -71,8 +81,8 @@ def run(lib, mode, timeline=False):
     def bwd(st):
         r = lib.fhvae_lstm_wave_bwd_planes(vp(dh_all), vp(dhl1), vp(dhl0), vp(W1), vp(c[1]), vp(a[1]), None, vp(dgs[1]),
                                            vp(Wi1), vp(W0), vp(c[0]), vp(a[0]), None, vp(dgs[0]), vp(xb), vp(dgp[1]),
-                                           vp(dgp[0]), ctypes.c_longlong(T * B * 4 * H), T, B, H, L, mode,
-                                           ctypes.c_void_p(st))
+                                           vp(dgp[0]), ctypes.c_longlong(T * B * 4 * H), *([vp(packed)] if NEWABI else []),
+                                           T, B, H, L, mode, ctypes.c_void_p(st))
         assert r == 0, lib.fhvae_last_error_string()
     t_b = graph_us(bwd)
     outs = h + c + a + hp + dgp + dgs
@@ -111,7 +121,8 @@ def main():
         if a.startswith("--modes"):
             modes = [int(v) for v in a.split("=")[1].split(",")]
     timeline = "--timeline" in sys.argv
-    global STRESS
+    global STRESS, PACK
+    PACK = "--no-pack" not in sys.argv
     for a in sys.argv[1:]:
         if a.startswith("--stress"):
             STRESS = int(a.split("=")[1])
@@ -131,6 +142,15 @@ def main():
                   + (f"   h0 vs fp32 SIMT {ref:.1e}" if ref is not None else ""), flush=True)
             if tl:
                 for layer in range(2):
+                    tops = [tl[layer][t][0] for t in range(T + 1)]
+                    print(f"     L{layer} periods: " + " ".join(str(tops[t + 1] - tops[t]) for t in range(T - 1 if layer else T))
+                          + f" | total {tops[T - 1 if layer else T] - tops[0]}")
+                    e = tl[layer]
+                    print(f"     L{layer}: entry->prologue done {e[1][15] - e[0][15]}  prologue done->loop end {e[2][15] - e[1][15]}  "
+                          f"first top - entry {tops[0] - e[0][15]}")
+                    if e[3][15]:
+                      print(f"        prologue: alloc+sync {e[3][15] - e[0][15]}  reg_inc {e[4][15] - e[3][15]}  W_hh->TMEM {e[5][15] - e[4][15]}  "
+                          f"W_ih1->smem {e[6][15] - e[5][15]}  sync {e[7][15] - e[6][15]}  Q {e[1][15] - e[7][15]}")
                     for t in range(9, 12):
                         r = tl[layer][t]
                         print(f"     L{layer} t{t}: loads_issued {r[6] - r[0]} waited+stored {r[7] - r[6]} pull_total {r[1] - r[0]} "
