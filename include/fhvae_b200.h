@@ -182,6 +182,22 @@ int fhvae_disc_bwd_finish(const float* z2mu, int64_t ld_z, const float* mu2, con
                           int nparts, const float* g, float* dz2mu, int64_t ld_dz, float* dmu2,
                           int B, int Z, void* stream);
 
+/* Sharded table (north star: "the mu2 table is sharded by utterance id with row gradients routed to their owner";
+ * row u lives on rank u mod W at local row u / W).  The softmax of simple_fhvae.py:119-122 runs over ALL rows, so
+ * per step every rank scores all B_global segments against its rows with the kernels above (B = B_global, table =
+ * the local shard) and the partials meet in fhvae_disc_combine_sharded.  Helpers of that exchange:
+ *   shard_pack:   packet (B, Z+4) rows [z2_mu | mu_idx as two 32-bit words | g = dL/dlog_qy | pad] -- one all-gather
+ *   shard_unpack: gathered packets (Bg rows) -> idx_g (may be NULL), lidx_g = local row on THIS rank or -1, g_g;
+ *                 ids < 0 or beyond the shard OR FHVAE_FLAG_BAD_INDEX into *err_flag (may be NULL)
+ *   combine:      part (nparts = W*nsplit, Bg, 2) in rank-major order -> lse_g (Bg,) bit-identical on every rank,
+ *                 log_qy (B_local,) = tgt - lse for this rank's segments [b_off, b_off + B_local). */
+int fhvae_shard_pack(const float* z2mu, int64_t ld_z, const int64_t* idx, const float* g, float* packet, int B, int Z,
+                     void* stream);
+int fhvae_shard_unpack(const float* packet, int Bg, int Z, int world, int rank, int64_t N_local, int64_t* idx_g,
+                       int64_t* lidx_g, float* g_g, int32_t* err_flag, void* stream);
+int fhvae_disc_combine_sharded(const float* part, int nparts, int Bg, const float* tgt, int b_off, int B_local,
+                               float* log_qy, float* lse_g, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * K0: mu2 table (simple_fhvae.py:39-54).  Exact int64 indexing; deterministic reductions.
  * ------------------------------------------------------------------------------------------- */

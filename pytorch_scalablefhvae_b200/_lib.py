@@ -77,6 +77,9 @@ PROTOTYPES = {
     "fhvae_disc_bwd_rows": [_p, _l, _p, _l, _i, _p, _p, _p, _i, _p],
     "fhvae_disc_bwd_segs": [_p, _l, _p, _l, _i, _p, _p, _i, _i, _p],
     "fhvae_disc_bwd_finish": [_p, _l, _p, _p, _i, _p, _p, _l, _p, _i, _i, _p],
+    "fhvae_shard_pack": [_p, _l, _p, _p, _p, _i, _i, _p],
+    "fhvae_shard_unpack": [_p, _i, _i, _i, _i, _l, _p, _p, _p, _p, _p],
+    "fhvae_disc_combine_sharded": [_p, _i, _i, _p, _i, _i, _p, _p, _p],
     "fhvae_mu2_gather": [_p, _p, _p, _i, _i, _l, _p, _p],
     "fhvae_mu2_scatter_reduce": [_p, _p, _p, _p, _i, _i, _l, _p],
     "fhvae_mu2_accumulate": [_p, _l, _p, _p, _p, _i, _i, _l, _p, _p],

@@ -245,6 +245,66 @@ __global__ void disc_bwd_finish_kernel(const float* __restrict__ z2mu, int64_t l
     dmu2[i] += gb * (z - my);
 }
 
+// ---- sharded table (row u lives on rank u mod W at local row u / W): per-step exchange helpers -----------
+// One packet row per segment: [z2_mu (Z floats) | mu_idx (int64, 2 floats) | g = dL/dlog_qy | pad] -- ONE all-gather
+// per step carries everything the other ranks need to score this rank's segments against their rows.
+__global__ void shard_pack_kernel(const float* __restrict__ z2mu, int64_t ld_z, const int64_t* __restrict__ idx,
+                                  const float* __restrict__ g, float* __restrict__ packet, int B, int Z) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int ld = Z + 4;
+    if (i >= B * ld) return;
+    const int b = i / ld, d = i % ld;
+    float v = 0.f;
+    if (d < Z) v = z2mu[(int64_t)b * ld_z + d];
+    else if (d == Z) v = __int_as_float((int)(uint32_t)(idx[b] & 0xffffffffll));
+    else if (d == Z + 1) v = __int_as_float((int)(uint32_t)((uint64_t)idx[b] >> 32));
+    else if (d == Z + 2) v = g[b];
+    packet[i] = v;
+}
+// gathered packets (Bg rows) -> local row of every global segment's utterance on THIS rank (-1: owned elsewhere),
+// the raw ids and the contiguous g vector.  Exact int64 arithmetic.
+__global__ void shard_unpack_kernel(const float* __restrict__ packet, int Bg, int Z, int world, int rank, int64_t N_local,
+                                    int64_t* __restrict__ idx_g, int64_t* __restrict__ lidx_g, float* __restrict__ g_g,
+                                    int32_t* __restrict__ err_flag) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bg) return;
+    const float* row = packet + (int64_t)b * (Z + 4);
+    const uint64_t lo = (uint32_t)__float_as_int(row[Z]), hi = (uint32_t)__float_as_int(row[Z + 1]);
+    const int64_t u = (int64_t)(lo | (hi << 32));
+    int64_t l = -1;
+    if (u >= 0 && (u % world) == rank) {
+        l = u / world;
+        if (l >= N_local) {                       // beyond the table: same treatment as fhvae_mu2_gather
+            l = -1;
+            if (err_flag) atomicOr(err_flag, FHVAE_FLAG_BAD_INDEX);
+        }
+    } else if (u < 0 && err_flag) {
+        atomicOr(err_flag, FHVAE_FLAG_BAD_INDEX);
+    }
+    if (idx_g) idx_g[b] = u;
+    lidx_g[b] = l;
+    g_g[b] = row[Z + 2];
+}
+// (max, sumexp) partials of every rank and N-split, combined in FIXED (rank-major) order for ALL global segments --
+// every rank computes bit-identical lse_g -- plus log q of this rank's own segments [b_off, b_off + B_local).
+__global__ void disc_combine_sharded_kernel(const float* __restrict__ part, int nparts, int Bg,
+                                            const float* __restrict__ tgt, int b_off, int B_local,
+                                            float* __restrict__ log_qy, float* __restrict__ lse_g) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= Bg) return;
+    float M = -INFINITY;
+    for (int i = 0; i < nparts; ++i) M = fmaxf(M, part[((int64_t)i * Bg + b) * 2]);
+    float S = 0.f;
+    for (int i = 0; i < nparts; ++i) {
+        const float m = part[((int64_t)i * Bg + b) * 2], s = part[((int64_t)i * Bg + b) * 2 + 1];
+        if (m != -INFINITY) S += s * expf(m - M);
+    }
+    const float L = M + logf(S);
+    lse_g[b] = L;
+    const int bl = b - b_off;
+    if (bl >= 0 && bl < B_local) log_qy[bl] = tgt[bl] - L;
+}
+
 static int64_t rows_per_split(int64_t N, int nsplit) {
     int64_t r = (N + nsplit - 1) / nsplit;
     return (r + D_ROWS - 1) / D_ROWS * D_ROWS;
@@ -333,5 +393,34 @@ extern "C" int fhvae_disc_bwd_finish(const float* z2mu, int64_t ld_z, const floa
     disc_bwd_finish_kernel<<<cdiv((int64_t)B * Z, 256), 256, 0, as_stream(stream)>>>(
         z2mu, ld_z, mu2, sumpm_part, nparts, g, dz2mu, ld_dz, dmu2, B, Z);
     FHVAE_LAUNCH_CHECK("disc_bwd_finish");
+    return 0;
+}
+
+
+extern "C" int fhvae_shard_pack(const float* z2mu, int64_t ld_z, const int64_t* idx, const float* g, float* packet,
+                                int B, int Z, void* stream) {
+    FHVAE_CHECK_ARG(z2mu && idx && g && packet && B > 0 && Z > 0, "shard_pack: bad argument");
+    shard_pack_kernel<<<cdiv((int64_t)B * (Z + 4), 256), 256, 0, as_stream(stream)>>>(z2mu, ld_z, idx, g, packet, B, Z);
+    FHVAE_LAUNCH_CHECK("shard_pack");
+    return 0;
+}
+
+extern "C" int fhvae_shard_unpack(const float* packet, int Bg, int Z, int world, int rank, int64_t N_local,
+                                  int64_t* idx_g, int64_t* lidx_g, float* g_g, int32_t* err_flag, void* stream) {
+    FHVAE_CHECK_ARG(packet && lidx_g && g_g && Bg > 0 && Z > 0 && world > 0 && rank >= 0 && rank < world && N_local >= 0,
+                    "shard_unpack: bad argument");
+    shard_unpack_kernel<<<cdiv(Bg, 256), 256, 0, as_stream(stream)>>>(packet, Bg, Z, world, rank, N_local, idx_g, lidx_g,
+                                                                      g_g, err_flag);
+    FHVAE_LAUNCH_CHECK("shard_unpack");
+    return 0;
+}
+
+extern "C" int fhvae_disc_combine_sharded(const float* part, int nparts, int Bg, const float* tgt, int b_off,
+                                          int B_local, float* log_qy, float* lse_g, void* stream) {
+    FHVAE_CHECK_ARG(part && tgt && log_qy && lse_g && nparts > 0 && Bg > 0 && b_off >= 0 && B_local > 0 &&
+                        b_off + B_local <= Bg, "disc_combine_sharded: bad argument");
+    disc_combine_sharded_kernel<<<cdiv(Bg, 128), 128, 0, as_stream(stream)>>>(part, nparts, Bg, tgt, b_off, B_local,
+                                                                              log_qy, lse_g);
+    FHVAE_LAUNCH_CHECK("disc_combine_sharded");
     return 0;
 }

@@ -225,7 +225,7 @@ class _FHVAECore(nn.Module):
             log_qy = -log_qy.mean()
         return lb, log_qy, log_px_z, nk1, nk2, log_pmu2
 
-    def train_step(self, x, mu_idx, num_segs, optimizer, alpha: float = 10.0, eps=None, allreduce=None):
+    def train_step(self, x, mu_idx, num_segs, optimizer, alpha: float = 10.0, eps=None, allreduce=None, shard=None):
         """Fused loop body of train_model.py:446-454: forward, loss = -mean(lb + alpha*log_qy)
         (train_model.py:243-251), backward, Adam -- one replayed launch sequence (one CUDA graph when
         ``use_cuda_graphs`` and no collective is interposed).  ``allreduce(flat_grads)`` is called
@@ -233,9 +233,12 @@ class _FHVAECore(nn.Module):
         if not x.is_cuda and not x.is_pinned():
             raise RuntimeError("train_step takes a CUDA or pinned-host batch (no CPU path)")
         B, T, F = x.shape
-        self._check_ids(mu_idx, num_segs, B, self.mu2_table.shape[0])
+        # with a sharded table (parallel.DataParallel(table="sharded")) mu_idx are GLOBAL row ids in [0, num_rows)
+        self._check_ids(mu_idx, num_segs, B, shard.num_rows if shard is not None else self.mu2_table.shape[0])
         plan = self._plan(B, T, F)
         plan.load_inputs(x, mu_idx, num_segs, eps)
+        if shard is not None:
+            return plan.run_train_step_sharded(optimizer, float(alpha), shard)
         return plan.run_train_step(optimizer, float(alpha), allreduce)
 
     @staticmethod
@@ -536,6 +539,176 @@ class _Plan:
             if g2 is not None:
                 allreduce(gflat)
                 g2.replay()
+        return self.loss
+
+    # ------------------------------------------------------------------ sharded mu2 table
+    _DISC_FWD = ("fhvae_mu2_gather", "fhvae_disc_fwd_partial", "fhvae_disc_target", "fhvae_disc_combine")
+    _DISC_BWD = ("fhvae_disc_bwd_segs", "fhvae_disc_bwd_rows", "fhvae_disc_bwd_finish", "fhvae_mu2_scatter_reduce")
+
+    def _sharded_segments(self, k):
+        """The train-step call lists cut where the discriminative chain meets the collectives:
+        S1 forward up to the z2 posterior | S2 rest of the forward | S3 ELBO forward+backward seam | S4 backward
+        down to the z2 head | S5 z2 head + z2 encoder backward.  The replicated-table kernels of the discriminative
+        chain are dropped (run_train_step_sharded drives their sharded counterparts between the segments)."""
+        cache = self.__dict__.setdefault("_shard_seg_cache", {})
+        if k in cache:
+            return cache[k]
+        fwd, bwd = self._train_lists(k)
+        nf = [c_[1] for c_ in fwd.calls]
+        nb = [c_[1] for c_ in bwd.calls]
+        iA = nf.index("fhvae_mu2_gather")
+        assert tuple(nf[iA:iA + 4]) == self._DISC_FWD and nf[-1] in ("fhvae_elbo_fwd_bwd", "fhvae_elbo_fwd")
+        fused = nf[-1] == "fhvae_elbo_fwd_bwd"
+        jD = max(i for i, c_ in enumerate(bwd.calls) if c_[1] == "join" and c_[2] == 2)
+        head = 0 if fused else 2                       # unfused: [step_coef, elbo_bwd] open the backward list
+        assert set(nb[head:head + 4]) == set(self._DISC_BWD), nb[:8]
+
+        def seg(calls, keep):
+            cl = CallList()
+            cl.calls, cl.keep = list(calls), keep
+            return cl
+        s1 = seg(fwd.calls[:iA], fwd.keep)
+        s2 = seg(fwd.calls[iA + 4:-1], fwd.keep)
+        s3 = seg([fwd.calls[-1]] + (bwd.calls[:2] if not fused else []), fwd.keep + bwd.keep)
+        s4 = seg(bwd.calls[head + 4:jD], bwd.keep)
+        s5 = seg(bwd.calls[jD + 1:], bwd.keep)
+        cache[k] = (s1, s2, s3, s4, s5)
+        return cache[k]
+
+    def run_train_step_sharded(self, optimizer, alpha, dp):
+        """One train step with the mu2 table sharded by row id over the ranks of ``dp`` (parallel.DataParallel):
+        the model's ``mu2_table`` parameter holds rows ``rank, rank+W, ...``; ``self.idx`` are GLOBAL row ids.
+        Exchange per step: all-gather (z2_mu, idx, g) | owner-served mu2 rows by reduce-scatter |
+        all-gather of the (max, sumexp) partials -> rank-ordered LSE | all-to-all of the sum_n p_bn m_n partials |
+        all-gather of the sparse row gradients, scatter-reduced by the owner in ascending global segment order |
+        all-reduce of the dense gradient prefix.  The dense softmax part of d table stays owner-local."""
+        m = self.m
+        k = 0
+        gflat = m._grad_buffer(k)
+        if self.bwd[k] is None:
+            self.bwd[k] = self._build_bwd(gflat)
+        B, Z, W, rank = self.B, self.Z2, dp.world, dp.rank
+        Bg = B * W
+        if not hasattr(self, "loss"):
+            self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        if self.__dict__.get("_gout_train") != (alpha, B):
+            self.gout.zero_()
+            self.gout[0].fill_(-1.0 / B)
+            self.gout[5].fill_(-alpha / B)
+            self._gout_train = (alpha, B)
+            self._gout_rows = None
+        sh = self.__dict__.get("_shard")
+        n_alloc = m.mu2_table.shape[0]
+        if sh is None or sh["key"] != (W, rank, dp.n_local):
+            f = self.f
+            ns = _lib.fn("fhvae_disc_nsplit")(Bg, n_alloc)
+            i64 = lambda n: torch.zeros(n, dtype=torch.int64, device=self.dev)
+            sh = self._shard = dict(
+                key=(W, rank, dp.n_local), ns=ns, packet=f(B, Z + 4), packet_g=f(Bg, Z + 4), lidx_g=i64(Bg), g_g=f(Bg),
+                mu2_send=f(Bg, Z), part=f(ns, Bg, 2), part_all=f(W * ns, Bg, 2), lse_g=f(Bg), sumpm=f(ns, Bg, Z),
+                sumpm_send=f(W, ns, B, Z), sumpm_recv=f(W * ns, B, Z), dmu2_g=f(Bg, Z),
+                touched_g=torch.zeros(Bg, dtype=torch.int32, device=self.dev),
+                stream=torch.cuda.Stream(), graphs={})
+            self.touched_global = sh["touched_g"]
+        ns = sh["ns"]
+        segs = self._sharded_segments(k)
+        lc = CallList()
+        lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss))
+        if not hasattr(self, "coef"):
+            raise RuntimeError("backward list not built")
+        N_local = dp.n_local
+        tab = ptr(m.mu2_table)
+        dtab = ptr(gflat, m._off["mu2_table"])
+        pk, pkg, ld = ptr(sh["packet"]), ptr(sh["packet_g"]), Z + 4
+        z2h, ldz = ptr(self.z2head), 2 * Z
+        g_loc = ptr(self.gout, 5 * B)
+        call = lambda name, *a: _lib.check(_lib.fn(name)(*a, current_stream_ptr()), name)
+
+        def run_seg(i, extra=None):
+            if not segs[i].calls and extra is None:
+                return
+
+            def body():
+                segs[i].run(current_stream_ptr())
+                if extra is not None:
+                    extra.run(current_stream_ptr())
+            # The first step runs eagerly (module loading / function attributes must not happen inside a capture, and a
+            # warm-up replay of ONE segment would double-apply its accumulating kernels); from the second step on
+            # each segment is captured once, without a warm-up run, and replayed.
+            if not m.use_cuda_graphs or not sh.get("warm"):
+                return body()
+            key = ("seg", i, alpha)
+            if key not in sh["graphs"]:
+                s_ = torch.cuda.Stream(priority=-1)
+                s_.wait_stream(torch.cuda.current_stream())
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=s_):
+                    body()
+                sh["graphs"][key] = g_
+            sh["graphs"][key].replay()
+
+        main, D = torch.cuda.current_stream(), sh["stream"]
+        ev = lambda s: (lambda e: (e.record(s), e)[1])(torch.cuda.Event())
+
+        run_seg(0)                                                   # ... z2 posterior
+        eA = ev(main)
+        with torch.cuda.stream(D):
+            D.wait_event(eA)
+            call("fhvae_shard_pack", z2h, ldz, ptr(self.idx), g_loc, pk, B, Z)
+            dp.all_gather(sh["packet_g"], sh["packet"])
+            call("fhvae_shard_unpack", pkg, Bg, Z, W, rank, N_local, None, ptr(sh["lidx_g"]), ptr(sh["g_g"]),
+                 ptr(self.nan_flag))
+            # owners serve the mu2 rows of ALL global segments; exactly one rank contributes a non-zero row
+            sh["mu2_send"].zero_()
+            call("fhvae_rows_copy", tab, ptr(sh["lidx_g"]), ptr(sh["mu2_send"]), None, Bg, Z)
+            dp.reduce_scatter(self.mu2, sh["mu2_send"])
+            if N_local > 0:
+                call("fhvae_disc_fwd_partial", pkg, ld, tab, N_local, Z, ptr(sh["part"]), ns, Bg)
+            else:
+                sh["part"][..., 0].fill_(float("-inf")); sh["part"][..., 1].zero_()
+            dp.all_gather(sh["part_all"], sh["part"])
+            call("fhvae_disc_target", z2h, ldz, ptr(self.mu2), ptr(self.tgt), B, Z)
+            call("fhvae_disc_combine_sharded", ptr(sh["part_all"]), W * ns, Bg, ptr(self.tgt), rank * B, B,
+                 ptr(self.out, 5 * B), ptr(sh["lse_g"]))
+            eB = ev(D)
+            # backward pieces that only need (z2_mu, lse, g) of all segments: dense d table (owner-local), sum_n p_bn m_n
+            if N_local > 0:
+                call("fhvae_disc_bwd_rows", pkg, ld, tab, N_local, Z, ptr(sh["lse_g"]), ptr(sh["g_g"]), dtab, Bg)
+                call("fhvae_disc_bwd_segs", pkg, ld, tab, N_local, Z, ptr(sh["lse_g"]), ptr(sh["sumpm"]), ns, Bg)
+            else:
+                sh["sumpm"].zero_()
+            sh["sumpm_send"].copy_(sh["sumpm"].view(ns, W, B, Z).permute(1, 0, 2, 3))
+            dp.all_to_all(sh["sumpm_recv"].view(W, ns, B, Z), sh["sumpm_send"])
+        run_seg(1)                                                   # z1 encoder, decoder (beside the exchange)
+        main.wait_event(eB)                                          # mu2 rows + log q(i|z2)
+        run_seg(2, lc)                                               # ELBO forward/backward seam, loss
+        eC = ev(main)
+        with torch.cuda.stream(D):
+            D.wait_event(eC)                                         # dz2head / dmu2 hold the ELBO part
+            call("fhvae_disc_bwd_finish", z2h, ldz, ptr(self.mu2), ptr(sh["sumpm_recv"]), W * ns, g_loc,
+                 ptr(self.dz2head), ldz, ptr(self.dmu2), B, Z)
+            dp.all_gather(sh["dmu2_g"], self.dmu2)
+            # sparse rows (KL + prior + target parts): the owner adds them in ascending GLOBAL segment order
+            call("fhvae_mu2_scatter_reduce", ptr(sh["dmu2_g"]), ptr(sh["lidx_g"]), dtab, ptr(sh["touched_g"]), Bg, Z,
+                 max(N_local, 1))
+            eD = ev(D)
+        run_seg(3)                                                   # decoder + z1 encoder backward
+        main.wait_event(eD)
+        run_seg(4)                                                   # z2 head + z2 encoder backward
+        dense = gflat[:m._off["mu2_table"]]
+        dp.allreduce_(dense)                                         # the table gradient stays with its owner
+
+        def adam():
+            optimizer.step_flat(m, gflat)
+        if not m.use_cuda_graphs:
+            adam()
+        else:
+            key = ("adam", id(optimizer), optimizer.hyper_key())
+            if key not in sh["graphs"]:
+                optimizer._state_for(m)
+                sh["graphs"][key] = self._capture(adam, restore=optimizer)
+            sh["graphs"][key].replay()
+        sh["warm"] = True
         return self.loss
 
     def _train_lists(self, k):

@@ -63,8 +63,51 @@ def main():
     assert torch.equal(again.cpu(), full[utts] * 2.0)
     other = torch.tensor([u for u in range(Nm) if u not in set(utts.tolist())][:50])
     assert torch.equal(table.fetch(other).cpu(), full[other]), "rows outside the sample stay untouched"
+    # ---- mu2 table SHARDED inside the train step (row u on rank u mod W): W-rank step == 1-GPU full-table step on
+    # the concatenated batch -- losses / dense parameters 1e-4, assembled table rows 1e-4, touched-row sets bit-exact
+    from pytorch_scalablefhvae_b200.parallel import shard_alloc_rows, owner_of
+    Nrows = 203                                                    # uneven shards
+    torch.manual_seed(1)
+    full = P.FHVAE(*args, seg_len=T, num_seqs=Nrows, gemm_mode=mode, use_cuda_graphs=True).to(dev)
+    fopt = P.FusedAdam(full.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    torch.manual_seed(1)
+    sm = P.FHVAE(*args, seg_len=T, num_seqs=shard_alloc_rows(Nrows, world), gemm_mode=mode, use_cuda_graphs=True).to(dev)
+    sopt = P.FusedAdam(sm.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    sdp = DataParallel(sm, sopt, table="sharded", num_rows=Nrows)
+    sdp.shard_table_(full.mu2_table.detach())
+    worst_s = 0.0
+    for step in range(3):
+        x, idx, nsegs = synth_batch(Bl * world, T, F, Nrows, seed=70 + step)
+        g = torch.Generator().manual_seed(10 + step)
+        eps = {"z1": torch.randn(Bl * world, Z, generator=g), "z2": torch.randn(Bl * world, Z, generator=g)}
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        l_s = sdp.train_step(x[sl].to(dev), idx[sl].to(dev), nsegs[sl].to(dev), 10.0, eps={k: v[sl] for k, v in eps.items()})
+        l_f = full.train_step(x.to(dev), idx.to(dev), nsegs.to(dev), fopt, 10.0, eps=eps)
+        worst_s = max(worst_s, abs(float(sdp.global_mean(l_s)) - float(l_f)) / abs(float(l_f)))
+        # touched rows: this rank's flags == first occurrences (in global segment order) of the rows it owns
+        first, seen = torch.zeros(Bl * world, dtype=torch.int32), set()
+        for b, r in enumerate(idx.tolist()):
+            if r not in seen and r % world == rank:
+                first[b] = 1
+            seen.add(r)
+        assert torch.equal(sm._plan(Bl, T, F).touched_global.cpu(), first), "touched-row set"
+    assert worst_s < 1e-4, worst_s
+    sm.check_flags()
+    tab = sdp.gather_table()
+    d = (tab - full.mu2_table.detach()).abs()
+    assert float(d.max()) <= 2 * 3 * 1e-3 and float((d <= 1e-4 * float(full.mu2_table.abs().max())).float().mean()) >= 0.999
+    for (k, p), (_, q) in zip(sm.named_parameters(), full.named_parameters()):
+        if k == "mu2_table":
+            continue
+        d = float((p - q).abs().max())
+        assert d <= 2 * 3 * 1e-3, (k, d)
+        frac = float(((p - q).abs() <= 1e-4 * float(q.abs().max())).float().mean())
+        assert frac >= 0.999, (k, frac)
+    dense = sm._flat[:sm._off["mu2_table"]].clone()
+    dist.broadcast(dense, src=0)
+    assert torch.equal(dense, sm._flat[:sm._off["mu2_table"]]), "dense replicas must stay bit-identical"
     if rank == 0:
-        print(f"mp_check ok: world {world}, loss rel err {worst:.2e}")
+        print(f"mp_check ok: world {world}, loss rel err {worst:.2e}, sharded-table loss rel err {worst_s:.2e}")
     dist.destroy_process_group()
 
 

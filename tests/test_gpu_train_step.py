@@ -236,3 +236,46 @@ def test_lr_change_recaptures_train_graph():
     _check_params(m, o, 4)
     with pytest.raises(ValueError):
         P.FusedAdam([{"params": list(m.parameters())[:3]}, {"params": list(m.parameters())[3:]}])
+
+
+@pytest.mark.parametrize("name,mode,graphs", [("fhvae_c1", P.MODE_BF16X3, True), ("fhvae_small", P.MODE_F32_SIMT, False),
+                                              ("simple_c0", P.MODE_F32_SIMT, True)])
+def test_sharded_table_step_world1_matches_oracle(name, mode, graphs):
+    """parallel.DataParallel(table="sharded") without a process group: every collective is a copy, so the WHOLE
+    sharded-table step (packet, owner-served rows, partial LSE, rank-ordered combine, sum_n p_bn m_n exchange, owner
+    scatter of the sparse rows, segment-wise graphs) runs on one GPU and must reproduce the oracle's full-table step."""
+    from pytorch_scalablefhvae_b200.parallel import DataParallel
+    cfg = CFGS[name]
+    m, o = _pair(cfg["kind"], cfg, gemm_mode=mode, use_cuda_graphs=graphs)
+    r, _ = _pair(cfg["kind"], cfg, gemm_mode=mode, use_cuda_graphs=graphs)     # same weights, replicated-table step
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    ropt = P.FusedAdam(r.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    oopt = O.make_adam(o.parameters())
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    dp = DataParallel(m, opt, table="sharded", num_rows=N)
+    for step in range(3):
+        x, idx, nsegs = synth_batch(B, T, F, N, seed=100 + step)
+        eps = _eps(B, m.z1_dim, m.z2_dim, seed=step)
+        loss = dp.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), 10.0, eps=eps)
+        rloss = r.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), ropt, 10.0, eps=eps)
+        ol, rout = O.train_step(o, oopt, x, idx, N, nsegs, 10.0, eps=eps)
+        assert_close(loss, ol, FP32_RTOL, f"{name}: loss vs oracle, step {step}")
+        plan, rplan = m._plan(B, T, F), r._plan(B, T, F)
+        if step == 0:
+            assert_close(plan.out[5], rout[1], FP32_RTOL, f"{name}: log_qy vs oracle")
+        # against the replicated-table step of the same kernels: only summation order differs
+        assert_close(loss, rloss, 1e-6, f"{name}: loss vs replicated, step {step}")
+        assert_close(plan.out, rplan.out, 2e-5, f"{name}: ELBO rows + log_qy vs replicated, step {step}")
+        gs, gr = m._grad_buffer(0), r._grad_buffer(0)
+        o_t = m._off["mu2_table"]
+        assert_close(gs[o_t:], gr[o_t:], 2e-5, f"{name}: d table vs replicated, step {step}")
+        # rows touched by the sparse part == distinct utterances, flagged at their first occurrence (bit-exact)
+        first, seen = torch.zeros(B, dtype=torch.int32), set()
+        for b, row in enumerate(idx.tolist()):
+            if row not in seen:
+                first[b] = 1
+                seen.add(row)
+        assert torch.equal(plan.touched_global.cpu(), first)
+        assert torch.equal(plan.touched_global, rplan.touched)
+    m.check_flags()
+    _check_params(m, o, 3, what=f"{name} sharded(W=1): ")
