@@ -4,10 +4,12 @@ from . import _lib
 from ._lib import MODE_BF16, MODE_BF16X3, MODE_F32_SIMT, build
 from .model import FHVAE, SimpleFHVAE, loss_function
 from .optim import FusedAdam
-from .inference import extract_posteriors, segment_table
-from .hierarchical import ShardedMu2Table, sample_sequences
+from .inference import extract_posteriors, extract_posteriors_sharded, segment_table, shard_utterances
+from .hierarchical import HierarchicalTrainer, ShardedMu2Table, sample_sequences
+from .parallel import DataParallel, shard_alloc_rows
 from .checkpoint import load_checkpoint_file, save_checkpoint
 
 __all__ = ["FHVAE", "SimpleFHVAE", "FusedAdam", "loss_function", "build", "MODE_F32_SIMT", "MODE_BF16X3",
            "MODE_BF16", "extract_posteriors", "segment_table", "ShardedMu2Table", "sample_sequences",
-           "load_checkpoint_file", "save_checkpoint"]
+           "load_checkpoint_file", "save_checkpoint", "HierarchicalTrainer", "DataParallel", "shard_alloc_rows",
+           "extract_posteriors_sharded", "shard_utterances"]

@@ -19,7 +19,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .inference import R_MU2
-from .parallel import route_to_owners, shard_rows
+from .parallel import DataParallel, route_to_owners, shard_alloc_rows, shard_rows
 from .plan import current_stream_ptr, ptr
 
 
@@ -85,3 +85,68 @@ class ShardedMu2Table:
         _lib.check(_lib.fn("fhvae_mu2_estimate_finish")(ptr(zsum), ptr(cnt), ptr(table), R_MU2, K, Z,
                                                         current_stream_ptr()), "fhvae_mu2_estimate_finish")
         return table
+
+
+
+class HierarchicalTrainer:
+    """One ROUND of hierarchical sampling end to end (BASELINE config 3; what train_model.py:424-436 sketches):
+
+        sample K utterances (bit-exact np.random.choice) -> fetch their rows from the owners of the sharded master
+        table -> [refresh: MAP re-estimate with the current encoder] -> `steps` data-parallel train steps on segments
+        of those utterances, the ACTIVE K-row table sharded by label (label l on rank l mod W) inside the train step
+        -> write the trained rows back to their owners.
+
+    ``model`` must be built with ``num_seqs = shard_alloc_rows(K, world)``; ``master`` is a ShardedMu2Table over all
+    utterances.  Labels handed to ``train_step`` are positions in the sampled list (train_model.py:436)."""
+
+    def __init__(self, model, optimizer, master: ShardedMu2Table, k: int, group: Optional[dist.ProcessGroup] = None):
+        self.model, self.optimizer, self.master, self.k = model, optimizer, master, int(k)
+        self.dp = DataParallel(model, optimizer, group=group, table="sharded", num_rows=self.k)
+        self.utts: Optional[torch.Tensor] = None
+        self.rounds = 0
+
+    def begin_round(self, seed: int, refresh=None) -> torch.Tensor:
+        """Sample + fetch (+ refresh).  Returns the sampled utterance ids (K,) int64, identical on every rank.
+        ``refresh``: optional (x_batches, label_batches) of this rank's segments for the MAP re-estimate."""
+        ids = np.arange(self.master.num_utts)
+        sel = np.random.RandomState(seed).choice(ids, self.k, replace=False)      # train_model.py:426-428
+        self.utts = torch.from_numpy(sel.astype(np.int64))
+        cache = self.master.fetch(self.utts)                                      # (K, Z) identical on every rank
+        if refresh is not None:
+            cache = self._refresh(cache, *refresh)
+        self.dp.shard_table_(cache)                                               # active rows label::W on this rank
+        self.optimizer.reset_state(self.model, "mu2_table")
+        self.rounds += 1
+        return self.utts
+
+    @torch.no_grad()
+    def _refresh(self, cache, x_batches, label_batches):
+        K, Z = cache.shape
+        dev = cache.device
+        zsum, cnt = torch.zeros(K, Z, device=dev), torch.zeros(K, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        acc = _lib.fn("fhvae_mu2_accumulate")
+        for x, lab in zip(x_batches, label_batches):
+            enc = self.model.encode(x)
+            lab = lab.to(dev)
+            _lib.check(acc(ptr(enc["z2_mu"]), 2 * Z, ptr(lab), ptr(zsum), ptr(cnt), x.shape[0], Z, K, ptr(err),
+                           current_stream_ptr()), "fhvae_mu2_accumulate")
+        if int(err):
+            raise IndexError("refresh: a label is outside [0, K) of the sampled cache")
+        if self.dp.world > 1:
+            dist.all_reduce(zsum, group=self.dp.group)
+            dist.all_reduce(cnt, group=self.dp.group)
+        out = cache.clone()
+        _lib.check(_lib.fn("fhvae_mu2_estimate_finish")(ptr(zsum), ptr(cnt), ptr(out), R_MU2, K, Z,
+                                                        current_stream_ptr()), "fhvae_mu2_estimate_finish")
+        return out
+
+    def train_step(self, x, labels, num_segs, alpha: float = 10.0, eps=None):
+        """labels (B,) int64 in [0, K): positions of the segments' utterances in the sampled list."""
+        return self.dp.train_step(x, labels, num_segs, alpha, eps=eps)
+
+    def end_round(self):
+        """Trained rows -> their owners in the master table (owner-local sparse row update)."""
+        cache = self.dp.gather_table()
+        self.master.write_back(self.utts, cache)
+        return cache

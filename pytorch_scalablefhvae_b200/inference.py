@@ -70,3 +70,23 @@ def extract_posteriors(model, feats: torch.Tensor, lengths: Sequence[int], seg_s
                                                     current_stream_ptr()), "fhvae_mu2_estimate_finish")
     return {"z1_mu": z1_mu, "z2_mu": z2_mu, "mu2": mu2, "seg_utt": seg_utt,
             "nsegs": torch.from_numpy(nsegs_np).to(dev)}
+
+
+
+def shard_utterances(num_utts: int, rank: int, world: int) -> np.ndarray:
+    """Utterances of `rank`: a contiguous block (utterances are independent: no collective on the data path)."""
+    per = (num_utts + world - 1) // world
+    return np.arange(rank * per, min(num_utts, (rank + 1) * per))
+
+
+@torch.no_grad()
+def extract_posteriors_sharded(model, feats_of, lengths: Sequence[int], rank: int, world: int, **kw):
+    """BASELINE config 4 at N GPUs: every rank extracts the posteriors of ITS block of utterances
+    (shard_utterances); ``feats_of(utt_ids) -> (sum(len), F)`` CUDA features of those utterances, packed.
+    Returns extract_posteriors' dict for the local block plus ``utts`` (their global ids).  Gathering the per-rank
+    results (if wanted at all -- eval_model.py writes per-utterance files) is left to the caller."""
+    mine = shard_utterances(len(lengths), rank, world)
+    lens = np.asarray(lengths)[mine]
+    out = extract_posteriors(model, feats_of(mine), lens, **kw)
+    out["utts"] = torch.from_numpy(mine)
+    return out

@@ -81,6 +81,18 @@ class FusedAdam(torch.optim.Optimizer):
                                         current_stream_ptr())
         _lib.check(rc, "fhvae_adam_flat")
 
+    @torch.no_grad()
+    def reset_state(self, mod, name: str):
+        """Zero the Adam moments of one parameter (hierarchical sampling: the rows of the active mu2 table stand
+        for NEW utterances after every re-sample, train_model.py:424-436, so their moments must not carry over)."""
+        st = self._state_for(mod)
+        o, n = mod._off[name], mod._shape[name]
+        cnt = 1
+        for d in n:
+            cnt *= int(d)
+        st["m"][o:o + cnt].zero_()
+        st["v"][o:o + cnt].zero_()
+
     # ---- torch.optim.Adam-compatible state (utils.py:142 saves optimizer.state_dict())
     def state_dict(self):
         state, idx = {}, 0

@@ -106,8 +106,38 @@ def main():
     dense = sm._flat[:sm._off["mu2_table"]].clone()
     dist.broadcast(dense, src=0)
     assert torch.equal(dense, sm._flat[:sm._off["mu2_table"]]), "dense replicas must stay bit-identical"
+    # ---- one hierarchical round (BASELINE config 3) over W ranks == single-GPU training on the fetched rows
+    Nm, K = 1003, 64
+    torch.manual_seed(2)
+    hm = P.FHVAE(*args, seg_len=T, num_seqs=shard_alloc_rows(K, world), gemm_mode=mode, use_cuda_graphs=True).to(dev)
+    hopt = P.FusedAdam(hm.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    torch.manual_seed(2)
+    hr = P.FHVAE(*args, seg_len=T, num_seqs=K, gemm_mode=mode, use_cuda_graphs=True).to(dev)
+    hropt = P.FusedAdam(hr.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    master = P.ShardedMu2Table(Nm, Z, dev, seed=5)
+    tr = P.HierarchicalTrainer(hm, hopt, master, K)
+    utts = tr.begin_round(seed=21)
+    assert utts.tolist() == __import__("numpy").random.RandomState(21).choice(__import__("numpy").arange(Nm), K, replace=False).tolist()
+    cache0 = master.fetch(utts)
+    with torch.no_grad():
+        hr.mu2_table.copy_(cache0)
+    worst_h = 0.0
+    for step in range(2):
+        x, lab, nsegs = synth_batch(Bl * world, T, F, K, seed=90 + step)
+        g = torch.Generator().manual_seed(30 + step)
+        eps = {"z1": torch.randn(Bl * world, Z, generator=g), "z2": torch.randn(Bl * world, Z, generator=g)}
+        sl = slice(rank * Bl, (rank + 1) * Bl)
+        l_h = tr.train_step(x[sl].to(dev), lab[sl].to(dev), nsegs[sl].to(dev), 10.0, eps={k: v[sl] for k, v in eps.items()})
+        l_r = hr.train_step(x.to(dev), lab.to(dev), nsegs.to(dev), hropt, 10.0, eps=eps)
+        worst_h = max(worst_h, abs(float(tr.dp.global_mean(l_h)) - float(l_r)) / abs(float(l_r)))
+    assert worst_h < 1e-4, worst_h
+    trained = tr.end_round()
+    d = (trained - hr.mu2_table.detach()).abs()
+    assert float(d.max()) <= 2 * 2 * 1e-3 and float((d <= 1e-4 * float(hr.mu2_table.abs().max())).float().mean()) >= 0.999
+    assert torch.equal(master.fetch(utts), trained), "owners hold the trained rows"
     if rank == 0:
-        print(f"mp_check ok: world {world}, loss rel err {worst:.2e}, sharded-table loss rel err {worst_s:.2e}")
+        print(f"mp_check ok: world {world}, loss rel err {worst:.2e}, sharded-table loss rel err {worst_s:.2e}, "
+              f"hierarchical round loss rel err {worst_h:.2e}")
     dist.destroy_process_group()
 
 

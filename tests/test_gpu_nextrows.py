@@ -148,3 +148,63 @@ def test_checkpoint_interop_with_reference_layout(tmp_path):
                tmp_path / "ref.tar")
     m3 = P.load_checkpoint_file(tmp_path / "ref.tar", finetune=True, input_size=24, num_seqs=4)[0]
     assert torch.equal(m3.state_dict()["pre_decoder.fc2.linear.weight"], ref_sd["pre_decoder.fc2.linear.weight"])
+
+
+def test_hierarchical_round_end_to_end():
+    """BASELINE config 3, one rank: sample (bit-exact) -> fetch from the master table -> K-row ACTIVE table sharded
+    inside the train step -> two steps == the oracle training on the fetched rows -> write-back touches exactly the
+    sampled master rows."""
+    Nm, K, Z2, B, T, F = 300, 24, 16, 10, 6, 8
+    m, o = _model_pair(N=K)
+    opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+    master = P.ShardedMu2Table(Nm, Z2, DEV, seed=3)
+    master0 = master.shard.clone()
+    tr = P.HierarchicalTrainer(m, opt, master, K)
+    utts = tr.begin_round(seed=11)
+    assert utts.tolist() == np.random.RandomState(11).choice(np.arange(Nm), K, replace=False).tolist()
+    assert torch.equal(m.mu2_table.detach(), master0[utts.to(DEV)])                    # exact rows, label = position
+    with torch.no_grad():
+        o.mu2_table.copy_(master0[utts.to(DEV)].cpu())
+    oopt = O.make_adam(o.parameters())
+    g = torch.Generator().manual_seed(4)
+    for step in range(2):
+        x = torch.randn(B, T, F, generator=g)
+        lab = torch.randint(0, K, (B,), generator=g)
+        ns = torch.randint(1, 50, (B,), generator=g)
+        eps = {"z1": torch.randn(B, 8, generator=g), "z2": torch.randn(B, 16, generator=g)}
+        loss = tr.train_step(x.to(DEV), lab.to(DEV), ns.to(DEV), 10.0, eps=eps)
+        rl, _ = O.train_step(o, oopt, x, lab, K, ns, 10.0, eps=eps)
+        assert_close(loss, rl, FP32_RTOL, f"loss step {step}")
+    cache = tr.end_round()
+    assert_close(cache, o.mu2_table.detach(), FP32_RTOL, "trained rows")
+    touched = torch.zeros(Nm, dtype=torch.bool, device=DEV)
+    touched[utts.to(DEV)] = True
+    assert torch.equal(master.shard[utts.to(DEV)], cache)                              # owners hold the trained rows
+    assert torch.equal(master.shard[~touched], master0[~touched])                      # all other rows bit-identical
+    # next round: fresh Adam moments for the (new) active rows, MAP refresh available
+    xs = [torch.randn(B, T, F, generator=g).to(DEV) for _ in range(2)]
+    labs = [torch.randint(0, K, (B,), generator=g) for _ in range(2)]
+    utts2 = tr.begin_round(seed=12, refresh=(xs, labs))
+    st = opt._flat_state[id(m)]
+    o_t = m._off["mu2_table"]
+    assert float(st["m"][o_t:].abs().max()) == 0.0 and float(st["v"][o_t:].abs().max()) == 0.0
+    assert utts2.tolist() != utts.tolist()
+
+
+def test_extract_posteriors_sharded_covers_all_utterances():
+    T, F, shift = 6, 8, 2
+    m, _ = _model_pair()
+    rng = np.random.default_rng(1)
+    lengths = [int(v) for v in rng.integers(6, 40, size=13)]
+    feats = torch.randn(sum(lengths), F, generator=torch.Generator().manual_seed(2)).to(DEV)
+    offs = np.concatenate([[0], np.cumsum(lengths)])
+    feats_of = lambda ids: torch.cat([feats[offs[u]:offs[u + 1]] for u in ids])
+    whole = {k: v.clone() for k, v in P.extract_posteriors(m, feats, lengths, seg_shift=shift, batch_size=16).items()}
+    seen, mu2 = [], torch.zeros_like(whole["mu2"])
+    for rank in range(3):
+        out = P.extract_posteriors_sharded(m, feats_of, lengths, rank, 3, seg_shift=shift, batch_size=16)
+        seen += out["utts"].tolist()
+        mu2[out["utts"].to(DEV)] = out["mu2"]
+    assert sorted(seen) == list(range(13))
+    assert_close(mu2, whole["mu2"], 1e-5, "mu2")             # per-utterance results do not depend on the sharding
+                                                             # (batch boundaries differ: summation order only)
