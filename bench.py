@@ -233,6 +233,7 @@ def workload_config(n_gpus, mode):
                         f"{c['B']}x{c['T']}x{c['F']} per GPU, {c['N']}-row mu2 table, fwd+bwd+Adam(lr 1e-3, "
                         f"betas .95/.999), alpha_dis {c['alpha']}",
             "global_batch": c["B"] * n_gpus, "gemm_mode": mode, "parallelism": f"dp{n_gpus}",
+            "allreduce": "none" if n_gpus == 1 else "one NCCL all-reduce of the flat gradient buffer between backward and Adam",
             "inputs": "the same device-resident synthetic batch every timed step (fresh eps draws each step)",
             "l2": "no flush: per-step working set (activations+saved gates ~330 MB, params/Adam ~55 MB) exceeds the 126 MB L2"}
 
@@ -255,6 +256,8 @@ def main():
     ap.add_argument("--mode", default=os.environ.get("FHVAE_MODE", "bf16x3"), choices=["f32", "bf16x3", "bf16"])
     ap.add_argument("--config", default="c1", choices=["c0", "c1", "c3", "c4"])
     ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce [z1 enc + decoder + table] beside the z2 BPTT "
+                                                           "(default: ONE all-reduce between backward and Adam, measured faster)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--breakdown", action="store_true", help="also print a per-kernel-family time split to stderr")
     args = ap.parse_args()
@@ -288,11 +291,12 @@ def main():
     x, idx, nsegs = synth(c["B"], c["T"], c["F"], c["N"], 1234 + rank)
     xd, idd, nsd = x.to(dev), idx.to(dev), nsegs.to(dev)
     xh, idh, nsh = x.pin_memory(), idx.pin_memory(), nsegs.pin_memory()
-    allreduce = None
+    allreduce, ovl = None, None
     if world > 1:
         from pytorch_scalablefhvae_b200.parallel import DataParallel
         dp = DataParallel(m, opt)                  # broadcasts rank 0's parameters, grad_scale = 1/world
-        allreduce = dp.allreduce_                  # ONE NCCL all-reduce of the flat gradient buffer per step
+        allreduce = dp.allreduce_                  # NCCL all-reduce of the flat gradient buffer ...
+        ovl = dp if args.overlap else None         # ... optionally in two ranges, the first beside the z2 encoder's BPTT
 
     def barrier():
         if world > 1:
@@ -303,7 +307,7 @@ def main():
 
     # ---- (1) device-resident inputs: the fused step
     for _ in range(args.warmup):
-        m.train_step(xd, idd, nsd, opt, c["alpha"], allreduce=allreduce)
+        m.train_step(xd, idd, nsd, opt, c["alpha"], allreduce=allreduce, overlap=ovl)
     barrier()
     l0 = lib.fhvae_launch_count()
     sampler = ClockSampler(local)
@@ -313,7 +317,7 @@ def main():
     barrier()
     ev0.record()
     for _ in range(args.steps):
-        loss = m.train_step(xd, idd, nsd, opt, c["alpha"], allreduce=allreduce)
+        loss = m.train_step(xd, idd, nsd, opt, c["alpha"], allreduce=allreduce, overlap=ovl)
     ev1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

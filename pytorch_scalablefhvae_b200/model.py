@@ -225,7 +225,8 @@ class _FHVAECore(nn.Module):
             log_qy = -log_qy.mean()
         return lb, log_qy, log_px_z, nk1, nk2, log_pmu2
 
-    def train_step(self, x, mu_idx, num_segs, optimizer, alpha: float = 10.0, eps=None, allreduce=None, shard=None):
+    def train_step(self, x, mu_idx, num_segs, optimizer, alpha: float = 10.0, eps=None, allreduce=None, shard=None,
+                   overlap=None):
         """Fused loop body of train_model.py:446-454: forward, loss = -mean(lb + alpha*log_qy)
         (train_model.py:243-251), backward, Adam -- one replayed launch sequence (one CUDA graph when
         ``use_cuda_graphs`` and no collective is interposed).  ``allreduce(flat_grads)`` is called
@@ -239,6 +240,8 @@ class _FHVAECore(nn.Module):
         plan.load_inputs(x, mu_idx, num_segs, eps)
         if shard is not None:
             return plan.run_train_step_sharded(optimizer, float(alpha), shard)
+        if overlap is not None and allreduce is not None and hasattr(self, "_z2_end") and self.use_cuda_graphs:
+            return plan.run_train_step_overlapped(optimizer, float(alpha), overlap)
         return plan.run_train_step(optimizer, float(alpha), allreduce)
 
     @staticmethod
@@ -539,6 +542,78 @@ class _Plan:
             if g2 is not None:
                 allreduce(gflat)
                 g2.replay()
+        return self.loss
+
+    # ------------------------------------------------------------------ data parallel, overlapped all-reduce
+    def run_train_step_overlapped(self, optimizer, alpha, dp):
+        """Data-parallel step whose gradient all-reduce overlaps the tail of the backward.  The flat gradient buffer is
+        laid out [z2 encoder | z1 encoder + decoder + table]; the second range is complete when the z1 encoder's
+        weight gradients are, i.e. before the z2 encoder's BPTT (the last ~15 % of the step) has run.  Three graphs:
+        A = forward + backward down to the z1 BPTT launch (critical path), W = the z1 stack's weight-gradient / bias
+        launches (side stream; followed there by the all-reduce of range 2), B = z2 head + z2 BPTT + its weight
+        gradients (main stream, concurrent with W and the all-reduce).  Then the all-reduce of range 1 and Adam."""
+        m = self.m
+        k = 0
+        gflat = m._grad_buffer(k)
+        if self.bwd[k] is None:
+            self.bwd[k] = self._build_bwd(gflat)
+        if not hasattr(self, "loss"):
+            self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
+        B = self.B
+        if self.__dict__.get("_gout_train") != (alpha, B):
+            self.gout.zero_()
+            self.gout[0].fill_(-1.0 / B)
+            self.gout[5].fill_(-alpha / B)
+            self._gout_train = (alpha, B)
+            self._gout_rows = None
+        ov = self.__dict__.get("_ovl")
+        if ov is None or ov["key"] != (alpha, id(optimizer), optimizer.hyper_key()):
+            fwd, bwd = self._train_lists(k)
+            jD = max(i for i, c_ in enumerate(bwd.calls) if c_[1] == "join" and c_[2] == 2)
+            head = bwd.calls[:jD]
+            iM = max(i for i, c_ in enumerate(head) if c_[0] is not None and c_[3] == 0)     # last main-stream launch
+            tail = head[iM + 1:]
+            assert all(c_[0] is None or c_[3] != 0 for c_ in tail)
+
+            def mk(calls, keep):
+                cl = CallList()
+                cl.calls, cl.keep = list(calls), keep
+                return cl
+            lc = CallList()
+            lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss))
+            A = mk(fwd.calls + lc.calls + head[:iM + 1] + [(None, "join", 2, 0)], fwd.keep + bwd.keep)
+            Wl = mk(tail, bwd.keep)
+            Bl = mk(bwd.calls[jD + 1:], bwd.keep)
+            optimizer._state_for(m)
+            # one eager pass (module loading must not happen inside a capture; no segment is warmed up on its own, which
+            # would double-apply accumulating kernels), then every piece is captured without a warm-up run
+            for cl in (A, Wl, Bl):
+                cl.run(current_stream_ptr())
+
+            def cap(f):
+                s_ = torch.cuda.Stream(priority=-1)
+                s_.wait_stream(torch.cuda.current_stream())
+                g_ = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g_, stream=s_):
+                    f()
+                return g_
+            ov = self._ovl = dict(key=(alpha, id(optimizer), optimizer.hyper_key()),
+                                  gA=cap(lambda: A.run(current_stream_ptr())), gW=cap(lambda: Wl.run(current_stream_ptr())),
+                                  gB=cap(lambda: Bl.run(current_stream_ptr())),
+                                  gC=cap(lambda: optimizer.step_flat(m, gflat)), side=torch.cuda.Stream())
+        main, side = torch.cuda.current_stream(), ov["side"]
+        z2_end = m._z2_end
+        ov["gA"].replay()
+        eA = torch.cuda.Event(); eA.record(main)
+        with torch.cuda.stream(side):
+            side.wait_event(eA)
+            ov["gW"].replay()
+            dp.allreduce_(gflat[z2_end:])                    # z1 encoder + decoder + table, beside the z2 BPTT
+            eR = torch.cuda.Event(); eR.record(side)
+        ov["gB"].replay()
+        dp.allreduce_(gflat[:z2_end])
+        main.wait_event(eR)
+        ov["gC"].replay()
         return self.loss
 
     # ------------------------------------------------------------------ sharded mu2 table (SURVEY.md 8e)
@@ -896,8 +971,8 @@ class _FHVAEPlan(_Plan):
         Z1, Z2, mode = self.Z1, self.Z2, self.mode
         TB = T * B
         pre = dict(self.NETS)
-        c.add("fhvae_add2", ptr(self.bsum), m.poff(m._bias_first[0]), m.poff(m._bias_first[1]),
-              m._bias_block_len, side=2)             # fused (b_ih + b_hh), beside the transpose
+        for bi, bh, n, boff in m._bias_blocks:       # fused (b_ih + b_hh), beside the transpose
+            c.add("fhvae_add2", ptr(self.bsum, boff), m.poff(bi), m.poff(bh), n, side=2)
         for k, buf in self.wave_packed.items():      # weight operand images: side stream 3, beside the x projection
             _, whh0, _, _ = _lstm_names(dict(self.NETS)[k], 0)
             wih1, whh1, _, _ = _lstm_names(dict(self.NETS)[k], 1)
@@ -1431,19 +1506,33 @@ class FHVAE(_FHVAECore):
         gauss("z2_gauss_layer", sum(self.z2_hus), Z2)
         lstm(*[nets[2][0], nets[2][2], nets[2][3]])
         gauss("dec_gauss_layer", self.x_hus[-1], F)
-        specs = wspecs + bih + bhh + gspecs["z1_gauss_layer"] + gspecs["z2_gauss_layer"] + gspecs["dec_gauss_layer"]
+        # flat-buffer LAYOUT (independent of the registration order): [z2 encoder | z1 encoder + decoder | table].  The z2
+        # encoder's gradients are the LAST ones a backward produces, so a data-parallel step can all-reduce the
+        # [z1 + decoder + table] range while the z2 BPTT is still running (parallel.DataParallel, overlap).  Inside a
+        # block: LSTM weights, all bias_ih, all bias_hh (one fused-bias launch per block), the Gaussian head.
+        is_z2 = lambda ns: ns[0].startswith("z2_pre_encoder")
+        blocks = [([w for w in wspecs if is_z2(w)], [b for b in bih if is_z2(b)], [b for b in bhh if is_z2(b)],
+                   gspecs["z2_gauss_layer"]),
+                  ([w for w in wspecs if not is_z2(w)], [b for b in bih if not is_z2(b)], [b for b in bhh if not is_z2(b)],
+                   gspecs["z1_gauss_layer"] + gspecs["dec_gauss_layer"])]
+        specs = [sp for blk in blocks for part in blk for sp in part]
         specs.append(("mu2_table", (int(num_seqs), Z2)))
         init["mu2_table"] = torch.empty(int(num_seqs), Z2).normal_(mean=0, std=init_std)
         self._init_flat(specs, init)
-        # fused-bias bookkeeping: b_ih block and b_hh block are contiguous and identically ordered
-        self._bias_first = (bih[0][0], bhh[0][0])
-        self._bias_block_len = sum(_prod(s) for _, s in bih)
-        assert self._off[bhh[0][0]] == self._off[bih[0][0]] + self._bias_block_len
-        self._bias_off = {}
+        self._z2_end = self._off[blocks[1][0][0][0]]            # flat offset where the z2-encoder block ends
+        # fused-bias bookkeeping: per block the b_ih run and the b_hh run are contiguous and identically ordered
+        self._bias_blocks, self._bias_off = [], {}
         short = {"z1_pre_encoder": "z1", "z2_pre_encoder": "z2", "pre_decoder": "dec"}
-        for name, _ in bih:
-            prefix, _, leaf = name.split(".")
-            self._bias_off[short[prefix], int(leaf.rsplit("l", 1)[1])] = self._off[name] - self._off[bih[0][0]]
+        boff = 0
+        for _, bi, bh, _ in blocks:
+            n = sum(_prod(sh) for _, sh in bi)
+            assert self._off[bh[0][0]] == self._off[bi[0][0]] + n
+            self._bias_blocks.append((bi[0][0], bh[0][0], n, boff))
+            for name, _ in bi:
+                prefix, _, leaf = name.split(".")
+                self._bias_off[short[prefix], int(leaf.rsplit("l", 1)[1])] = boff + self._off[name] - self._off[bi[0][0]]
+            boff += n
+        self._bias_block_len = boff
         for pfx in ("z1_gauss_layer", "z2_gauss_layer", "dec_gauss_layer"):
             _check_adjacent(self._off, self._shape, pfx + ".mulayer.weight", pfx + ".logvar_layer.weight")
             _check_adjacent(self._off, self._shape, pfx + ".mulayer.bias", pfx + ".logvar_layer.bias")

@@ -22,14 +22,14 @@ def main():
     mode = P.MODE_BF16X3
     args = (T * F, [H, H], [H, H], Z, Z, [H, H])
     torch.manual_seed(0)
-    m = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode).to(dev)
+    m = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode, use_cuda_graphs=True).to(dev)   # overlapped all-reduce path
     opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
-    dp = DataParallel(m, opt)
+    dp = DataParallel(m, opt, overlap=True)
     torch.manual_seed(0)
     ref = P.FHVAE(*args, seg_len=T, num_seqs=N, gemm_mode=mode).to(dev)
     ropt = P.FusedAdam(ref.parameters(), lr=1e-3, betas=(0.95, 0.999))
     worst = 0.0
-    for step in range(2):
+    for step in range(3):
         x, idx, nsegs = synth_batch(Bl * world, T, F, N, seed=50 + step)
         g = torch.Generator().manual_seed(step)
         eps = {"z1": torch.randn(Bl * world, Z, generator=g), "z2": torch.randn(Bl * world, Z, generator=g)}
@@ -39,7 +39,7 @@ def main():
         worst = max(worst, abs(float(dp.global_mean(l_dp)) - float(l_ref)) / abs(float(l_ref)))
     for (k, p), (_, q) in zip(m.named_parameters(), ref.named_parameters()):
         d = float((p - q).abs().max())
-        assert d <= 2 * 2 * 1e-3, (k, d)                                       # bounded (Adam sign-like at |g|~0)
+        assert d <= 2 * 3 * 1e-3, (k, d)                                       # bounded (Adam sign-like at |g|~0)
         frac = float(((p - q).abs() <= 1e-4 * float(q.abs().max())).float().mean())
         assert frac >= 0.999, (k, frac)
     assert worst < 1e-4, worst
