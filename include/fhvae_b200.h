@@ -47,6 +47,14 @@ int fhvae_version(void);
 int fhvae_built_for_sm(void);              /* 100 */
 /* kernels launched by this process through this library so far (bench.py `gpu_launches`) */
 unsigned long long fhvae_launch_count(void);
+/* Process-wide switch (returns the previous value).  On: every split-K launch of fhvae_gemm_batch /
+ * fhvae_wgrad_planes_batch uses at most TWO partials per output tile, added into a pre-zeroed C by
+ * red.global.add -- (0 + a) + b == (0 + b) + a exactly, so results no longer depend on arrival order and two runs
+ * of a step are bit-identical (everything else on the path already sums in a fixed order).  Off (default): K is
+ * split to fill the SMs (faster; weight gradients differ in the last bits from run to run).  Launch geometries are
+ * baked into captured CUDA graphs: set it before the first step. */
+int fhvae_set_deterministic(int on);
+int fhvae_get_deterministic(void);
 
 /* ---------------------------------------------------------------------------------------------
  * K1/K3/K5/K8 dense contractions.  Replaces nn.Linear addmm (simple_fhvae.py:130-134,208-212),

@@ -99,11 +99,13 @@ PROTOTYPES = {
     "fhvae_head_bwd": [_p, _i, _p, _l, _i, _p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _p],
     "fhvae_step_coef": [_p, _p, _p, _i, _i, _i, _p],
     "fhvae_loss_mean": [_p, _p, _f, _i, _p, _p],
+    "fhvae_set_deterministic": [_i],
+    "fhvae_get_deterministic": [],
     "fhvae_version": [],
     "fhvae_built_for_sm": [],
     "fhvae_launch_count": [],
 }
-NO_STATUS = {"fhvae_lstm_wave_pack_bytes", "fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
+NO_STATUS = {"fhvae_set_deterministic", "fhvae_get_deterministic", "fhvae_lstm_wave_pack_bytes", "fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
 EXPORTS = sorted(list(PROTOTYPES) + ["fhvae_last_error_string"])
 
 _lib = None
@@ -155,6 +157,12 @@ def check(status: int, name: str = ""):
     if status != 0:
         msg = load().fhvae_last_error_string().decode()
         raise FhvaeError(f"{name or 'libfhvae_b200'} failed with status {status}: {msg}")
+
+
+def set_deterministic(on: bool = True) -> bool:
+    """Fixed summation order in every split-K launch (two bit-identical runs of a step); returns the previous
+    setting.  Call before the first step: captured CUDA graphs bake the launch geometry in."""
+    return bool(load().fhvae_set_deterministic(1 if on else 0))
 
 
 def fn(name: str):

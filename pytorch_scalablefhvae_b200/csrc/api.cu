@@ -8,6 +8,8 @@ namespace fhvae {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+static std::atomic<int> g_deterministic{0};
+bool deterministic_mode() { return g_deterministic.load(std::memory_order_relaxed) != 0; }
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -98,6 +100,12 @@ extern "C" int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const f
     return lstm_bwd_simt(dh_all, dh_last, W_hh, c_all, acts, dgates, dgsum, dc, T, B, H,
                          as_stream(stream));
 }
+
+extern "C" int fhvae_set_deterministic(int on) {
+    const int prev = g_deterministic.exchange(on ? 1 : 0);
+    return prev;
+}
+extern "C" int fhvae_get_deterministic() { return g_deterministic.load() ? 1 : 0; }
 
 static constexpr int WAVE_MIN_B = 32;
 

@@ -14,6 +14,7 @@ namespace fhvae {
 
 void set_error(const char* fmt, ...);
 void count_launches(int n);   // process-wide kernel-launch counter (bench.py gpu_launches)
+bool deterministic_mode();    // fhvae_set_deterministic: split-K launches keep a fixed summation order
 
 #define FHVAE_CHECK_ARG(cond, ...)                     \
     do {                                               \

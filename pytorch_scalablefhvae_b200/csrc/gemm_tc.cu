@@ -496,6 +496,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
             ks = want_split < max_split ? want_split : max_split;
             if (ks > 32) ks = 32;
             if (ks < 1) ks = 1;
+            // deterministic mode: <= 2 partials into a zeroed C commute exactly; accumulating launches (beta == 1) do not split
+            if (deterministic_mode()) ks = p.beta == 0.f ? (ks > 2 ? 2 : ks) : 1;
         }
         q.kb_per_split = cdiv(nkb, ks);
         q.ksplit = cdiv(nkb, q.kb_per_split);

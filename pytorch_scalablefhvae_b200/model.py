@@ -188,7 +188,7 @@ class _FHVAECore(nn.Module):
     # ------------------------------------------------------------------ forward
     def _plan(self, B: int, T: int, F: int) -> "_Plan":
         self._ensure_flat()
-        key = (B, T, F, self.gemm_mode, self._flat.data_ptr())
+        key = (B, T, F, self.gemm_mode, self._flat.data_ptr(), _lib.load().fhvae_get_deterministic())
         plan = self._plans.get(key)
         if plan is None:
             plan = self._make_plan(B, T, F)

@@ -279,3 +279,36 @@ def test_sharded_table_step_world1_matches_oracle(name, mode, graphs):
         assert torch.equal(plan.touched_global, rplan.touched)
     m.check_flags()
     _check_params(m, o, 3, what=f"{name} sharded(W=1): ")
+
+
+def test_deterministic_switch_makes_steps_bit_identical():
+    """P.set_deterministic(True): two runs of three full config-1 train steps (bf16x3, graphs) are bit-identical --
+    loss, every parameter, the Adam moments -- and still match the oracle; the default mode is allowed to differ in the
+    last bits (split-K partials meet in red.global.add in arrival order)."""
+    cfg = CFGS["fhvae_c1"]
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+
+    def run():
+        m, o = _pair("fhvae", cfg, gemm_mode=P.MODE_BF16X3, use_cuda_graphs=True)
+        opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+        losses = []
+        for step in range(3):
+            x, idx, nsegs = synth_batch(B, T, F, N, seed=100 + step)
+            eps = _eps(B, 32, 32, seed=step)
+            losses.append(m.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), opt, 10.0, eps=eps).clone())
+        st = opt._flat_state[id(m)]
+        return torch.stack(losses).cpu(), m._flat.detach().clone().cpu(), st["m"].clone().cpu(), m, o
+
+    prev = P.set_deterministic(True)
+    try:
+        la, pa, ma, m, o = run()
+        lb, pb, mb, _, _ = run()
+        assert torch.equal(la, lb) and torch.equal(pa, pb) and torch.equal(ma, mb)
+        oopt = O.make_adam(o.parameters())
+        for step in range(3):
+            x, idx, nsegs = synth_batch(B, T, F, N, seed=100 + step)
+            rl, _ = O.train_step(o, oopt, x, idx, N, nsegs, 10.0, eps=_eps(B, 32, 32, seed=step))
+            assert_close(la[step], rl, FP32_RTOL, f"deterministic mode: loss step {step}")
+        _check_params(m, o, 3, what="deterministic mode: ")
+    finally:
+        P.set_deterministic(prev)
