@@ -63,6 +63,12 @@ constexpr int WMAXT = 63;          // flag = epoch * 64 + t + 1
 #ifndef WAVE_TMA
 #define WAVE_TMA 0           // 1: forward h exchange = plain payload + release/acquire flag + cp.async.bulk straight into the
 #endif                       //    MMA operand buffer (half the bytes of LL words, no register staging, no compute-warp work)
+#ifndef WAVE_FWD2
+#define WAVE_FWD2 0          // 1: forward as two independent 16-row chains per CTA (lstm_wave_fwd2_kernel).  Bit-identical, but
+#endif                       // measured SLOWER (131 vs 105 us per launch): see the kernel's header comment
+#ifndef WAVE_FWD2_QUIET
+#define WAVE_FWD2_QUIET 0
+#endif
 #ifndef WAVE_SAVE_FIRST
 #define WAVE_SAVE_FIRST 0    // 1: the HBM stores of the previous step are issued before the exchange loads
 #endif
@@ -814,6 +820,398 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
 }
 
 // ================================================================================================
+// Two-chain forward wavefront (WAVE_FWD2).  Per step the single-chain kernel above spends ~40 % of its period waiting
+// for the exchange (publish -> L2 -> the peers' polls -> MMAs): pure latency, with every unit of the SM idle.  Here
+// the group's 32 batch rows are run as two INDEPENDENT 16-row recurrences ("chains": warps 0-7 own rows 0-15, warps
+// 8-15 rows 16-31 -- the gate phase and the cell phase already partition the rows this way), each with its own
+// barriers, accumulators (tcgen05.mma N = 16) and LL words, so one chain computes while the other one's h_t is in
+// flight.  Same bytes, same MMAs, same arithmetic as the single-chain kernel (bit-identical results); the exchange
+// buffer layout is unchanged (a chain publishes / pulls the words of its rows).  The layer-1 input projection stays
+// ONE N = 32 product per step (the SS-mode A operand read would otherwise double): it is issued once both chains
+// have gathered h_{t-1}, in four chunks between which the issuer keeps serving recurrent products, accumulates into a
+// double-buffered TMEM tile and is read out one step later (top of the next iteration, in the shadow of the exchange).
+// MEASURED (B200, T=20, B=256, bf16x3): 131 us per launch vs 105 us for the single-chain kernel, with or without quiet
+// waiting (WAVE_FWD2_QUIET); per-chain period 11.0 k cycles vs 8.3 k.  The exchange wait is therefore NOT idle latency
+// that a second chain can fill: each chain still waits for the slowest of 8 CTAs, and that CTA is now also busy with its
+// other chain.  Kept as a compile-time experiment (tools/build_variant.sh fwd2 -DWAVE_FWD2=1); not used by default.
+// ================================================================================================
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_chain(int ch) { asm volatile("bar.sync %0, 256;" ::"r"(1 + ch) : "memory"); }
+
+template <bool X3>
+__global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_constant__ WaveFwdArgs a) {
+    using S = WaveFwdSmem<X3>;
+    constexpr int NB = WNB, NT = WNT, CH = WH, UC = WU, NBC = WNB / 2;
+    constexpr int NWC = (X3 ? 2 : 1) * 128;    // LL words of one slice that belong to one chain
+    constexpr int CPW = 8, RPT = 2, H4 = 4 * CH;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    float (*gates)[NB][UC + 1] = reinterpret_cast<float (*)[NB][UC + 1]>(smem + S::G_OFF);
+    uint64_t* hb_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [chain][buffer]: the chain's 8 warps -> issuer
+    uint64_t* rec_done = hb_full + 4;                                     // [chain]
+    uint64_t* p1_done = hb_full + 6;                                      // [buffer]
+    uint64_t* w_full = hb_full + 8;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(hb_full + 9);
+    uint32_t* epoch_slot = tmem_slot + 1;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, cg = (warp >> 2) & 3;
+    const int ch = (warp >> 3) & 1, ct = tid & 255;          // chain, thread index inside the chain (compute warps)
+    const int layer = blockIdx.x / (a.G * WG);
+    const int grp = (blockIdx.x / WG) % a.G;
+    const int rank = blockIdx.x % WG;
+    const int T = a.T, B = a.B;
+    const int b0 = a.b_off + grp * NB;
+    const bool p1_duty = (layer == 0 && a.L == 2);
+    const int nsteps = p1_duty ? T + 1 : T;
+    const float* P = layer ? nullptr : a.P0;
+    const float* Q = layer ? nullptr : a.Q0;
+    const float* W_hh = layer ? a.Whh1 : a.Whh0;
+    float* h_all = layer ? a.h1 : a.h0;
+    __nv_bfloat16* h_pl = layer ? a.hp1 : a.hp0;
+    float* c_all = layer ? a.c1 : a.c0;
+    float* acts = layer ? a.a1 : a.a0;
+    uint32_t* cnt = reinterpret_cast<uint32_t*>(a.xchg) + (((a.L - 1) * 2 + layer) * WMAXG + grp) * WG + rank;
+    uint4* own = a.xchg + WHDR + ((size_t)(layer * a.Gs + grp) * T) * (WG * WSLICE);
+    uint4* p1x = a.xchg + WHDR + ((size_t)(2 * a.Gs) * T) * (WG * WSLICE) + ((size_t)grp * T) * (WG * WPSLICE) + rank * WPSLICE;
+
+    constexpr int NACC = 2;
+    constexpr int WCOLS = CH / 2;
+    constexpr int ACOL = (X3 ? 2 : 1) * WCOLS;
+    constexpr int TCOLS = 512;                 // W (256 / 128) + recurrent acc 2 chains x 2 x 16 + projection acc 2 x 2 x 32
+    if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
+    if (tid == 32) {
+        for (int i = 0; i < 4; ++i) mbar_init(&hb_full[i], NT / 64);      // 8 warps per chain
+        mbar_init(&rec_done[0], 1); mbar_init(&rec_done[1], 1);
+        mbar_init(&p1_done[0], 1); mbar_init(&p1_done[1], 1); mbar_init(w_full, 1);
+        fence_mbar_init();
+        *epoch_slot = *cnt;
+        if (p1_duty && a.packed)
+            wave_load_S_image(a.packed + WavePack<X3>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t fbase = (*epoch_slot) << 6;
+    constexpr uint32_t W_LBO = WNC * 16, H_LBO = NB * 16, SBO_ = 128;
+    const uint32_t tmem_d = tmem_base + ACOL;                  // recurrent accumulators [chain][NACC][NBC]
+    const uint32_t tmem_p = tmem_d + 2 * NACC * NBC;           // projection accumulators [buffer][NACC][NB]
+    constexpr uint32_t idesc16 = make_idesc_bf16(WNC, NBC), idesc32 = make_idesc_bf16(WNC, NB);
+    const uint32_t hb_u = smem_u32(smem + S::H_OFF), wih_u = smem_u32(smem + S::W_OFF);
+
+    if (warp >= NT / 32) {
+        // ================= tcgen05 issuer: serves whichever chain has its operand ready, projection chunks in between
+        reg_dec<32>();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp == NT / 32 && elect_one()) {
+            if (p1_duty && a.packed) mbar_wait(w_full, 0);
+            int ts0 = 1, ts1 = 1, p1_t = 1, p1_s = 0;
+            uint32_t spins = 0;
+            while (ts0 < nsteps || ts1 < nsteps || (p1_duty && p1_t < nsteps)) {
+                bool progressed = false;
+#pragma unroll 1
+                for (int c = 0; c < 2; ++c) {
+                    const int t = c ? ts1 : ts0;
+                    if (t >= nsteps || !mbar_test(&hb_full[c * 2 + (t & 1)], ((t - 1) >> 1) & 1)) continue;
+                    tc_fence_after();
+                    if (t < T) {
+                        const uint32_t hbt = hb_u + (t & 1) * S::H_BUF + (uint32_t)c * (NBC * 16);
+                        const uint64_t dhh0 = make_smem_desc(hbt, H_LBO, SBO_);
+                        const uint64_t dhl0 = make_smem_desc(hbt + S::H_PART, H_LBO, SBO_);
+#pragma unroll 1
+                        for (int j = 0; j < WG; ++j) {
+#pragma unroll
+                            for (int ks = 0; ks < 2; ++ks) {
+                                const int s = 2 * j + ks;
+                                const uint64_t ih = (uint64_t)((s * 2 * H_LBO) >> 4);
+                                const uint32_t awh = tmem_base + (uint32_t)(s * 8);
+                                const uint32_t td = tmem_d + (uint32_t)((c * NACC + ks) * NBC);
+                                const uint32_t first = j > 0 ? 1u : 0u;
+                                if (X3) {
+                                    umma_bf16_ts(td, awh + WCOLS, dhh0 + ih, idesc16, first);
+                                    umma_bf16_ts(td, awh, dhl0 + ih, idesc16, 1u);
+                                    umma_bf16_ts(td, awh, dhh0 + ih, idesc16, 1u);
+                                } else {
+                                    umma_bf16_ts(td, awh, dhh0 + ih, idesc16, first);
+                                }
+                            }
+                        }
+                        umma_commit(&rec_done[c]);
+                    }
+                    if (c) ++ts1; else ++ts0;
+                    progressed = true;
+                }
+                if (p1_duty && p1_t < nsteps && p1_t < ts0 && p1_t < ts1) {
+                    // a quarter of P1(p1_t) = W_ih1_slice * h0_{p1_t - 1}^T over all 32 rows (both chains gathered it)
+                    const uint32_t hbt = hb_u + (p1_t & 1) * S::H_BUF;
+                    const uint32_t koff = (uint32_t)p1_s * 2 * H_LBO, woff = (uint32_t)p1_s * 2 * W_LBO;
+                    uint64_t dh = make_smem_desc(hbt + koff, H_LBO, SBO_), dl = make_smem_desc(hbt + S::H_PART + koff, H_LBO, SBO_);
+                    uint64_t dwh = make_smem_desc(wih_u + woff, W_LBO, SBO_), dwl = make_smem_desc(wih_u + S::W_PART + woff, W_LBO, SBO_);
+#pragma unroll 1
+                    for (int i = 0; i < 4; ++i) {
+                        const int s = p1_s + i;
+                        const uint32_t td = tmem_p + (uint32_t)(((p1_t & 1) * NACC + (s % NACC)) * NB);
+                        const uint32_t first = s >= NACC ? 1u : 0u;
+                        if (X3) {
+                            umma_bf16(td, dwl, dh, idesc32, first);
+                            umma_bf16(td, dwh, dl, idesc32, 1u);
+                            umma_bf16(td, dwh, dh, idesc32, 1u);
+                        } else {
+                            umma_bf16(td, dwh, dh, idesc32, first);
+                        }
+                        dh += (uint64_t)((2 * H_LBO) >> 4); dl += (uint64_t)((2 * H_LBO) >> 4);
+                        dwh += (uint64_t)((2 * W_LBO) >> 4); dwl += (uint64_t)((2 * W_LBO) >> 4);
+                    }
+                    p1_s += 4;
+                    if (p1_s == CH / 16) {
+                        umma_commit(&p1_done[p1_t & 1]);
+                        p1_s = 0;
+                        ++p1_t;
+                    }
+                    progressed = true;
+                }
+                if (progressed) spins = 0;
+                else if (++spins > FHVAE_SPIN_LIMIT * 16u) __trap();
+            }
+        }
+        __syncwarp();
+    } else {
+        // ================= compute warps =================
+        reg_inc<112>();
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
+        if (a.packed) {
+            wave_load_T_image<X3>(a.packed + WavePack<X3>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
+        } else {
+            const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+            float4 wv[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+                uint32_t hi[16], lo[16];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 w4 = wv[hf * 8 + i];
+                    const float v[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+                    for (int j = 0; j < 2; ++j) {
+                        hi[2 * i + j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+                        lo[2 * i + j] = pack_bf16(v[2 * j] - __uint_as_float(hi[2 * i + j] << 16),
+                                                  v[2 * j + 1] - __uint_as_float(hi[2 * i + j] & 0xffff0000u));
+                    }
+                }
+                tmem_st16(ta + hf * 16, hi);
+                if (X3) tmem_st16(ta + WCOLS + hf * 16, lo);
+            }
+        }
+        tmem_wait_st();
+        if (p1_duty && !a.packed) {
+            const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+            const int r = q * 32 + lane;
+#pragma unroll 2
+            for (int i = 0; i < 8; ++i) {
+                const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
+                const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
+                const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+                const uint32_t off = (uint32_t)(cg * 8 + i) * W_LBO + (uint32_t)r * 16;
+                if (X3) {
+                    uint4 hi, lo;
+                    split_bf16(v, hi, lo);
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + off) = hi;
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + S::W_PART + off) = lo;
+                } else {
+                    *reinterpret_cast<uint4*>(smem + S::W_OFF + off) =
+                        make_uint4(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]), pack_bf16(v[4], v[5]), pack_bf16(v[6], v[7]));
+                }
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const int col = q * CH + rank * UC + lane;
+        float qv[CPW];
+        {
+            const float bias = (layer == 1 && a.b1) ? __ldg(a.b1 + col) : 0.f;
+#pragma unroll
+            for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
+        }
+        float creg[RPT];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) creg[i] = 0.f;
+        const int kglob = rank * UC + lane;
+        const uint32_t hoff_k = (uint32_t)(kglob >> 3) * H_LBO + (uint32_t)(kglob & 7) * 2;
+        const int llw = (cg * 4) * 128 + q * 32 + lane;
+        float aval[CPW], hreg[RPT];
+        // this thread's LL word of a slice: (bf16 part, K chunk, row of ITS chain, 8-byte half)
+        const int xw_part = ct >> 7, xw_kcl = ((ct & 127) >> 1) >> 4, xw_row = ch * NBC + (((ct & 127) >> 1) & 15), xw_half = ct & 1;
+        const int xw_word = xw_part * 256 + ((xw_kcl * NB + xw_row) << 1) + xw_half;
+        const uint32_t xw_off = (uint32_t)xw_part * S::H_PART + (uint32_t)xw_kcl * H_LBO + (uint32_t)xw_row * 16 + xw_half * 8;
+        const bool xw_on = ct < NWC;
+        const uint32_t acc_addr = tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * NACC * NBC + (cg & 1) * CPW);
+        auto store_saved = [&](int ts) {
+            float* At = acts + ((size_t)ts * B + b0 + cg * CPW) * H4 + col;
+#pragma unroll
+            for (int b = 0; b < CPW; ++b) At[(size_t)b * H4] = aval[b];
+#pragma unroll
+            for (int i = 0; i < RPT; ++i) {
+                const size_t o = ((size_t)ts * B + b0 + warp * RPT + i) * CH + kglob;
+                h_all[o] = hreg[i];
+                c_all[o] = creg[i];
+                if (h_pl) {
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(hreg[i]);
+                    h_pl[o] = hh;
+                    h_pl[o + a.hps] = __float2bfloat16_rn(hreg[i] - __bfloat162float(hh));
+                }
+            }
+        };
+        // P1(tau) = W_ih1_slice * h0_{tau-1}^T: TMEM tile tau&1 -> LL words of step tau-1 for the layer-1 CTA of this rank
+        auto p1_readout = [&](int tau) {
+            mbar_wait(&p1_done[tau & 1], ((tau - 1) >> 1) & 1);
+            tc_fence_after();
+            const uint32_t pb = tmem_p + ((uint32_t)(q * 32) << 16) + (uint32_t)((tau & 1) * NACC * NB + cg * CPW);
+            float pa[CPW];
+            tmem_ld_nb<CPW>(pb, pa);
+#pragma unroll
+            for (int k = 1; k < NACC; ++k) {
+                float part[CPW];
+                tmem_ld_nb<CPW>(pb + (uint32_t)(k * NB), part);
+#pragma unroll
+                for (int b = 0; b < CPW; ++b) pa[b] += part[b];
+            }
+#pragma unroll
+            for (int j = 0; j < CPW / 2; ++j)
+                st_ll(p1x + (size_t)(tau - 1) * (WG * WPSLICE) + llw + j * 128, __float_as_uint(pa[2 * j]),
+                      __float_as_uint(pa[2 * j + 1]), fbase + tau);
+        };
+
+        for (int t = 0; t < nsteps; ++t) {
+            const bool real = t < T;
+            WTL(t, 0);
+            uint8_t* hbt = smem + S::H_OFF + (t & 1) * S::H_BUF;
+            // the projection issued behind the PREVIOUS step: complete before this iteration overwrites the operand rows
+            // it read (own slice, cell phase below) -- and read out here, in the shadow of the exchange
+            if (p1_duty && t >= 2) p1_readout(t - 1);
+            if (t > 0) {
+                const uint4* slot = own + (size_t)(t - 1) * (WG * WSLICE);
+#if WAVE_FWD2_QUIET
+                // quiet wait: ONE lane per peer polls a sentinel word of this chain's rows, the chain's other warps sleep
+                // at the named barrier (no poll traffic competing with the chain that is computing)
+                if ((warp & 7) == 0) {
+                    if (lane < WG - 1) {
+                        const int lastw = (X3 ? 256 : 0) + ((3 * NB + ch * NBC + NBC - 1) << 1) + 1;
+                        const uint4* sp = slot + (lane + (lane >= rank ? 1 : 0)) * WSLICE + lastw;
+                        uint4 sv = ld_ll(sp);
+                        wait_ll(sv, sp, fbase + t);
+                    }
+                    __syncwarp();
+                }
+                bar_chain(ch);
+#endif
+                if (xw_on) {
+                    uint4 hv[7];
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) hv[i] = ld_ll(slot + (i + (i >= rank ? 1 : 0)) * WSLICE + xw_word);
+                    wait_ll_all<7, true>(hv, [&](int i) { return slot + (i + (i >= rank ? 1 : 0)) * WSLICE + xw_word; }, fbase + t);
+#pragma unroll
+                    for (int i = 0; i < 7; ++i) {
+                        const int src = i + (i >= rank ? 1 : 0);
+                        *reinterpret_cast<uint2*>(hbt + xw_off + (uint32_t)(src * 4) * H_LBO) = make_uint2(hv[i].x, hv[i].z);
+                    }
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&hb_full[ch * 2 + (t & 1)]);
+                store_saved(t - 1);
+            }
+            float pv[CPW];
+            uint4 pl[CPW / 2];
+            if (real) {
+                if (layer == 0) {
+                    const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
+#pragma unroll
+                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
+                }
+                float acc[CPW];
+                if (t > 0) {
+                    mbar_wait(&rec_done[ch], (t - 1) & 1);
+                    WTL(t, 2);
+                    tc_fence_after();
+                    tmem_ld_nb<CPW>(acc_addr, acc);
+#pragma unroll
+                    for (int k = 1; k < NACC; ++k) {
+                        float part[CPW];
+                        tmem_ld_nb<CPW>(acc_addr + (uint32_t)(k * NBC), part);
+#pragma unroll
+                        for (int b = 0; b < CPW; ++b) acc[b] += part[b];
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < CPW; ++b) acc[b] = 0.f;
+                }
+                if (layer == 1) {
+                    wait_ll_all<CPW / 2, true>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
+#pragma unroll
+                    for (int j = 0; j < CPW / 2; ++j) {
+                        pv[2 * j] = __uint_as_float(pl[j].x);
+                        pv[2 * j + 1] = __uint_as_float(pl[j].z);
+                    }
+                }
+#pragma unroll
+                for (int b = 0; b < CPW; ++b) {
+                    const float pre = acc[b] + pv[b] + qv[b];
+                    aval[b] = (q == 2) ? tanhf_fast(pre) : sigmoidf_fast(pre);
+                    gates[q][cg * CPW + b][lane] = aval[b];
+                }
+                tc_fence_before();
+                bar_chain(ch);
+                WTL(t, 4);
+                uint8_t* hbn = smem + S::H_OFF + ((t + 1) & 1) * S::H_BUF;
+#pragma unroll
+                for (int i = 0; i < RPT; ++i) {
+                    const int b = warp * RPT + i;
+                    const float ig = gates[0][b][lane], fg = gates[1][b][lane], gg = gates[2][b][lane], og = gates[3][b][lane];
+                    const float c = fmaf(fg, creg[i], ig * gg);
+                    creg[i] = c;
+                    const float h = og * tanhf_fast(c);
+                    hreg[i] = h;
+                    const __nv_bfloat16 hh = __float2bfloat16_rn(h);
+                    *reinterpret_cast<__nv_bfloat16*>(hbn + hoff_k + b * 16) = hh;
+                    if (X3)
+                        *reinterpret_cast<__nv_bfloat16*>(hbn + S::H_PART + hoff_k + b * 16) = __float2bfloat16_rn(h - __bfloat162float(hh));
+                }
+                bar_chain(ch);
+                WTL(t, 5);
+                if (t + 1 < nsteps && xw_on) {
+                    const uint2 d = *reinterpret_cast<const uint2*>(hbn + xw_off + (uint32_t)(rank * 4) * H_LBO);
+                    st_ll(own + (size_t)t * (WG * WSLICE) + rank * WSLICE + xw_word, d.x, d.y, fbase + t + 1);
+                }
+            }
+        }
+        if (p1_duty) p1_readout(nsteps - 1);
+        else store_saved(T - 1);
+    }
+    if (tid == 0) *cnt = (fbase >> 6) + 1;
+    tc_fence_before();
+    __syncthreads();
+    if (warp == NT / 32) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// ================================================================================================
 // BPTT wavefront (top layer first)
 // ================================================================================================
 // Per step t (descending) the CTA that owns 32 units computes dgates_t pointwise and contributes the split-K
@@ -1244,7 +1642,11 @@ template <bool X3>
 static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
     using S = WaveFwdSmem<X3>;
     static bool attr = false;
+#if WAVE_FWD2
+    auto kern = lstm_wave_fwd2_kernel<X3>;
+#else
     auto kern = lstm_wave_fwd_kernel<X3>;
+#endif
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL2);
         if (e != cudaSuccess) {
