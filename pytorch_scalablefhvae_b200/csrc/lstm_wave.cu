@@ -46,10 +46,10 @@ constexpr int WMAXT = 63;          // flag = epoch * 64 + t + 1
 
 // ---- experiment switches (tools/build_variant.sh + tools/wave_bench.py); the defaults are the measured best
 #ifndef WAVE_POLL_SEQ_FWD
-#define WAVE_POLL_SEQ_FWD 1  // forward h gather: wait word by word (measured: 116 us/launch vs 173 us with the parallel wait,
-#endif                       // whose retry loads need 28 more registers -> spills in the 112-register compute warps)
+#define WAVE_POLL_SEQ_FWD 1  // forward h gather, wait_ll_all MODE: 1 word by word, 0 invalid words of a round together (28 more
+#endif                       // registers -> spills: 173 vs 116 us/launch), 2 re-read everything per round
 #ifndef WAVE_POLL_SEQ_BWD
-#define WAVE_POLL_SEQ_BWD 0  // BPTT reduce-scatter: all outstanding words per retry round (measured: 111 vs 134 us/launch)
+#define WAVE_POLL_SEQ_BWD 0  // BPTT reduce-scatter: MODE 0 (measured: 111 vs 134 us/launch with MODE 1)
 #endif
 #ifndef WAVE_P_FIRST
 #define WAVE_P_FIRST 0       // 1: request this step's input projection before the exchange instead of after it
@@ -127,14 +127,28 @@ __device__ __forceinline__ void fence_proxy_async_all() {
 // one L2 round trip (~260 cycles) however many words are outstanding.  (Waiting word by word -- wait_ll in a loop --
 // serialises the round trips: 7 peer slices that all miss their first poll cost 7 dependent trips, which was
 // 2900-3700 of the 10600 cycles of a forward wavefront step in round 1.)
-template <int N, bool SEQ, typename AddrFn>
+template <int N, int MODE, typename AddrFn>
 __device__ __forceinline__ uint32_t wait_ll_all(uint4 (&v)[N], AddrFn addr, uint32_t flag) {
     uint32_t spins = 0;
-    if constexpr (SEQ) {
+    if constexpr (MODE == 1) {
+        // word by word: a word that missed its first poll costs its own dependent L2 round trip
 #pragma unroll
         for (int i = 0; i < N; ++i) spins += wait_ll(v[i], addr(i), flag);
         return spins;
+    } else if constexpr (MODE == 2) {
+        // re-read EVERYTHING until every word is valid: one round trip per retry round, no predicates, no extra
+        // registers (valid words stay valid within a step, so re-reading them is harmless)
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int i = 0; i < N; ++i) ok = ok && v[i].y == flag && v[i].w == flag;
+            if (ok) return spins;
+            if (++spins > FHVAE_SPIN_LIMIT) __trap();
+#pragma unroll
+            for (int i = 0; i < N; ++i) v[i] = ld_ll(addr(i));
+        }
     } else {
+        // re-issue only the still-invalid words of a round together (needs the retry loads in separate registers)
         for (;;) {
             uint32_t bad = 0;
 #pragma unroll
@@ -364,7 +378,7 @@ __device__ __forceinline__ void wave_store(const uint4* slot, int rank, uint32_t
     if (tid < NW) {
         const int part = tid >> 8, rem = tid & 255, chunk = rem >> 1, half = rem & 1;
         const int kcl = chunk / WNB, row = chunk % WNB;
-        wait_ll_all<NS, WAVE_POLL_SEQ_FWD != 0>(v, [&](int i) { return slot + (SKIP_OWN ? i + (i >= rank ? 1 : 0) : i) * WSLICE + tid; }, flag);
+        wait_ll_all<NS, WAVE_POLL_SEQ_FWD>(v, [&](int i) { return slot + (SKIP_OWN ? i + (i >= rank ? 1 : 0) : i) * WSLICE + tid; }, flag);
 #pragma unroll
         for (int i = 0; i < NS; ++i) {
             const int src = SKIP_OWN ? i + (i >= rank ? 1 : 0) : i;
@@ -722,7 +736,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
                 WTL(t, 3);
                 if (layer == 1) {
-                    wait_ll_all<CPW / 2, WAVE_POLL_SEQ_FWD != 0>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
+                    wait_ll_all<CPW / 2, WAVE_POLL_SEQ_FWD>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
 #pragma unroll
                     for (int j = 0; j < CPW / 2; ++j) {
                         pv[2 * j] = __uint_as_float(pl[j].x);
@@ -1122,7 +1136,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
                     uint4 hv[7];
 #pragma unroll
                     for (int i = 0; i < 7; ++i) hv[i] = ld_ll(slot + (i + (i >= rank ? 1 : 0)) * WSLICE + xw_word);
-                    wait_ll_all<7, true>(hv, [&](int i) { return slot + (i + (i >= rank ? 1 : 0)) * WSLICE + xw_word; }, fbase + t);
+                    wait_ll_all<7, 1>(hv, [&](int i) { return slot + (i + (i >= rank ? 1 : 0)) * WSLICE + xw_word; }, fbase + t);
 #pragma unroll
                     for (int i = 0; i < 7; ++i) {
                         const int src = i + (i >= rank ? 1 : 0);
@@ -1164,7 +1178,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
                     for (int b = 0; b < CPW; ++b) acc[b] = 0.f;
                 }
                 if (layer == 1) {
-                    wait_ll_all<CPW / 2, true>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
+                    wait_ll_all<CPW / 2, 1>(pl, [&](int j) { return p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128; }, fbase + t + 1);
 #pragma unroll
                     for (int j = 0; j < CPW / 2; ++j) {
                         pv[2 * j] = __uint_as_float(pl[j].x);
@@ -1457,7 +1471,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
 #endif
 #pragma unroll
             for (int i = 0; i < PER; ++i) v[i] = ld_ll(src + tid + i * NT);
-            wait_ll_all<PER, WAVE_POLL_SEQ_BWD != 0>(v, [&](int i) { return src + tid + i * NT; }, fbase + (uint32_t)(T - t));
+            wait_ll_all<PER, WAVE_POLL_SEQ_BWD>(v, [&](int i) { return src + tid + i * NT; }, fbase + (uint32_t)(T - t));
 #pragma unroll
             for (int i = 0; i < PER; ++i) {
                 const int w = tid + i * NT;
@@ -1558,7 +1572,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
 #endif
 #pragma unroll
                 for (int src = 0; src < WG; ++src) pr[src] = ld_ll(rd + src * WRS);
-                wait_ll_all<WG, WAVE_POLL_SEQ_BWD != 0>(pr, [&](int src) { return rd + src * WRS; }, fbase + k + 1);
+                wait_ll_all<WG, WAVE_POLL_SEQ_BWD>(pr, [&](int src) { return rd + src * WRS; }, fbase + k + 1);
 #pragma unroll
                 for (int src = 0; src < WG; ++src) {                      // fixed summation order: deterministic
                     dh[0] += __uint_as_float(pr[src].x);
