@@ -69,6 +69,9 @@ constexpr int WMAXT = 63;          // flag = epoch * 64 + t + 1
 #ifndef WAVE_FWD2_QUIET
 #define WAVE_FWD2_QUIET 0
 #endif
+#ifndef WAVE_COOPERATIVE
+#define WAVE_COOPERATIVE -1  // 1 / 0: always / never launch cooperatively; -1: env FHVAE_WAVE_COOPERATIVE=1 decides (default off)
+#endif
 #ifndef WAVE_SAVE_FIRST
 #define WAVE_SAVE_FIRST 0    // 1: the HBM stores of the previous step are issued before the exchange loads
 #endif
@@ -1639,11 +1642,94 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     if (warp == NT / 32) tmem_dealloc<TCOLS>(tmem_base);
 }
 
-bool lstm_wave_supported(int T, int B, int H, int L) {
-    return H == WH && B % WNB == 0 && T >= 1 && T <= WMAXT && (L == 1 || L == 2);
+
+// Forward progress of a launch needs ALL its CTAs co-resident (they spin on each other's words): the launch size is
+// derived from the CURRENT device (SM count x resident CTAs per SM for this kernel's shared memory), not from a
+// compile-time constant, and an over-sized grid is refused with an error instead of hanging (MIG slice, MPS SM
+// limit, a smaller part).  With FHVAE_WAVE_COOPERATIVE=1 the launch is additionally cooperative: the driver
+// gang-schedules the grid, i.e. it starts only when every CTA has an SM.  Default off: measured 0.949 vs 0.928 ms per
+// step (a gang-scheduled launch cannot start while the previous stack's weight-gradient CTAs still drain), and without
+// it forward progress only needs every OTHER resident kernel to terminate on its own, which holds for every kernel of
+// this library (tests/test_gpu_train_step.py::test_wavefront_launch_survives_sm_hogging_neighbours); a protocol
+// bug traps after FHVAE_SPIN_LIMIT polls instead of hanging the GPU.
+static bool wave_cooperative() {
+#if WAVE_COOPERATIVE >= 0
+    return WAVE_COOPERATIVE != 0;
+#else
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FHVAE_WAVE_COOPERATIVE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v == 1;
+#endif
+}
+static int device_index() {
+    int d = 0;
+    cudaGetDevice(&d);
+    return d < 0 || d >= 64 ? 0 : d;
+}
+static int device_sm_count() {
+    static int cache[64] = {0};
+    const int d = device_index();
+    if (cache[d] == 0) {
+        int n = 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || n <= 0) n = 0;
+        cache[d] = n > 0 ? n : -1;
+    }
+    return cache[d] > 0 ? cache[d] : 0;
+}
+static int wave_groups_per_launch(int L) {          // 18 or 9 on a full B200 (148 SMs, 1 CTA of 181-214 KB per SM)
+    const int g = device_sm_count() / (WG * L);
+    return g > WMAXG ? WMAXG : g;
+}
+template <typename K>
+static int wave_launch(K kern, const char* name, int grid, size_t smem, void* args, cudaStream_t st) {
+    // (kernel, device) pairs whose shared-memory attribute / occupancy have been checked -- keyed by the kernel's
+    // address: the bf16x3 and bf16 instantiations share one function-pointer TYPE, hence one copy of this template
+    static const void* ready_k[16] = {nullptr};
+    static int ready_d[16] = {0};
+    static int n_ready = 0;
+    const int d = device_index();
+    bool ready = false;
+    for (int i = 0; i < n_ready; ++i) ready = ready || (ready_k[i] == reinterpret_cast<const void*>(kern) && ready_d[i] == d);
+    if (!ready) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        int occ = 0;
+        if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, WNTA, smem);
+        if (e != cudaSuccess || occ < 1) {
+            set_error("%s: %d B of shared memory per CTA not available on this device (%s)", name, (int)smem,
+                      e != cudaSuccess ? cudaGetErrorString(e) : "0 resident CTAs per SM");
+            return e != cudaSuccess ? (int)e : FHVAE_ENOSUP;
+        }
+        if (n_ready < 16) {
+            ready_k[n_ready] = reinterpret_cast<const void*>(kern);
+            ready_d[n_ready++] = d;
+        }
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(WNTA);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative;
+    at[0].val.cooperative = wave_cooperative() ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    void* kargs[1] = {args};
+    cudaError_t e = cudaLaunchKernelExC(&cfg, reinterpret_cast<const void*>(kern), kargs);
+    count_launches(1);
+    if (e != cudaSuccess) {
+        set_error("%s: launch of %d co-resident CTAs failed: %s", name, grid, cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
 }
 
-static int wave_groups_per_launch(int L) { return (kNumSM / (WG * L)) > WMAXG ? WMAXG : kNumSM / (WG * L); }   // 18 or 9
+bool lstm_wave_supported(int T, int B, int H, int L) {
+    return H == WH && B % WNB == 0 && T >= 1 && T <= WMAXT && (L == 1 || L == 2) && wave_groups_per_launch(L) >= 1;
+}
 
 size_t lstm_wave_xchg_bytes(int T, int B, int L) {
     int gs = B / WNB;
@@ -1655,27 +1741,22 @@ size_t lstm_wave_xchg_bytes(int T, int B, int L) {
 template <bool X3>
 static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
     using S = WaveFwdSmem<X3>;
-    static bool attr = false;
 #if WAVE_FWD2
     auto kern = lstm_wave_fwd2_kernel<X3>;
 #else
     auto kern = lstm_wave_fwd_kernel<X3>;
 #endif
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL2);
-        if (e != cudaSuccess) {
-            set_error("lstm_wave_fwd: cudaFuncSetAttribute(%d B): %s", S::TOTAL2, cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr = true;
-    }
     const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L);
+    if (gmax < 1) {
+        set_error("lstm_wave_fwd: the device has too few SMs for one group of %d CTAs x %d layers", WG, a.L);
+        return FHVAE_ENOSUP;
+    }
     a.Gs = gtot < gmax ? gtot : gmax;
     for (int g0 = 0; g0 < gtot; g0 += gmax) {          // all CTAs of a launch must be co-resident (one per SM)
         a.G = (gtot - g0) < gmax ? (gtot - g0) : gmax;
         a.b_off = g0 * WNB;
-        kern<<<a.L * a.G * WG, WNTA, a.L == 2 ? S::TOTAL2 : S::TOTAL1, st>>>(a);
-        FHVAE_LAUNCH_CHECK("lstm_wave_fwd");
+        const int r = wave_launch(kern, "lstm_wave_fwd", a.L * a.G * WG, S::TOTAL2, &a, st);   // (single-layer launches
+        if (r) return r;                                                                        //  simply leave W_OFF.. unused)
     }
     return 0;
 }
@@ -1700,23 +1781,18 @@ size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L) {
 template <bool X3>
 static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
     using S = WaveBwdSmem<X3>;
-    static bool attr = false;
     auto kern = lstm_wave_bwd_kernel<X3>;
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::TOTAL2);
-        if (e != cudaSuccess) {
-            set_error("lstm_wave_bwd: cudaFuncSetAttribute(%d B): %s", S::TOTAL2, cudaGetErrorString(e));
-            return (int)e;
-        }
-        attr = true;
-    }
     const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L);
+    if (gmax < 1) {
+        set_error("lstm_wave_bwd: the device has too few SMs for one group of %d CTAs x %d layers", WG, a.L);
+        return FHVAE_ENOSUP;
+    }
     a.Gs = gtot < gmax ? gtot : gmax;
     for (int g0 = 0; g0 < gtot; g0 += gmax) {
         a.G = (gtot - g0) < gmax ? (gtot - g0) : gmax;
         a.b_off = g0 * WNB;
-        kern<<<a.L * a.G * WG, WNTA, a.L == 2 ? S::TOTAL2 : S::TOTAL1, st>>>(a);
-        FHVAE_LAUNCH_CHECK("lstm_wave_bwd");
+        const int r = wave_launch(kern, "lstm_wave_bwd", a.L * a.G * WG, S::TOTAL2, &a, st);
+        if (r) return r;
     }
     return 0;
 }

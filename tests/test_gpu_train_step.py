@@ -312,3 +312,31 @@ def test_deterministic_switch_makes_steps_bit_identical():
         _check_params(m, o, 3, what="deterministic mode: ")
     finally:
         P.set_deterministic(prev)
+
+
+def test_wavefront_launch_survives_sm_hogging_neighbours():
+    """the wavefront kernels are 128 mutually spinning CTAs.  They are launched cooperatively (the
+    driver gang-schedules the grid), so kernels of other streams that hold SMs only delay them: a train step running
+    beside a stream of large matmuls finishes (no spin-limit trap, no hang) with the same loss as when it runs alone."""
+    cfg = CFGS["fhvae_c1"]
+    B, T, F, N = cfg["B"], cfg["T"], cfg["F"], cfg["N"]
+    x, idx, nsegs = synth_batch(B, T, F, N)
+    eps = _eps(B, 32, 32)
+
+    def losses(hog):
+        m, _ = _pair("fhvae", cfg, gemm_mode=P.MODE_BF16X3, use_cuda_graphs=True)
+        opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
+        side = torch.cuda.Stream()
+        a = torch.randn(8192, 8192, device=DEV, dtype=torch.bfloat16)
+        out = []
+        for step in range(6):
+            if hog:
+                with torch.cuda.stream(side):
+                    for _ in range(4):
+                        a @ a                                   # ~0.7 ms each on all SMs, beside the step
+            out.append(m.train_step(x.to(DEV), idx.to(DEV), nsegs.to(DEV), opt, 10.0, eps=eps).clone())
+        torch.cuda.synchronize()
+        return torch.stack(out).cpu()
+
+    alone, hogged = losses(False), losses(True)
+    assert_close(hogged, alone, 1e-5, "losses beside SM-hogging kernels")
