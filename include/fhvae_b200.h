@@ -342,6 +342,12 @@ int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* dh_last_top
                                void* dg_top_planes, void* dg_bot_planes, int64_t plane_stride, const void* packed,
                                int T, int B, int H, int nlayers, int mode, void* stream);
 
+/* out[0..n) ~ N(0,1): the eps draws of GaussianLayer.forward (torch.randn_like, simple_fhvae.py:214) as a kernel of this
+ * library (Philox4x32-10 keyed by `seed`, Box-Muller).  `offset` is a DEVICE counter (zero-initialised by the caller)
+ * that the launch advances, so replays of a captured launch draw fresh numbers; `done_counter`: zero-initialised
+ * device uint32 scratch.  Not bit-compatible with torch's generator (nothing in the reference pins the draws). */
+int fhvae_randn(float* out, int64_t n, uint64_t seed, unsigned long long* offset, uint32_t* done_counter, void* stream);
+
 /* x (B,T,F), mu_idx (B int64, may be NULL), num_segs (B int64, may be NULL) -> the step's static input buffers, one
  * launch (device-to-device; the batch of train_model.py:444-445 into CUDA-graph-stable storage).  x is also written
  * time-major (T,B,F) into x_tm when x_tm != NULL (what fhvae_transpose_bt does as a separate launch). */

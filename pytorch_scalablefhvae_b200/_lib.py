@@ -86,6 +86,7 @@ PROTOTYPES = {
     "fhvae_mu2_estimate_finish": [_p, _p, _p, _f, _l, _i, _p],
     "fhvae_rows_copy": [_p, _p, _p, _p, _l, _i, _p],
     "fhvae_adam_flat": [_p, _p, _p, _p, _l, _f, _f, _f, _f, _f, _p, _p, _p],
+    "fhvae_randn": [_p, _l, C.c_uint64, _p, _p, _p],
     "fhvae_transpose_bt": [_p, _p, _i, _i, _i, _p],
     "fhvae_gather_segments": [_p, _p, _p, _p, _p, _i, _i, _i, _l, _p],
     "fhvae_colsum_batch": [C.POINTER(ColsumProblem), _i, _p],

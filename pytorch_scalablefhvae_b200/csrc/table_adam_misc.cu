@@ -161,6 +161,50 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     }
 }
 
+// ---------------------------------------------------------------- eps ~ N(0,1) -------------------
+// torch.randn_like of GaussianLayer.forward (simple_fhvae.py:214) as a kernel of this library, so that the draw is a
+// node of the step's CUDA graph instead of an ATen launch in front of it.  Philox4x32-10 (counter = element group,
+// key = seed; the per-launch offset lives in a DEVICE counter that the last CTA bumps, so every replay of a captured
+// launch draws fresh numbers) + Box-Muller.  Not bit-compatible with torch's generator (nothing in the reference pins
+// the draws; parity tests inject eps).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += 0x9E3779B9u;
+        key.y += 0xBB67AE85u;
+    }
+    return ctr;
+}
+__global__ void __launch_bounds__(256) randn_kernel(float* __restrict__ out, int64_t n, uint64_t seed,
+                                                    unsigned long long* __restrict__ offset, uint32_t* __restrict__ done) {
+    const unsigned long long off = *reinterpret_cast<volatile unsigned long long*>(offset);
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;           // one group of 4 normals per thread
+    if (g * 4 < n) {
+        const unsigned long long c = off + (unsigned long long)g;
+        const uint4 r = philox4x32_10(make_uint4((uint32_t)c, (uint32_t)(c >> 32), 0u, 0u),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        const float k = 2.3283064365386963e-10f;                                 // 2^-32
+        const float u0 = ((float)r.x + 0.5f) * k, u1 = ((float)r.y + 0.5f) * k;
+        const float u2 = ((float)r.z + 0.5f) * k, u3 = ((float)r.w + 0.5f) * k;
+        const float ra = sqrtf(-2.f * logf(fminf(u0, 0.99999994f))), rb = sqrtf(-2.f * logf(fminf(u2, 0.99999994f)));
+        float s0, c0, s1, c1;
+        sincospif(2.f * u1, &s0, &c0);
+        sincospif(2.f * u3, &s1, &c1);
+        const float v[4] = {ra * c0, ra * s0, rb * c1, rb * s1};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (g * 4 + i < n) out[g * 4 + i] = v[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {                      // the last CTA to finish advances the stream (every CTA has read it)
+        __threadfence();
+        if (atomicInc(done, gridDim.x - 1) == gridDim.x - 1) *offset = off + (unsigned long long)((n + 3) / 4);
+    }
+}
+
 // ---------------------------------------------------------------- helpers ------------------------
 __global__ void transpose_bt_kernel(const float* __restrict__ src, float* __restrict__ dst, int B, int T,
                                     int F) {
@@ -401,5 +445,13 @@ extern "C" int fhvae_axpy(float* y, const float* x, float a, int64_t n, void* st
     FHVAE_CHECK_ARG(y && x && n > 0, "axpy: bad argument");
     axpy_kernel<<<cdiv(n, 256), 256, 0, as_stream(stream)>>>(y, x, a, n);
     FHVAE_LAUNCH_CHECK("axpy");
+    return 0;
+}
+
+extern "C" int fhvae_randn(float* out, int64_t n, uint64_t seed, unsigned long long* offset, uint32_t* done_counter,
+                           void* stream) {
+    FHVAE_CHECK_ARG(out && offset && done_counter && n > 0, "randn: bad argument");
+    randn_kernel<<<cdiv((n + 3) / 4, 256), 256, 0, as_stream(stream)>>>(out, n, seed, offset, done_counter);
+    FHVAE_LAUNCH_CHECK("randn");
     return 0;
 }

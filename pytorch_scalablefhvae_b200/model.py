@@ -380,6 +380,14 @@ class _Plan:
         self.nsegs = torch.ones(B, dtype=torch.int64, device=self.dev)
         self.eps_all = f(B * (Z1 + Z2))                # [eps2 | eps1]: one normal_() launch draws both
         self.eps2, self.eps1 = self.eps_all[:B * Z2].view(B, Z2), self.eps_all[B * Z2:].view(B, Z1)
+        # eps ~ N(0,1) (torch.randn_like, simple_fhvae.py:214; z2 first, then z1) drawn by the library's own Philox kernel
+        # as the first node of the step: seeded from torch's generator when the plan is built, advanced on the device
+        self._rng_state = torch.zeros(2, dtype=torch.int64, device=self.dev)       # [offset, done counter]
+        self._rng_seed = (int(torch.initial_seed()) * 0x9E3779B97F4A7C15 + B * 1000003 + T * 10007 + F) & (2 ** 64 - 1)
+        self._draw = True
+        self.rng = CallList()
+        self.rng.add("fhvae_randn", ptr(self.eps_all), self.eps_all.numel(), self._rng_seed, ptr(self._rng_state),
+                     ptr(self._rng_state, 1))
         # forward state
         self.z1head, self.z2head = f(B, 2 * Z1), f(B, 2 * Z2)
         self.zcat = f(B, Z1 + Z2)                     # [z1_sample | z2_sample]
@@ -433,17 +441,24 @@ class _Plan:
         if eps is not None:
             self.eps1.copy_(eps["z1"].reshape(self.eps1.shape), non_blocking=True)
             self.eps2.copy_(eps["z2"].reshape(self.eps2.shape), non_blocking=True)
-        else:                                        # torch.randn_like, simple_fhvae.py:214 (z2 first, then z1)
-            self.eps_all.normal_()
+        self._draw = eps is None                     # True: the step itself draws eps (self.rng, first node of the graph)
 
     # ---- execution
     def run_forward(self):
+        draw = self._draw
+
+        def body():
+            if draw:
+                self.rng.run(current_stream_ptr())
+            self.fwd.run(current_stream_ptr())
         if self.m.use_cuda_graphs:
             if self._graph_fwd is None:
-                self._graph_fwd = self._capture(lambda: self.fwd.run(current_stream_ptr()))
-            self._graph_fwd.replay()
+                self._graph_fwd = {}
+            if draw not in self._graph_fwd:
+                self._graph_fwd[draw] = self._capture(body)
+            self._graph_fwd[draw].replay()
         else:
-            self.fwd.run(current_stream_ptr())
+            body()
 
     def run_encode(self):
         """Replay only the encoder prefix of the forward list (marked by ``n_encode_calls``)."""
@@ -509,7 +524,11 @@ class _Plan:
 
         fwd_list, bwd_list = self._train_lists(k)
 
+        draw = self._draw
+
         def fwd_bwd():
+            if draw:
+                self.rng.run(current_stream_ptr())
             fwd_list.run(current_stream_ptr())
             loss_call.run(current_stream_ptr(), join=False)   # side stream 1, beside the backward list ...
             bwd_list.run(current_stream_ptr())
@@ -529,7 +548,7 @@ class _Plan:
         else:
             # the captured Adam launch bakes its hyper-parameters in: a changed lr / betas / eps / grad_scale
             # (LR scheduler, load_state_dict, a DataParallel wrapper created later) re-captures
-            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key())
+            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key(), draw)
             graphs = self.__dict__.setdefault("_train_graphs", {})
             if key not in graphs:
                 optimizer._state_for(m)               # allocate Adam state outside capture
@@ -566,7 +585,8 @@ class _Plan:
             self.gout[5].fill_(-alpha / B)
             self._gout_train = (alpha, B)
             self._gout_rows = None
-        ov = self.__dict__.get("_ovl")
+        draw = self._draw
+        ov = self.__dict__.get("_ovl", {}).get(draw)
         if ov is None or ov["key"] != (alpha, id(optimizer), optimizer.hyper_key()):
             fwd, bwd = self._train_lists(k)
             jD = max(i for i, c_ in enumerate(bwd.calls) if c_[1] == "join" and c_[2] == 2)
@@ -581,7 +601,8 @@ class _Plan:
                 return cl
             lc = CallList()
             lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss))
-            A = mk(fwd.calls + lc.calls + head[:iM + 1] + [(None, "join", 2, 0)], fwd.keep + bwd.keep)
+            A = mk((self.rng.calls if draw else []) + fwd.calls + lc.calls + head[:iM + 1] + [(None, "join", 2, 0)],
+                   fwd.keep + bwd.keep)
             Wl = mk(tail, bwd.keep)
             Bl = mk(bwd.calls[jD + 1:], bwd.keep)
             optimizer._state_for(m)
@@ -597,7 +618,7 @@ class _Plan:
                 with torch.cuda.graph(g_, stream=s_):
                     f()
                 return g_
-            ov = self._ovl = dict(key=(alpha, id(optimizer), optimizer.hyper_key()),
+            ov = self.__dict__.setdefault("_ovl", {})[draw] = dict(key=(alpha, id(optimizer), optimizer.hyper_key()),
                                   gA=cap(lambda: A.run(current_stream_ptr())), gW=cap(lambda: Wl.run(current_stream_ptr())),
                                   gB=cap(lambda: Bl.run(current_stream_ptr())),
                                   gC=cap(lambda: optimizer.step_flat(m, gflat)), side=torch.cuda.Stream())
@@ -704,6 +725,8 @@ class _Plan:
                 return
 
             def body():
+                if i == 0 and draw:
+                    self.rng.run(current_stream_ptr())
                 segs[i].run(current_stream_ptr())
                 if extra is not None:
                     extra.run(current_stream_ptr())
@@ -712,7 +735,7 @@ class _Plan:
             # each segment is captured once, without a warm-up run, and replayed.
             if not m.use_cuda_graphs or not sh.get("warm"):
                 return body()
-            key = ("seg", i, alpha)
+            key = ("seg", i, alpha, draw if i == 0 else None)
             if key not in sh["graphs"]:
                 s_ = torch.cuda.Stream(priority=-1)
                 s_.wait_stream(torch.cuda.current_stream())
@@ -722,6 +745,7 @@ class _Plan:
                 sh["graphs"][key] = g_
             sh["graphs"][key].replay()
 
+        draw = self._draw
         main, D = torch.cuda.current_stream(), sh["stream"]
         ev = lambda s: (lambda e: (e.record(s), e)[1])(torch.cuda.Event())
 
