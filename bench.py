@@ -255,6 +255,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--mode", default=os.environ.get("FHVAE_MODE", "bf16x3"), choices=["f32", "bf16x3", "bf16"])
     ap.add_argument("--config", default="c1", choices=["c0", "c1", "c3", "c4"])
+    ap.add_argument("--hidden", type=int, default=None, help="c1 only: LSTM width instead of 256 (the reference CLI default is 128)")
+    ap.add_argument("--zdim", type=int, default=None, help="c1 only: z1/z2 dimension instead of 32 (reference CLI default 16)")
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--overlap", action="store_true", help="N>1: all-reduce [z1 enc + decoder + table] beside the z2 BPTT "
                                                            "(default: ONE all-reduce between backward and Adam, measured faster)")
@@ -264,6 +266,10 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.hidden is not None:
+        CFG["H"] = args.hidden
+    if args.zdim is not None:
+        CFG["Z"] = args.zdim
     if args.impl == "reference":
         run_reference(args, rank, world)
         return

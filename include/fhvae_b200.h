@@ -101,7 +101,7 @@ int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
                    int T, int B, int H, int mode, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Layer-wavefront recurrence over a stack of 1 or 2 LSTM layers in ONE launch (H == 256, B % 32 == 0,
+ * Layer-wavefront recurrence over a stack of 1 or 2 LSTM layers in ONE launch (H in {128, 256}: groups of H/32 CTAs; B % 32 == 0,
  * T <= 63, tensor-core modes only).  Layer 1 runs one step behind layer 0 and computes its own input
  * projection  h0_t W_ih1^T + bias1  from the words layer 0 publishes, so the (T,B,4H) projection buffer and
  * the projection GEMM of layer 1 do not exist.  Replaces the nn.LSTM(num_layers=2) forward of the

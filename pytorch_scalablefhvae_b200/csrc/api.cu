@@ -35,17 +35,17 @@ int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_h
                      cudaStream_t st);
 
 bool lstm_wave_supported(int T, int B, int H, int L);
-size_t lstm_wave_xchg_bytes(int T, int B, int L);
+size_t lstm_wave_xchg_bytes(int T, int B, int H, int L);
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
-                  void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0 = nullptr, void* hp1 = nullptr,
+                  void* xchg, int T, int B, int H, int L, int mode, cudaStream_t st, void* hp0 = nullptr, void* hp1 = nullptr,
                   long long hps = 0, const void* packed = nullptr);
-size_t lstm_wave_pack_bytes(int L, int mode);
-int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int L, int mode, cudaStream_t st);
-size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L);
+size_t lstm_wave_pack_bytes(int H, int L, int mode);
+int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int H, int L, int mode, cudaStream_t st);
+size_t lstm_wave_bwd_xchg_bytes(int T, int B, int H, int L);
 int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
                   const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
-                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st,
+                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int H, int L, int mode, cudaStream_t st,
                   void* dgp1 = nullptr, void* dgp0 = nullptr, long long dgps = 0, const void* packed = nullptr);
 
 }  // namespace fhvae
@@ -115,7 +115,7 @@ extern "C" int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int m
 
 extern "C" long long fhvae_lstm_wave_xchg_bytes(int T, int B, int H, int nlayers) {
     if (!lstm_wave_supported(T, B, H, nlayers)) return 0;
-    return (long long)lstm_wave_xchg_bytes(T, B, nlayers);
+    return (long long)lstm_wave_xchg_bytes(T, B, H, nlayers);
 }
 
 extern "C" int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0,
@@ -123,10 +123,10 @@ extern "C" int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float
                                    float* h1, float* c1, float* acts1, void* xchg, int T, int B, int H,
                                    int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
-                    "lstm_wave_fwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+                    "lstm_wave_fwd: needs a tensor-core mode, H in {128, 256}, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh0 && h0 && c0 && acts0 && xchg && (P0 || Q0), "lstm_wave_fwd: null pointer (layer 0)");
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih1 && W_hh1 && h1 && c1 && acts1), "lstm_wave_fwd: null pointer (layer 1)");
-    return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, nlayers,
+    return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, H, nlayers,
                          mode, as_stream(stream));
 }
 
@@ -136,30 +136,30 @@ extern "C" int fhvae_lstm_wave_fwd_planes(const float* P0, const float* Q0, cons
                                           void* h1_planes, int64_t plane_stride, const void* packed, int T, int B, int H,
                                           int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
-                    "lstm_wave_fwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+                    "lstm_wave_fwd: needs a tensor-core mode, H in {128, 256}, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh0 && h0 && c0 && acts0 && xchg && (P0 || Q0), "lstm_wave_fwd: null pointer (layer 0)");
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih1 && W_hh1 && h1 && c1 && acts1), "lstm_wave_fwd: null pointer (layer 1)");
-    return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, nlayers,
+    return lstm_wave_fwd(P0, Q0, W_hh0, h0, c0, acts0, W_ih1, bias1, W_hh1, h1, c1, acts1, xchg, T, B, H, nlayers,
                          mode, as_stream(stream), h0_planes, nlayers == 2 ? h1_planes : nullptr, plane_stride, packed);
 }
 
 extern "C" long long fhvae_lstm_wave_pack_bytes(int H, int nlayers, int mode) {
     if (!fhvae_lstm_wave_supported(1, WAVE_MIN_B, H, nlayers, mode)) return 0;
-    return (long long)lstm_wave_pack_bytes(nlayers, mode);
+    return (long long)lstm_wave_pack_bytes(H, nlayers, mode);
 }
 
 extern "C" int fhvae_lstm_wave_pack(const float* W_hh0, const float* W_ih1, const float* W_hh1, void* packed, int H,
                                     int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(1, WAVE_MIN_B, H, nlayers, mode),
-                    "lstm_wave_pack: needs a tensor-core mode, H == 256, 1 or 2 layers");
+                    "lstm_wave_pack: needs a tensor-core mode, H in {128, 256}, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh0 && packed && (nlayers == 1 || (W_ih1 && W_hh1)), "lstm_wave_pack: null pointer");
     FHVAE_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "lstm_wave_pack: the image buffer must be 128-byte aligned");
-    return lstm_wave_pack(W_hh0, W_ih1, W_hh1, packed, nlayers, mode, as_stream(stream));
+    return lstm_wave_pack(W_hh0, W_ih1, W_hh1, packed, H, nlayers, mode, as_stream(stream));
 }
 
 extern "C" long long fhvae_lstm_wave_bwd_xchg_bytes(int T, int B, int H, int nlayers) {
     if (!lstm_wave_supported(T, B, H, nlayers)) return 0;
-    return (long long)lstm_wave_bwd_xchg_bytes(T, B, nlayers);
+    return (long long)lstm_wave_bwd_xchg_bytes(T, B, H, nlayers);
 }
 
 extern "C" int fhvae_lstm_wave_bwd(const float* dh_all_top, const float* dh_last_top, const float* dh_last_bot,
@@ -168,13 +168,13 @@ extern "C" int fhvae_lstm_wave_bwd(const float* dh_all_top, const float* dh_last
                                    const float* acts_bot, float* dgates_bot, float* dgsum_bot, void* xchg, int T, int B,
                                    int H, int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
-                    "lstm_wave_bwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+                    "lstm_wave_bwd: needs a tensor-core mode, H in {128, 256}, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh_top && c_top && acts_top && dgates_top && xchg, "lstm_wave_bwd: null pointer (top layer)");
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih_top && W_hh_bot && c_bot && acts_bot && dgates_bot),
                     "lstm_wave_bwd: null pointer (bottom layer)");
     FHVAE_CHECK_ARG(dh_all_top || dh_last_top || (nlayers == 2 && dh_last_bot), "lstm_wave_bwd: no incoming gradient");
     return lstm_wave_bwd(dh_all_top, dh_last_top, dh_last_bot, W_hh_top, c_top, acts_top, dgates_top, dgsum_top, W_ih_top,
-                         W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, nlayers, mode, as_stream(stream));
+                         W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, H, nlayers, mode, as_stream(stream));
 }
 
 extern "C" int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* dh_last_top, const float* dh_last_bot,
@@ -185,13 +185,13 @@ extern "C" int fhvae_lstm_wave_bwd_planes(const float* dh_all_top, const float* 
                                           void* dg_bot_planes, int64_t plane_stride, const void* packed, int T, int B, int H,
                                           int nlayers, int mode, void* stream) {
     FHVAE_CHECK_SUP(fhvae_lstm_wave_supported(T, B, H, nlayers, mode),
-                    "lstm_wave_bwd: needs a tensor-core mode, H == 256, B %% 32 == 0, T <= 63, 1 or 2 layers");
+                    "lstm_wave_bwd: needs a tensor-core mode, H in {128, 256}, B %% 32 == 0, T <= 63, 1 or 2 layers");
     FHVAE_CHECK_ARG(W_hh_top && c_top && acts_top && (dgates_top || dg_top_planes) && xchg,
                     "lstm_wave_bwd: null pointer (top layer)");
     FHVAE_CHECK_ARG(nlayers == 1 || (W_ih_top && W_hh_bot && c_bot && acts_bot && (dgates_bot || dg_bot_planes)),
                     "lstm_wave_bwd: null pointer (bottom layer)");
     FHVAE_CHECK_ARG(dh_all_top || dh_last_top || (nlayers == 2 && dh_last_bot), "lstm_wave_bwd: no incoming gradient");
     return lstm_wave_bwd(dh_all_top, dh_last_top, dh_last_bot, W_hh_top, c_top, acts_top, dgates_top, dgsum_top, W_ih_top,
-                         W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, nlayers, mode, as_stream(stream),
+                         W_hh_bot, c_bot, acts_bot, dgates_bot, dgsum_bot, xchg, T, B, H, nlayers, mode, as_stream(stream),
                          dg_top_planes, nlayers == 2 ? dg_bot_planes : nullptr, plane_stride, packed);
 }

@@ -187,40 +187,41 @@ extern "C" int fhvae_debug_wave_timeline(long long* out) { return (int)cudaMemcp
 //   S images (the UMMA no-swizzle K-major shared-memory operand, 64 KB per part): copied verbatim by cp.async.bulk.
 // Order in the buffer: fwdT[layer][rank], fwdS[rank] (2-layer stacks), bwdT[layer][rank], bwdS[rank].
 // ================================================================================================
-template <bool X3> struct WavePack {
-    static constexpr size_t IMG = (X3 ? 2 : 1) * 65536;
-    __host__ __device__ static constexpr int n_images(int L) { return 16 * L + (L == 2 ? 16 : 0); }
-    __host__ __device__ static constexpr size_t fwdT(int L, int layer, int rank) { return (size_t)(layer * WG + rank) * IMG; }
-    __host__ __device__ static constexpr size_t fwdS(int L, int rank) { return (size_t)(L * WG + rank) * IMG; }
+template <bool X3, int CH = WH> struct WavePack {
+    static constexpr int NG = CH / WU, HF = CH / 128;                  // CTAs per group, 128-unit halves
+    static constexpr size_t IMG = (size_t)(X3 ? 2 : 1) * HF * 32768;   // every image: parts x CH x 128 bf16
+    __host__ __device__ static constexpr int n_images(int L) { return 2 * NG * L + (L == 2 ? 2 * NG : 0); }
+    __host__ __device__ static constexpr size_t fwdT(int L, int layer, int rank) { return (size_t)(layer * NG + rank) * IMG; }
+    __host__ __device__ static constexpr size_t fwdS(int L, int rank) { return (size_t)(L * NG + rank) * IMG; }
     __host__ __device__ static constexpr size_t bwdT(int L, int layer, int rank) {
-        return (size_t)(L * WG + (L == 2 ? WG : 0) + layer * WG + rank) * IMG;
+        return (size_t)(L * NG + (L == 2 ? NG : 0) + layer * NG + rank) * IMG;
     }
-    __host__ __device__ static constexpr size_t bwdS(int L, int rank) { return (size_t)(2 * L * WG + WG + rank) * IMG; }
+    __host__ __device__ static constexpr size_t bwdS(int L, int rank) { return (size_t)(2 * L * NG + NG + rank) * IMG; }
 };
 
 struct WavePackArgs { const float* Whh[2]; const float* Wih1; uint8_t* out; int L; };
 
-template <bool X3>
+template <bool X3, int CH>
 __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ WavePackArgs a) {
-    using PK = WavePack<X3>;
-    constexpr int CH = WH, UC = WU, NC = WNC, NT = WNT;
+    using PK = WavePack<X3, CH>;
+    constexpr int UC = WU, NC = WNC, NT = WNT, WG = CH / WU, HF = CH / 128, KQ = CH / 4;   // KQ: k-values per column group
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, cg = (warp >> 2) & 3;
     const int L = a.L;
     int img = blockIdx.x;
     const int nT = L * WG, nS = (L == 2) ? WG : 0;
-    auto store_T = [&](uint8_t* dst, const uint32_t (&w)[32], int part) {     // 32 words: [hf 2][16]
-        uint4* o = reinterpret_cast<uint4*>(dst) + (size_t)(warp * (X3 ? 16 : 8) + part * 8) * 32 + lane;
+    auto store_T = [&](uint8_t* dst, const uint32_t (&w)[HF * 16], int part) {     // HF*16 words: [hf][16]
+        uint4* o = reinterpret_cast<uint4*>(dst) + (size_t)(warp * ((X3 ? 2 : 1) * HF * 4) + part * HF * 4) * 32 + lane;
 #pragma unroll
-        for (int v = 0; v < 8; ++v) o[v * 32] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+        for (int v = 0; v < HF * 4; ++v) o[v * 32] = make_uint4(w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
     };
     if (img < nT) {
         // ---- forward TMEM image: lane n = gate q * 32 + unit, 32-bit column c = (k, k+1) pair, k = 2c
         const int layer = img / WG, rank = img % WG;
-        const float* src = a.Whh[layer] + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
-        uint32_t hi[32], lo[32];
+        const float* src = a.Whh[layer] + (size_t)(q * CH + rank * UC + lane) * CH + cg * KQ;
+        uint32_t hi[HF * 16], lo[HF * 16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < KQ / 4; ++i) {
             const float4 w4 = __ldg(reinterpret_cast<const float4*>(src) + i);
             const float v[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
@@ -237,32 +238,32 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
     }
     img -= nT;
     if (img < nS) {
-        // ---- forward shared-memory image of the W_ih1 slice: [part][K chunk 32][row 128] x 16 B
+        // ---- forward shared-memory image of the W_ih1 slice: [part][K chunk CH/8][row 128] x 16 B
         const int rank = img;
-        const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+        const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * KQ;
         const int r = q * 32 + lane;
         uint8_t* dst = a.out + PK::fwdS(L, rank);
 #pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < KQ / 8; ++i) {
             const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
             const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
             const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-            const uint32_t off = (uint32_t)(cg * 8 + i) * (NC * 16) + (uint32_t)r * 16;
+            const uint32_t off = (uint32_t)(cg * (KQ / 8) + i) * (NC * 16) + (uint32_t)r * 16;
             uint4 hi, lo;
             split_bf16(v, hi, lo);
             *reinterpret_cast<uint4*>(dst + off) = hi;
-            if (X3) *reinterpret_cast<uint4*>(dst + 65536 + off) = lo;
+            if (X3) *reinterpret_cast<uint4*>(dst + PK::IMG / 2 + off) = lo;
         }
         return;
     }
     img -= nS;
     if (img < nT) {
-        // ---- BPTT TMEM image of W_hh^T: lane = unit n (two halves of 128), column = pair of the CTA's 128 gate columns
+        // ---- BPTT TMEM image of W_hh^T: lane = unit n (HF halves of 128), column = pair of the CTA's 128 gate columns
         const int layer = img / WG, rank = img % WG, g = cg;
         const float* W = a.Whh[layer];
-        uint32_t hi[32], lo[32];
+        uint32_t hi[HF * 16], lo[HF * 16];
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int hf = 0; hf < HF; ++hf) {
             const int n = hf * 128 + q * 32 + lane;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
@@ -280,14 +281,14 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
     }
     img -= nT;
     {
-        // ---- BPTT shared-memory image of W_ih1^T: [part][unit half 2][K chunk 16][unit 128] x 16 B
+        // ---- BPTT shared-memory image of W_ih1^T: [part][unit half HF][K chunk 16][unit 128] x 16 B
         const int rank = img;
         uint8_t* dst = a.out + PK::bwdS(L, rank);
         constexpr int WIT = CH * (NC / 8) / NT;
 #pragma unroll 2
         for (int i = 0; i < WIT; ++i) {
             const int item = tid + i * NT;
-            const int n = item & (CH - 1), kc = item >> 8;
+            const int n = item % CH, kc = item / CH;
             float v[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -298,23 +299,23 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
             uint4 hi, lo;
             split_bf16(v, hi, lo);
             *reinterpret_cast<uint4*>(dst + off) = hi;
-            if (X3) *reinterpret_cast<uint4*>(dst + 65536 + off) = lo;
+            if (X3) *reinterpret_cast<uint4*>(dst + PK::IMG / 2 + off) = lo;
         }
     }
 }
 
-// packed T image -> this thread's TMEM columns: 8 coalesced 16-byte loads + 2 tcgen05.st.x16 per bf16 part
-template <bool X3>
+// packed T image -> this thread's TMEM columns: HF*4 coalesced 16-byte loads + HF tcgen05.st.x16 per bf16 part
+template <bool X3, int HF>
 __device__ __forceinline__ void wave_load_T_image(const uint8_t* img, int warp, int lane, uint32_t ta, uint32_t half_stride,
                                                   uint32_t part_stride) {
 #pragma unroll
     for (int part = 0; part < (X3 ? 2 : 1); ++part) {
-        const uint4* src = reinterpret_cast<const uint4*>(img) + (size_t)(warp * (X3 ? 16 : 8) + part * 8) * 32 + lane;
-        uint4 u[8];
+        const uint4* src = reinterpret_cast<const uint4*>(img) + (size_t)(warp * ((X3 ? 2 : 1) * HF * 4) + part * HF * 4) * 32 + lane;
+        uint4 u[HF * 4];
 #pragma unroll
-        for (int v = 0; v < 8; ++v) u[v] = __ldg(src + v * 32);
+        for (int v = 0; v < HF * 4; ++v) u[v] = __ldg(src + v * 32);
 #pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
+        for (int hf = 0; hf < HF; ++hf) {
             const uint32_t w[16] = {u[4 * hf].x,     u[4 * hf].y,     u[4 * hf].z,     u[4 * hf].w,
                                     u[4 * hf + 1].x, u[4 * hf + 1].y, u[4 * hf + 1].z, u[4 * hf + 1].w,
                                     u[4 * hf + 2].x, u[4 * hf + 2].y, u[4 * hf + 2].z, u[4 * hf + 2].w,
@@ -338,23 +339,23 @@ struct WaveFwdArgs {
     const uint8_t* packed;          // optional pre-packed operand images of the weights (wave_pack_kernel); NULL: convert here
 };
 
-template <bool X3>
+template <bool X3, int CH = WH>
 struct WaveFwdSmem {
-    static constexpr int H_PART = WNB * WH * 2;                // 32 x 256 bf16 = 16 KB
+    static constexpr int H_PART = WNB * CH * 2;                // 32 x 256 bf16 = 16 KB
     static constexpr int H_BUF = (X3 ? 2 : 1) * H_PART;
     static constexpr int H_OFF = 0;                            // h_{t-1} operand, double-buffered
     static constexpr int G_OFF = 2 * H_BUF;
     static constexpr int G_BYTES = 4 * WNB * (WU + 1) * 4;     // gates[4][NB][33] fp32
     static constexpr int BAR_OFF = G_OFF + G_BYTES;
     static constexpr int W_OFF = (BAR_OFF + 256 + 1023) / 1024 * 1024;
-    static constexpr int W_PART = WNC * WH * 2;                // 128 x 256 bf16 = 64 KB
+    static constexpr int W_PART = WNC * CH * 2;                // 128 x 256 bf16 = 64 KB
     static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
     static constexpr int TOTAL1 = W_OFF;                       // single layer: no resident W_ih
     static constexpr int TOTAL2 = W_OFF + W_BYTES;
 };
 
 // pull NS slices (all 8, or the 7 peers) of one published step into an MMA operand buffer
-template <bool X3, int NS, bool SKIP_OWN>
+template <bool X3, int CH, int NS, bool SKIP_OWN>
 __device__ __forceinline__ void wave_load(const uint4* slot, int rank, uint4 (&v)[NS], uint32_t flag) {
     constexpr int NW = (X3 ? 2 : 1) * 256;
     if ((int)threadIdx.x < NW) {
@@ -373,9 +374,9 @@ __device__ __forceinline__ void wave_load(const uint4* slot, int rank, uint4 (&v
         }
     }
 }
-template <bool X3, int NS, bool SKIP_OWN>
+template <bool X3, int CH, int NS, bool SKIP_OWN>
 __device__ __forceinline__ void wave_store(const uint4* slot, int rank, uint32_t flag, uint4 (&v)[NS], uint8_t* dst) {
-    using S = WaveFwdSmem<X3>;
+    using S = WaveFwdSmem<X3, CH>;
     constexpr int NW = (X3 ? 2 : 1) * 256;
     const int tid = threadIdx.x;
     if (tid < NW) {
@@ -399,17 +400,18 @@ __device__ __forceinline__ void bar_compute() { asm volatile("bar.sync 1, %0;" :
 // issued by the dedicated MMA warp behind the recurrent MMAs and published as LL words; layer 1 consumes it
 // exactly like layer 0 consumes the GEMM-produced P0.  Warps 0..15 = gate/cell math + exchange, warp 16 =
 // tcgen05 issuer (so the ~2000-cycle SS-mode projection never blocks a compute warp).
-template <bool X3>
+template <bool X3, int CH_>
 __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_constant__ WaveFwdArgs a) {
-    using S = WaveFwdSmem<X3>;
-    constexpr int NB = WNB, NT = WNT, CH = WH, UC = WU;
+    using S = WaveFwdSmem<X3, CH_>;
+    constexpr int NB = WNB, NT = WNT, CH = CH_, UC = WU;
+    constexpr int WG = CH / WU, HF = CH / 128, KQ = CH / 4;   // CTAs per group (shadows the H = 256 constant), 128-k halves, k per column group
     constexpr int NW = (X3 ? 2 : 1) * 256;     // LL words of one slice actually used
     constexpr int NCG = NT / 128;              // column groups: warps sharing one TMEM lane quarter
     constexpr int CPW = NB / NCG;              // batch rows (TMEM columns) per thread in the gate phase
     constexpr int RPT = NB * 32 / NT;          // batch rows per thread in the cell phase
     constexpr int H4 = 4 * CH;
     static_assert(CPW == 8 && RPT == 2, "LL packing of P1 assumes 8 rows per thread");
-    static_assert(WH / 16 == 2 * WG, "two K=16 steps per exchanged slice");
+    static_assert(CH / 16 == 2 * WG, "two K=16 steps per exchanged slice");
     extern __shared__ __align__(1024) uint8_t smem[];
     float (*gates)[NB][UC + 1] = reinterpret_cast<float (*)[NB][UC + 1]>(smem + S::G_OFF);
     uint64_t* hb_full = reinterpret_cast<uint64_t*>(smem + S::BAR_OFF);   // [2 buffers] compute warps -> issuer
@@ -456,7 +458,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         *epoch_slot = *cnt;
         *p1_safe = 0;
         if (p1_duty && a.packed)
-            wave_load_S_image(a.packed + WavePack<X3>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
+            wave_load_S_image(a.packed + WavePack<X3, CH>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
     tc_fence_before();
     __syncthreads();
@@ -571,16 +573,16 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         // ================= compute warps =================
         reg_inc<112>();   // 20 warps x 96 regs at launch = 16 x 112 + 4 x 32 (setmaxnreg only moves registers inside the CTA)
         WTL(4, 15);
-        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
+        const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * (KQ / 2));
         if (a.packed) {
-            wave_load_T_image<X3>(a.packed + WavePack<X3>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
+            wave_load_T_image<X3, HF>(a.packed + WavePack<X3, CH>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
         } else {
-            const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
-            float4 wv[16];
+            const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * KQ;
+            float4 wv[KQ / 4];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = 0; i < KQ / 4; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
 #pragma unroll
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < HF; ++hf) {
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -601,14 +603,14 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         WTL(5, 15);
         if (p1_duty && !a.packed) {
             // resident W_ih1 slice as an smem A operand: row n = gate*32 + unit, K-chunk planes of W_LBO bytes
-            const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
+            const float* s1 = a.Wih1 + (size_t)(q * CH + rank * UC + lane) * CH + cg * KQ;
             const int r = q * 32 + lane;
 #pragma unroll 2
-            for (int i = 0; i < 8; ++i) {
+            for (int i = 0; i < KQ / 8; ++i) {
                 const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
                 const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
                 const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
-                const uint32_t off = (uint32_t)(cg * 8 + i) * W_LBO + (uint32_t)r * 16;
+                const uint32_t off = (uint32_t)(cg * (KQ / 8) + i) * W_LBO + (uint32_t)r * 16;
                 if (X3) {
                     uint4 hi, lo;
                     split_bf16(v, hi, lo);
@@ -687,7 +689,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             if (t > 0) {
                 // h_{t-1}: the 7 peer slices (own slice was written locally by the cell phase)
                 const uint4* slot = own + (size_t)(t - 1) * (WG * WSLICE);
-                uint4 hv[7];
+                uint4 hv[WG - 1];
 #if WAVE_SAVE_FIRST
                 store_saved(t - 1);
 #endif
@@ -702,9 +704,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                 }
                 bar_compute();
 #endif
-                wave_load<X3, 7, true>(slot, rank, hv, fbase + t);
+                wave_load<X3, CH, WG - 1, true>(slot, rank, hv, fbase + t);
                 WTL(t, 6);
-                wave_store<X3, 7, true>(slot, rank, fbase + t, hv, hbt);
+                wave_store<X3, CH, WG - 1, true>(slot, rank, fbase + t, hv, hbt);
                 WTL(t, 7);
                 fence_proxy_async();         // also covers this thread's own-slice stores of the previous cell phase
                 tc_fence_before();
@@ -865,7 +867,7 @@ __device__ __forceinline__ void bar_chain(int ch) { asm volatile("bar.sync %0, 2
 
 template <bool X3>
 __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_constant__ WaveFwdArgs a) {
-    using S = WaveFwdSmem<X3>;
+    using S = WaveFwdSmem<X3, WH>;
     constexpr int NB = WNB, NT = WNT, CH = WH, UC = WU, NBC = WNB / 2;
     constexpr int NWC = (X3 ? 2 : 1) * 128;    // LL words of one slice that belong to one chain
     constexpr int CPW = 8, RPT = 2, H4 = 4 * CH;
@@ -1007,7 +1009,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
         reg_inc<112>();
         const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 32);
         if (a.packed) {
-            wave_load_T_image<X3>(a.packed + WavePack<X3>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
+            wave_load_T_image<X3, 2>(a.packed + WavePack<X3>::fwdT(a.L, layer, rank), warp, lane, ta, 16, WCOLS);
         } else {
             const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
             float4 wv[16];
@@ -1252,7 +1254,7 @@ struct WaveBwdArgs {
     const uint8_t* packed;          // optional pre-packed operand images of the weights (wave_pack_kernel)
 };
 
-template <bool X3>
+template <bool X3, int CH = WH>
 struct WaveBwdSmem {
     static constexpr int G_PART = WNB * WNC * 2;               // dgates operand, 32 rows x 128 gate cols bf16 = 8 KB
     static constexpr int G_BUF = (X3 ? 2 : 1) * G_PART;
@@ -1261,7 +1263,7 @@ struct WaveBwdSmem {
     static constexpr int BAR_OFF = 3 * G_BUF;
     static constexpr int W_OFF = (BAR_OFF + 64 + 1023) / 1024 * 1024;
     static constexpr int W_HALF = 128 * WNC * 2;               // 128 units x 128 gate cols bf16 = 32 KB
-    static constexpr int W_PART = 2 * W_HALF;
+    static constexpr int W_PART = (CH / 128) * W_HALF;
     static constexpr int W_BYTES = (X3 ? 2 : 1) * W_PART;
     static constexpr int TOTAL1 = W_OFF;
     static constexpr int TOTAL2 = W_OFF + W_BYTES;
@@ -1269,10 +1271,11 @@ struct WaveBwdSmem {
 constexpr int WRS = 512;           // uint4 words of one (dst, src) partial tile: 32 units x 16 row pairs
 constexpr int WDG = 2048;          // uint4 words of one published dgates slice (2 parts x 16 chunks x 32 rows x 2 halves)
 
-template <bool X3>
+template <bool X3, int CH_>
 __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_constant__ WaveBwdArgs a) {
-    using S = WaveBwdSmem<X3>;
-    constexpr int NB = WNB, NT = WNT, CH = WH, UC = WU, NC = WNC;
+    using S = WaveBwdSmem<X3, CH_>;
+    constexpr int NB = WNB, NT = WNT, CH = CH_, UC = WU, NC = WNC;
+    constexpr int WG = CH / WU, HF = CH / 128;                 // CTAs per group (shadows the H = 256 constant), 128-unit halves
     constexpr int NCG = NT / 128, CPW = NB / NCG, RPT = NB * 32 / NT, H4 = 4 * CH;
     constexpr int NPARTW = (X3 ? 2 : 1) * 1024;               // LL words of a dgates slice actually used
     static_assert(CPW == 8 && RPT == 2, "LL packing assumes 8 columns per thread / 2 rows per thread");
@@ -1308,9 +1311,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     uint4* dgx = a.xchg + WHDR + ((size_t)(2 * a.Gs) * 2) * (WG * WG * WRS) + ((size_t)grp * T) * (WG * WDG) + rank * WDG;
 
     constexpr int NACC = 2;
-    constexpr int ABUF = 2 * NACC * NB;                        // one accumulator set: 2 unit halves x NACC x NB columns
+    constexpr int ABUF = HF * NACC * NB;                       // one accumulator set: HF unit halves x NACC x NB columns
     constexpr int WCOLS = NC / 2;                              // 64 columns per (half, part) of the resident W_hh^T
-    constexpr int ACOL = (X3 ? 2 : 1) * 2 * WCOLS;             // 256 / 128
+    constexpr int ACOL = (X3 ? 2 : 1) * HF * WCOLS;            // 256 / 128 (H = 256), 128 / 64 (H = 128)
     constexpr int TCOLS = (ACOL + 2 * ABUF) <= 256 ? 256 : 512;
     if (warp == NT / 32) tmem_alloc<TCOLS>(tmem_slot);
     if (tid == 32) {
@@ -1319,7 +1322,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
         fence_mbar_init();
         *epoch_slot = *cnt;
         if (bottom && a.packed)
-            wave_load_S_image(a.packed + WavePack<X3>::bwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
+            wave_load_S_image(a.packed + WavePack<X3, CH>::bwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
     tc_fence_before();
     __syncthreads();
@@ -1342,11 +1345,11 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
             auto rec = [&](uint32_t as, uint32_t accumulate) {
                 const uint64_t dgh0 = make_smem_desc(g0_u, G_LBO, SBO_), dgl0 = make_smem_desc(g0_u + S::G_PART, G_LBO, SBO_);
 #pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
+                for (int hf = 0; hf < HF; ++hf) {
 #pragma unroll 2
                     for (int s = 0; s < NC / 16; ++s) {
                         const uint64_t ig = (uint64_t)((s * 2 * G_LBO) >> 4);
-                        const uint32_t awh = tmem_base + (uint32_t)(hf * WCOLS + s * 8), awl = awh + 2 * WCOLS;
+                        const uint32_t awh = tmem_base + (uint32_t)(hf * WCOLS + s * 8), awl = awh + HF * WCOLS;
                         const uint32_t td = tmem_acc + as * ABUF + (uint32_t)((hf * NACC + (s % NACC)) * NB);
                         const uint32_t first = (accumulate || s >= NACC) ? 1u : 0u;
                         if (X3) {
@@ -1364,7 +1367,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 const uint64_t dgh0 = make_smem_desc(gb, G_LBO, SBO_), dgl0 = make_smem_desc(gb + S::G_PART, G_LBO, SBO_);
                 const uint64_t dwh0 = make_smem_desc(w_u, W_LBO, SBO_), dwl0 = make_smem_desc(w_u + S::W_PART, W_LBO, SBO_);
 #pragma unroll 1
-                for (int hf = 0; hf < 2; ++hf) {
+                for (int hf = 0; hf < HF; ++hf) {
 #pragma unroll 2
                     for (int s = 0; s < NC / 16; ++s) {
                         const uint64_t iw = (uint64_t)((hf * S::W_HALF + s * 2 * W_LBO) >> 4), ig = (uint64_t)((s * 2 * G_LBO) >> 4);
@@ -1403,14 +1406,14 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
         reg_inc<112>();
         if (a.packed) {
             const int layer_of = bottom ? 0 : a.L - 1;
-            wave_load_T_image<X3>(a.packed + WavePack<X3>::bwdT(a.L, layer_of, rank), warp, lane,
-                                  tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16), WCOLS, 2 * WCOLS);
+            wave_load_T_image<X3, HF>(a.packed + WavePack<X3, CH>::bwdT(a.L, layer_of, rank), warp, lane,
+                                      tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(cg * 16), WCOLS, HF * WCOLS);
             tmem_wait_st();
         } else {   // resident A operand of the recurrent product: lane = unit n (per half), column = (k, k+1) pair of the
             // CTA's 128 gate columns k = g*32 + u;  A[n][k] = W_hh[(g*H + 32*rank + u) * H + n];  cg <-> gate g
             const int g = cg;
 #pragma unroll 1
-            for (int hf = 0; hf < 2; ++hf) {
+            for (int hf = 0; hf < HF; ++hf) {
                 const int n = hf * 128 + q * 32 + lane;
                 uint32_t hi[16], lo[16];
 #pragma unroll
@@ -1422,7 +1425,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 }
                 const uint32_t ta = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(hf * WCOLS + g * 16);
                 tmem_st16(ta, hi);
-                if (X3) tmem_st16(ta + 2 * WCOLS, lo);
+                if (X3) tmem_st16(ta + HF * WCOLS, lo);
             }
             tmem_wait_st();
         }
@@ -1432,7 +1435,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
 #pragma unroll 2
             for (int i = 0; i < WIT; ++i) {
                 const int item = tid + i * NT;
-                const int n = item & (CH - 1), kc = item >> 8;
+                const int n = item % CH, kc = item / CH;
                 float v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
@@ -1541,7 +1544,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 tc_fence_after();
                 uint4* wr = rs + (size_t)(k & 1) * (WG * WG * WRS);
 #pragma unroll
-                for (int hf = 0; hf < 2; ++hf) {
+                for (int hf = 0; hf < HF; ++hf) {
                     float pv[CPW];
                     const uint32_t tb = tmem_acc + (uint32_t)((t & 1) * ABUF + hf * NACC * NB) + ((uint32_t)(q * 32) << 16);
                     tmem_ld_nb<CPW>(tb + (uint32_t)(cg * CPW), pv);
@@ -1679,8 +1682,8 @@ static int device_sm_count() {
     }
     return cache[d] > 0 ? cache[d] : 0;
 }
-static int wave_groups_per_launch(int L) {          // 18 or 9 on a full B200 (148 SMs, 1 CTA of 181-214 KB per SM)
-    const int g = device_sm_count() / (WG * L);
+static int wave_groups_per_launch(int L, int H) {   // H = 256: 18 or 9 on a full B200 (148 SMs, 1 CTA of 181-214 KB per SM)
+    const int g = device_sm_count() / ((H / WU) * L);
     return g > WMAXG ? WMAXG : g;
 }
 template <typename K>
@@ -1728,34 +1731,37 @@ static int wave_launch(K kern, const char* name, int grid, size_t smem, void* ar
 }
 
 bool lstm_wave_supported(int T, int B, int H, int L) {
-    return H == WH && B % WNB == 0 && T >= 1 && T <= WMAXT && (L == 1 || L == 2) && wave_groups_per_launch(L) >= 1;
+    return (H == 256 || H == 128) && B % WNB == 0 && T >= 1 && T <= WMAXT && (L == 1 || L == 2) &&
+           wave_groups_per_launch(L, H) >= 1;
 }
 
-size_t lstm_wave_xchg_bytes(int T, int B, int L) {
+size_t lstm_wave_xchg_bytes(int T, int B, int H, int L) {
     int gs = B / WNB;
-    const int gmax = wave_groups_per_launch(L);
+    const int gmax = wave_groups_per_launch(L, H), ng = H / WU;
     if (gs > gmax) gs = gmax;
-    return ((size_t)WHDR + (size_t)gs * T * WG * (L == 2 ? 2 * WSLICE + WPSLICE : WSLICE)) * sizeof(uint4);
+    return ((size_t)WHDR + (size_t)gs * T * ng * (L == 2 ? 2 * WSLICE + WPSLICE : WSLICE)) * sizeof(uint4);
 }
 
-template <bool X3>
+template <bool X3, int CH>
 static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
-    using S = WaveFwdSmem<X3>;
+    using S = WaveFwdSmem<X3, CH>;
+    constexpr int NG = CH / WU;
 #if WAVE_FWD2
-    auto kern = lstm_wave_fwd2_kernel<X3>;
+    static_assert(CH == WH || true, "");
+    auto kern = CH == WH ? lstm_wave_fwd2_kernel<X3> : lstm_wave_fwd_kernel<X3, CH>;
 #else
-    auto kern = lstm_wave_fwd_kernel<X3>;
+    auto kern = lstm_wave_fwd_kernel<X3, CH>;
 #endif
-    const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L);
+    const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L, CH);
     if (gmax < 1) {
-        set_error("lstm_wave_fwd: the device has too few SMs for one group of %d CTAs x %d layers", WG, a.L);
+        set_error("lstm_wave_fwd: the device has too few SMs for one group of %d CTAs x %d layers", NG, a.L);
         return FHVAE_ENOSUP;
     }
     a.Gs = gtot < gmax ? gtot : gmax;
     for (int g0 = 0; g0 < gtot; g0 += gmax) {          // all CTAs of a launch must be co-resident (one per SM)
         a.G = (gtot - g0) < gmax ? (gtot - g0) : gmax;
         a.b_off = g0 * WNB;
-        const int r = wave_launch(kern, "lstm_wave_fwd", a.L * a.G * WG, S::TOTAL2, &a, st);   // (single-layer launches
+        const int r = wave_launch(kern, "lstm_wave_fwd", a.L * a.G * NG, S::TOTAL2, &a, st);   // (single-layer launches
         if (r) return r;                                                                        //  simply leave W_OFF.. unused)
     }
     return 0;
@@ -1763,35 +1769,38 @@ static int launch_wave_fwd(WaveFwdArgs a, cudaStream_t st) {
 
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
-                  void* xchg, int T, int B, int L, int mode, cudaStream_t st, void* hp0, void* hp1, long long hps,
+                  void* xchg, int T, int B, int H, int L, int mode, cudaStream_t st, void* hp0, void* hp1, long long hps,
                   const void* packed) {
     WaveFwdArgs a{P0, Q0, Whh0, h0, c0, a0, Wih1, b1, Whh1, h1, c1, a1, reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
                   reinterpret_cast<__nv_bfloat16*>(hp0), reinterpret_cast<__nv_bfloat16*>(hp1), hps,
                   reinterpret_cast<const uint8_t*>(packed)};
-    return mode == FHVAE_MODE_BF16X3 ? launch_wave_fwd<true>(a, st) : launch_wave_fwd<false>(a, st);
+    const bool x3 = mode == FHVAE_MODE_BF16X3;
+    if (H == 256) return x3 ? launch_wave_fwd<true, 256>(a, st) : launch_wave_fwd<false, 256>(a, st);
+    return x3 ? launch_wave_fwd<true, 128>(a, st) : launch_wave_fwd<false, 128>(a, st);
 }
 
-size_t lstm_wave_bwd_xchg_bytes(int T, int B, int L) {
+size_t lstm_wave_bwd_xchg_bytes(int T, int B, int H, int L) {
     int gs = B / WNB;
-    const int gmax = wave_groups_per_launch(L);
+    const int gmax = wave_groups_per_launch(L, H), ng = H / WU;
     if (gs > gmax) gs = gmax;
-    return ((size_t)WHDR + (size_t)L * gs * 2 * WG * WG * WRS + (L == 2 ? (size_t)gs * T * WG * WDG : 0)) * sizeof(uint4);
+    return ((size_t)WHDR + (size_t)L * gs * 2 * ng * ng * WRS + (L == 2 ? (size_t)gs * T * ng * WDG : 0)) * sizeof(uint4);
 }
 
-template <bool X3>
+template <bool X3, int CH>
 static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
-    using S = WaveBwdSmem<X3>;
-    auto kern = lstm_wave_bwd_kernel<X3>;
-    const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L);
+    using S = WaveBwdSmem<X3, CH>;
+    constexpr int NG = CH / WU;
+    auto kern = lstm_wave_bwd_kernel<X3, CH>;
+    const int gtot = a.B / WNB, gmax = wave_groups_per_launch(a.L, CH);
     if (gmax < 1) {
-        set_error("lstm_wave_bwd: the device has too few SMs for one group of %d CTAs x %d layers", WG, a.L);
+        set_error("lstm_wave_bwd: the device has too few SMs for one group of %d CTAs x %d layers", NG, a.L);
         return FHVAE_ENOSUP;
     }
     a.Gs = gtot < gmax ? gtot : gmax;
     for (int g0 = 0; g0 < gtot; g0 += gmax) {
         a.G = (gtot - g0) < gmax ? (gtot - g0) : gmax;
         a.b_off = g0 * WNB;
-        const int r = wave_launch(kern, "lstm_wave_bwd", a.L * a.G * WG, S::TOTAL2, &a, st);
+        const int r = wave_launch(kern, "lstm_wave_bwd", a.L * a.G * NG, S::TOTAL2, &a, st);
         if (r) return r;
     }
     return 0;
@@ -1799,30 +1808,39 @@ static int launch_wave_bwd(WaveBwdArgs a, cudaStream_t st) {
 
 int lstm_wave_bwd(const float* dh_all, const float* dh_last1, const float* dh_last0, const float* Whh1, const float* c1,
                   const float* a1, float* dg1, float* dgsum1, const float* Wih1, const float* Whh0, const float* c0,
-                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int L, int mode, cudaStream_t st,
+                  const float* a0, float* dg0, float* dgsum0, void* xchg, int T, int B, int H, int L, int mode, cudaStream_t st,
                   void* dgp1, void* dgp0, long long dgps, const void* packed) {
     WaveBwdArgs a{dh_all, dh_last1, dh_last0, Whh1, c1, a1, dg1, dgsum1, Wih1, Whh0, c0, a0, dg0, dgsum0,
                   reinterpret_cast<uint4*>(xchg), T, B, 0, 0, 0, L,
                   reinterpret_cast<__nv_bfloat16*>(dgp1), reinterpret_cast<__nv_bfloat16*>(dgp0), dgps,
                   reinterpret_cast<const uint8_t*>(packed)};
-    return mode == FHVAE_MODE_BF16X3 ? launch_wave_bwd<true>(a, st) : launch_wave_bwd<false>(a, st);
+    const bool x3 = mode == FHVAE_MODE_BF16X3;
+    if (H == 256) return x3 ? launch_wave_bwd<true, 256>(a, st) : launch_wave_bwd<false, 256>(a, st);
+    return x3 ? launch_wave_bwd<true, 128>(a, st) : launch_wave_bwd<false, 128>(a, st);
 }
 
-size_t lstm_wave_pack_bytes(int L, int mode) {
-    return mode == FHVAE_MODE_BF16X3 ? WavePack<true>::n_images(L) * WavePack<true>::IMG
-                                     : WavePack<false>::n_images(L) * WavePack<false>::IMG;
+template <bool X3, int CH>
+static size_t pack_bytes(int L) { return WavePack<X3, CH>::n_images(L) * WavePack<X3, CH>::IMG; }
+
+size_t lstm_wave_pack_bytes(int H, int L, int mode) {
+    const bool x3 = mode == FHVAE_MODE_BF16X3;
+    if (H == 256) return x3 ? pack_bytes<true, 256>(L) : pack_bytes<false, 256>(L);
+    return x3 ? pack_bytes<true, 128>(L) : pack_bytes<false, 128>(L);
 }
 
 // layer-indexed weights: Whh_l0 (bottom / only layer), Wih1 + Whh_l1 (second layer of a 2-layer stack)
-int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int L, int mode, cudaStream_t st) {
+template <bool X3, int CH>
+static void launch_pack(const WavePackArgs& a, cudaStream_t st) {
+    wave_pack_kernel<X3, CH><<<WavePack<X3, CH>::n_images(a.L), WNT, 0, st>>>(a);
+}
+int lstm_wave_pack(const float* Whh_l0, const float* Wih1, const float* Whh_l1, void* out, int H, int L, int mode,
+                   cudaStream_t st) {
     WavePackArgs a{{Whh_l0, Whh_l1}, Wih1, reinterpret_cast<uint8_t*>(out), L};
-    if (mode == FHVAE_MODE_BF16X3)
-        wave_pack_kernel<true><<<WavePack<true>::n_images(L), WNT, 0, st>>>(a);
-    else
-        wave_pack_kernel<false><<<WavePack<false>::n_images(L), WNT, 0, st>>>(a);
+    const bool x3 = mode == FHVAE_MODE_BF16X3;
+    if (H == 256) { if (x3) launch_pack<true, 256>(a, st); else launch_pack<false, 256>(a, st); }
+    else          { if (x3) launch_pack<true, 128>(a, st); else launch_pack<false, 128>(a, st); }
     FHVAE_LAUNCH_CHECK("lstm_wave_pack");
     return 0;
 }
 
 }  // namespace fhvae
-

@@ -944,7 +944,7 @@ class _FHVAEPlan(_Plan):
         self.wave = {k: bool(use_wave and self.L[k] == 2 and len(set(hus)) == 1 and
                              _lib.fn("fhvae_lstm_wave_supported")(T, B, self.H[k], 2, self.mode))
                      for (k, _), hus in zip(self.NETS, (m.z2_hus, m.z1_hus, m.x_hus))}
-        self.wave_xchg = self.wave_xchg_bwd = None
+        self.wave_xchg, self.wave_xchg_bwd = {}, {}      # one exchange buffer per hidden width (zeroed ONCE)
         # pre-packed weight operands of the wavefront kernels (fhvae_lstm_wave_pack): rebuilt at the start of every
         # forward list from the current weights, consumed by the stack's forward AND BPTT launch
         self.wave_packed = {}
@@ -953,10 +953,10 @@ class _FHVAEPlan(_Plan):
                 if on:
                     nb = _lib.fn("fhvae_lstm_wave_pack_bytes")(self.H[k], 2, self.mode)
                     self.wave_packed[k] = torch.zeros(nb // 4, dtype=torch.float32, device=self.dev)
-        if any(self.wave.values()):
-            Hw = next(self.H[k] for k in self.wave if self.wave[k])
-            nbytes = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, Hw, 2)
-            self.wave_xchg = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)   # zeroed ONCE
+        for k, on in self.wave.items():
+            if on and self.H[k] not in self.wave_xchg:
+                nbytes = _lib.fn("fhvae_lstm_wave_xchg_bytes")(T, B, self.H[k], 2)
+                self.wave_xchg[self.H[k]] = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)
         for k, _ in self.NETS:
             H = self.H[k]
             for l in range(self.L[k]):
@@ -1023,7 +1023,7 @@ class _FHVAEPlan(_Plan):
                 c.add("fhvae_lstm_wave_fwd_planes", ptr(self.P[k, 0]) if (k, 0) in self.P else None, q0, m.poff(whh0),
                       ptr(self.h[k, 0]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]), m.poff(wih1), self._bs(k, 1),
                       m.poff(whh1), ptr(self.h[k, 1]), ptr(self.c[k, 1]), ptr(self.acts[k, 1]),
-                      ptr(self.wave_xchg), hp[0], hp[1], T * B * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
+                      ptr(self.wave_xchg[H]), hp[0], hp[1], T * B * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
                       T, B, H, 2, mode)
                 return
             for l in range(self.L[k]):
@@ -1153,9 +1153,9 @@ class _FHVAEPlan(_Plan):
             dh_all = dh_all_top
             if self.wave[k]:
                 # both layers in one wavefront launch; dh of layer 0 never exists in HBM (lstm_wave.cu)
-                if self.wave_xchg_bwd is None:
+                if H not in self.wave_xchg_bwd:
                     nbytes = _lib.fn("fhvae_lstm_wave_bwd_xchg_bytes")(T, B, H, 2)
-                    self.wave_xchg_bwd = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)
+                    self.wave_xchg_bwd[H] = torch.zeros(nbytes // 4, dtype=torch.float32, device=self.dev)
                 n0, n1 = _lstm_names(pre[k], 0), _lstm_names(pre[k], 1)
                 dgp = [planes_of(self.dg[k, l]).data_ptr() if use_tma else None for l in (0, 1)]
                 if use_tma:
@@ -1164,7 +1164,7 @@ class _FHVAEPlan(_Plan):
                 c.add("fhvae_lstm_wave_bwd_planes", dh_all_top, dh_last_of(1), dh_last_of(0), m.poff(n1[1]),
                       ptr(self.c[k, 1]), ptr(self.acts[k, 1]), None if use_tma else ptr(self.dg[k, 1]),
                       ptr(self.dgsum[k, 1]), m.poff(n1[0]), m.poff(n0[1]), ptr(self.c[k, 0]), ptr(self.acts[k, 0]),
-                      None if use_tma else ptr(self.dg[k, 0]), ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd),
+                      None if use_tma else ptr(self.dg[k, 0]), ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd[H]),
                       dgp[1], dgp[0], T * B * 4 * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
                       T, B, H, 2, mode)
                 for l in (1, 0):

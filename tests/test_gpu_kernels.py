@@ -271,7 +271,8 @@ def _wave_xchg(T, B, H, L):
 
 def _wave_packed(W0, Wi1, W1, H, L, mode):
     nb = _lib.fn("fhvae_lstm_wave_pack_bytes")(H, L, mode)
-    assert nb == (16 * L + (16 if L == 2 else 0)) * (2 if mode == 1 else 1) * 65536
+    ng = H // 32
+    assert nb == (2 * ng * L + (2 * ng if L == 2 else 0)) * (2 if mode == 1 else 1) * (H // 128) * 32768
     buf = torch.zeros(nb // 4, device=DEV)
     call("fhvae_lstm_wave_pack", ptr(W0), ptr(Wi1) if Wi1 is not None else None, ptr(W1) if W1 is not None else None,
          ptr(buf), H, L, mode)
@@ -279,13 +280,15 @@ def _wave_packed(W0, Wi1, W1, H, L, mode):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("T,B,L,repeat", [(1, 32, 1, 1), (3, 64, 2, 2), (20, 256, 1, 2), (20, 256, 2, 3), (7, 320, 2, 1),
-                                           (20, 608, 1, 1)])
-def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
+@pytest.mark.parametrize("T,B,L,repeat,H", [(1, 32, 1, 1, 256), (3, 64, 2, 2, 256), (20, 256, 1, 2, 256), (20, 256, 2, 3, 256),
+                                             (7, 320, 2, 1, 256), (20, 608, 1, 1, 256),
+                                             (1, 32, 1, 1, 128), (3, 64, 2, 2, 128), (20, 256, 2, 3, 128), (20, 256, 1, 2, 128),
+                                             (5, 608, 2, 1, 128)])
+def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode, H):
     """Layer-wavefront recurrence (one launch for the stack, LL exchange through L2, layer-1 projection
     in-kernel) against the exact fp32 per-layer kernels + fp32 projection GEMM.  Repeated launches reuse the
-    exchange buffer (per-CTA launch counters make the flags unique)."""
-    H = 256
+    exchange buffer (per-CTA launch counters make the flags unique).  H = 256: groups of 8 CTAs; H = 128 (the
+    reference's CLI default width, train_model.py:145-168): groups of 4."""
     P = rnd(T, B, 4 * H, seed=1, scale=0.7)
     Q = rnd(B, 4 * H, seed=2, scale=0.3)
     W0 = rnd(4 * H, H, seed=3, scale=1.0 / 16)
@@ -326,14 +329,16 @@ def test_lstm_wave_fwd_matches_simt(T, B, L, repeat, mode):
 
 
 @pytest.mark.parametrize("mode", [1, 2])
-@pytest.mark.parametrize("T,B,L,use_all,use_last,repeat", [(1, 32, 1, True, True, 1), (4, 64, 2, False, True, 2),
-                                                           (20, 256, 1, True, False, 2), (20, 256, 2, True, True, 3),
-                                                           (20, 256, 2, False, True, 1), (2, 320, 2, True, True, 1),
-                                                           (5, 608, 1, True, True, 1)])
-def test_lstm_wave_bwd_matches_simt(T, B, L, use_all, use_last, repeat, mode):
+@pytest.mark.parametrize("T,B,L,use_all,use_last,repeat,H", [(1, 32, 1, True, True, 1, 256), (4, 64, 2, False, True, 2, 256),
+                                                             (20, 256, 1, True, False, 2, 256), (20, 256, 2, True, True, 3, 256),
+                                                             (20, 256, 2, False, True, 1, 256), (2, 320, 2, True, True, 1, 256),
+                                                             (5, 608, 1, True, True, 1, 256),
+                                                             (1, 32, 1, True, True, 1, 128), (4, 64, 2, False, True, 2, 128),
+                                                             (20, 256, 2, True, True, 3, 128), (20, 256, 1, True, False, 2, 128),
+                                                             (3, 608, 2, True, True, 1, 128)])
+def test_lstm_wave_bwd_matches_simt(T, B, L, use_all, use_last, repeat, mode, H):
     """BPTT wavefront (top layer first; dh0_t = dg0_{t+1} W_hh0 + dg1_t W_ih1 inside the kernel) against the exact
     fp32 per-layer BPTT kernels + fp32 dgrad GEMM."""
-    H = 256
     f = lambda *s: torch.zeros(*s, device=DEV)
     P, Q = rnd(T, B, 4 * H, seed=1, scale=0.7), rnd(B, 4 * H, seed=2, scale=0.3)
     W0 = rnd(4 * H, H, seed=3, scale=1.0 / 16)

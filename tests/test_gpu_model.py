@@ -70,6 +70,8 @@ CFGS = {
     "simple_ragged": dict(kind="simple", B=7, T=3, F=8, N=9, args=(24, [24, 16], [8, 40], 8, 16, [16, 24])),
     "fhvae_small": dict(kind="fhvae", B=10, T=6, F=8, N=13, args=(48, [32, 32], [32, 32], 8, 16, [32, 32])),
     "fhvae_1layer_3layer": dict(kind="fhvae", B=5, T=4, F=12, N=6, args=(48, [16], [24, 24, 24], 16, 8, [40, 40])),
+    # the reference's CLI default widths (train_model.py:145-168): 2x128 LSTMs, z dims 16 -> tensor-core recurrence with groups of 4 CTAs
+    "fhvae_h128": dict(kind="fhvae", B=64, T=20, F=80, N=100, args=(1600, [128, 128], [128, 128], 16, 16, [128, 128])),
     "fhvae_c1": dict(kind="fhvae", B=256, T=20, F=80, N=1000, args=(1600, [256, 256], [256, 256], 32, 32, [256, 256])),
 }
 

@@ -36,6 +36,7 @@ def _check_params(m, o, steps, lr=1e-3, what=""):
     ("fhvae_c1", P.MODE_BF16X3, False),
     ("fhvae_c1", P.MODE_F32_SIMT, True),
     ("fhvae_small", P.MODE_F32_SIMT, True),
+    ("fhvae_h128", P.MODE_BF16X3, True),        # reference CLI default widths: wavefront kernels with 4-CTA groups
     ("fhvae_1layer_3layer", P.MODE_BF16X3, True),
     ("simple_c0", P.MODE_BF16X3, True),
     ("simple_c0", P.MODE_F32_SIMT, True),
@@ -64,6 +65,8 @@ def test_train_step_matches_oracle(name, mode, graphs):
             assert_close(plan.out[row], ref, FP32_RTOL, f"{name}: {nm} step {step}")
     assert opt.steps_taken() == steps
     m.check_flags()
+    if name in ("fhvae_c1", "fhvae_h128") and mode != P.MODE_F32_SIMT:
+        assert all(plan.wave.values()), "the tensor-core wavefront recurrence must serve this shape"
     _check_params(m, o, steps, what=f"{name}: ")
 
 
