@@ -574,8 +574,12 @@ class _Plan:
         m = self.m
         k = 0
         gflat = m._grad_buffer(k)
-        if self.bwd[k] is None:
+        if self.bwd[k] is None or self.__dict__.get("_wgrad_split", True):
+            # this schedule needs every z1 / decoder gradient complete before the z2 part starts: no deferred half
+            self._wgrad_split = False
             self.bwd[k] = self._build_bwd(gflat)
+            self.__dict__.pop("_train_list_cache", None)
+            self.__dict__.pop("_train_graphs", None)
         if not hasattr(self, "loss"):
             self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
         B = self.B
@@ -1100,7 +1104,7 @@ class _FHVAEPlan(_Plan):
         planes_of = self.planes_of
         made = set()           # fp32 tensors whose planes are written by the kernel that produces them
 
-        def split(ts, side=1):
+        def split(ts, side=1):   # (side: the stream of the launch that consumes the planes)
             probs = [SplitProblem(ptr(t), planes_of(t).data_ptr(), t.shape[-1], t.shape[-1], t.numel(),
                                   t.numel() // t.shape[-1], t.shape[-1]) for t in ts]
             for i in range(0, len(probs), _lib.SPLIT_MAX_BATCH):
@@ -1124,18 +1128,18 @@ class _FHVAEPlan(_Plan):
                 wg.append(gemm_tn(ptr(G, g_row * M), M, ptr(X, x_row * N), N, Cp, ldc, M, N, K))
 
         class _Side(list):     # weight-gradient GEMMs + bias column sums: flushed to side stream 1 right behind their inputs
-            def flush(self_):
+            def flush(self_, side=1):
                 if fresh:
-                    split(list(fresh))
+                    split(list(fresh), side=side)
                     fresh.clear()
                 for i in range(0, len(wgp), _lib.WGRAD_MAX_BATCH):
                     chunk = wgp[i:i + _lib.WGRAD_MAX_BATCH]
                     arr = (WgradProblem * len(chunk))(*chunk)
                     c.keep.append(arr)
-                    c.add("fhvae_wgrad_planes_batch", arr, len(chunk), mode, side=1)
+                    c.add("fhvae_wgrad_planes_batch", arr, len(chunk), mode, side=side)
                 wgp.clear()
                 if self_:
-                    c.gemm(list(self_), mode, side=1)
+                    c.gemm(list(self_), mode, side=side)
                     self_.clear()
                 if cs:
                     # tiny, latency-bound: next to, not behind, the GEMMs -- and on its own stream, so that the join
@@ -1146,7 +1150,10 @@ class _FHVAEPlan(_Plan):
         if use_tma:
             split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k]) if not self.wave[k]] + [self.x_tm])
 
-        def stack_bwd(k, dh_all_top, dh_last_of, extra=None):
+        split_mode = int(os.environ.get("FHVAE_WGRAD_SPLIT", "1"))     # 0: one launch behind the BPTT; 1: layer-1 half there,
+        split_wgrad = split_mode != 0 and self.__dict__.get("_wgrad_split", True)   # layer-0 half deferred; 2: all deferred
+
+        def stack_bwd(k, dh_all_top, dh_last_of, extra=None, defer=None):
             """BPTT through the stack of net k, top layer first.  Returns nothing; fills dg/dgsum.  ``extra`` appends
             the weight gradients that only need this stack's dgates, so that they share its side-stream flush."""
             H = self.H[k]
@@ -1167,6 +1174,12 @@ class _FHVAEPlan(_Plan):
                       None if use_tma else ptr(self.dg[k, 0]), ptr(self.dgsum[k, 0]), ptr(self.wave_xchg_bwd[H]),
                       dgp[1], dgp[0], T * B * 4 * H, ptr(self.wave_packed[k]) if k in self.wave_packed else None,
                       T, B, H, 2, mode)
+                # A full-width weight-gradient launch (128 CTAs x 193 KB) right behind the BPTT holds the SMs the NEXT
+                # stack's 128-CTA wavefront launch needs until it has drained (CUPTI: the next BPTT became fully resident
+                # ~28-33 us after its head kernel had finished).  So only the layer-1 half is launched here, where it hides
+                # behind the head kernel; the layer-0 half is forked AFTER the head kernel (`defer`): it becomes ready
+                # together with the next wavefront launch, which wins the SMs (high-priority stream), and trickles in on
+                # the ~20 SMs the wavefront leaves free.  The last stack has nothing to hide behind: one launch.
                 for l in (1, 0):
                     wih, whh, bih, bhh = _lstm_names(pre[k], l)
                     if T > 1:
@@ -1176,9 +1189,23 @@ class _FHVAEPlan(_Plan):
                     cs.append(ColsumProblem(ptr(self.dgsum[k, l]), g(bih), g(bhh), 4 * H, B, 4 * H))
                     if l > 0:
                         wgrad_tn(self.dg[k, l], 0, self.h[k, l - 1], 0, g(wih), H, 4 * H, H, TB)
+                        if defer is not None and split_mode == 1:
+                            wg.flush()                  # layer-1 half + every column sum queued so far
                 if extra:
                     extra()
-                wg.flush()
+                if defer is None:
+                    wg.flush()
+                else:                                   # layer-0 half: flushed by the caller behind the next head kernel
+                    held = (list(wgp), list(wg), list(fresh))
+                    wgp.clear(); wg.clear(); fresh.clear()
+                    if split_mode != 1 and cs:          # (column sums are never deferred)
+                        c.colsum(list(cs), side=3)
+                        cs.clear()
+
+                    def later():
+                        wgp.extend(held[0]); wg.extend(held[1]); fresh.extend(held[2])
+                        wg.flush(side=4)
+                    defer.append(later)
                 return
             for l in reversed(range(self.L[k])):
                 wih, whh, bih, bhh = _lstm_names(pre[k], l)
@@ -1225,6 +1252,7 @@ class _FHVAEPlan(_Plan):
                 wg.append(gemm_tn(ptr(dhead), 2 * Z, hT, H, g(wname, l * H), L * H, 2 * Z, H, B))
             wg.flush()         # everything queued so far is ready: runs beside this stack's BPTT, not after it
 
+        deferred: List = []
         # ---------------- decoder
         Hd, Ld = self.H["dec"], self.L["dec"]
         if not m.detach_px:
@@ -1232,7 +1260,7 @@ class _FHVAEPlan(_Plan):
             cs.append(ColsumProblem(ptr(self.dxhead), g("dec_gauss_layer.mulayer.bias"), None, 2 * F, TB, 2 * F))
             c.gemm([gemm_nn(ptr(self.dxhead), 2 * F, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
                             ptr(self.dhA), Hd, TB, Hd, 2 * F)], mode)
-            stack_bwd("dec", ptr(self.dhA), lambda l: None)
+            stack_bwd("dec", ptr(self.dhA), lambda l: None, defer=deferred if split_wgrad else None)
             wih_d = _lstm_names(pre["dec"], 0)[0]
             wg.append(gemm_tn(ptr(self.dgsum["dec", 0]), 4 * Hd, ptr(self.zcat), Z1 + Z2, g(wih_d), Z1 + Z2,
                               4 * Hd, Z1 + Z2, B))
@@ -1249,13 +1277,15 @@ class _FHVAEPlan(_Plan):
         # ---------------- z1 encoder
         Hz1 = self.H["z1"]
         head_bwd("z1", self.dz1head, Z1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias", **z1_from)
+        while deferred:
+            deferred.pop(0)()          # the decoder stack's layer-0 weight gradients: ready together with the z1 BPTT
         wih_z1 = _lstm_names(pre["z1"], 0)[0]
 
         def z1_extra():
             wgrad_tn(self.dg["z1", 0], 0, self.x_tm, 0, g(wih_z1), F + Z2, 4 * Hz1, F, TB)
             wg.append(gemm_tn(ptr(self.dgsum["z1", 0]), 4 * Hz1, ptr(self.zcat, Z1), Z1 + Z2, g(wih_z1, F), F + Z2,
                               4 * Hz1, Z2, B))
-        stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]), extra=z1_extra)
+        stack_bwd("z1", None, lambda l: ptr(self.dhT["z1", l]), extra=z1_extra, defer=deferred if split_wgrad else None)
         # ---------------- z2 encoder
         Hz2 = self.H["z2"]
         # dz2_sample = (decoder part, already in dzcat[:, Z1:]) + dQ @ W_z ; dz2head also carries the side-2 chain's part
@@ -1263,6 +1293,8 @@ class _FHVAEPlan(_Plan):
         head_bwd("z2", self.dz2head, Z2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias",
                  eps=self.eps2, head=self.z2head, roff=Z1, dgsum=ptr(self.dgsum["z1", 0]), NG=4 * Hz1, Wq=m.poff(wih_z1, F),
                  ld_wq=F + Z2, Kq=Z2, dzoff=Z1, beta=1)
+        while deferred:
+            deferred.pop(0)()          # the z1 stack's layer-0 weight gradients: beside the z2 BPTT
         wih_z2 = _lstm_names(pre["z2"], 0)[0]
         stack_bwd("z2", None, lambda l: ptr(self.dhT["z2", l]),
                   extra=lambda: wgrad_tn(self.dg["z2", 0], 0, self.x_tm, 0, g(wih_z2), F, 4 * Hz2, F, TB))

@@ -19,7 +19,7 @@ def main():
     mode = {"f32": P.MODE_F32_SIMT, "bf16x3": P.MODE_BF16X3, "bf16": P.MODE_BF16}[os.environ.get("FHVAE_MODE", "bf16x3")]
     torch.manual_seed(0)
     m = P.FHVAE(c["T"] * c["F"], [c["H"]] * c["L"], [c["H"]] * c["L"], c["Z"], c["Z"], [c["H"]] * c["L"],
-                seg_len=c["T"], num_seqs=c["N"], gemm_mode=mode).to(dev)
+                seg_len=c["T"], num_seqs=c["N"], gemm_mode=mode, use_cuda_graphs=True).to(dev)
     opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
     x, idx, nsegs = bench.synth(c["B"], c["T"], c["F"], c["N"], 1234)
     xd, idd, nsd = x.to(dev), idx.to(dev), nsegs.to(dev)
