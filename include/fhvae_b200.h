@@ -319,6 +319,25 @@ typedef struct fhvae_split_problem {
 } fhvae_split_problem;
 int fhvae_split_planes_batch(const fhvae_split_problem* problems, int n_problems, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Projection GEMM on pre-split planes (csrc/gemm_proj.cu): C[M,N] = A[M,K] W[N,K]^T (+ bias[N]) -- nn.Linear forward
+ * (simple_fhvae.py:130-134, 208-212) for the short-K, large-M products on the critical path of the LSTM model (layer-0
+ * input projections of x over all T*B rows, the decoder's Gaussian head).  A and W are bf16 hi/lo planes
+ * [2][rows][K] with K contiguous (hi at element r*ld + k, lo at plane_stride + r*ld + k), fed by TMA; K % 16 == 0,
+ * leading dimensions and plane strides multiples of 8 elements, 16-byte aligned.  C (fp32, leading dim ldc) is
+ * overwritten.  mode = FHVAE_MODE_BF16X3 (three products) or FHVAE_MODE_BF16 (hi*hi only).
+ * ------------------------------------------------------------------------------------------- */
+#define FHVAE_PROJ_MAX_BATCH 8
+typedef struct fhvae_proj_problem {
+    const void*  A;
+    const void*  W;
+    float*       C;
+    const float* bias;
+    int32_t      M, N, K, reserved;
+    int64_t      lda, a_plane_stride, ldw, w_plane_stride, ldc;
+} fhvae_proj_problem;
+int fhvae_proj_planes_batch(const fhvae_proj_problem* problems, int n_problems, int mode, void* stream);
+
 /* The wavefront recurrence with bf16 hi/lo planes as additional (fwd) or alternative (bwd) outputs: the planes are
  * the TMA operands of fhvae_wgrad_planes_batch, written by the kernel that produces the tensor instead of by a
  * separate fhvae_split_planes_batch pass.  *_planes: bf16 [2][T*B*width], hi at element i, lo at plane_stride + i

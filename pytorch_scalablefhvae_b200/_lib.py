@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfhvae_b200.so")
-SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_wgrad.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "heads.cu", "disc.cu",
+SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_wgrad.cu", "gemm_proj.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "heads.cu", "disc.cu",
            "table_adam_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -22,6 +22,7 @@ MODE_F32_SIMT, MODE_BF16X3, MODE_BF16 = 0, 1, 2
 FLAG_NAN, FLAG_BAD_INDEX = 1, 2          # bits of the device status word (include/fhvae_b200.h)
 GEMM_MAX_BATCH = 24
 WGRAD_MAX_BATCH = 8
+PROJ_MAX_BATCH = 8
 SPLIT_MAX_BATCH = 16
 COLSUM_MAX_BATCH = 16
 
@@ -37,6 +38,12 @@ class WgradProblem(C.Structure):
     _fields_ = [("A", C.c_void_p), ("B", C.c_void_p), ("C", C.c_void_p), ("M", C.c_int32), ("N", C.c_int32),
                 ("K", C.c_int32), ("reserved", C.c_int32), ("lda", C.c_int64), ("a_plane_stride", C.c_int64),
                 ("ldb", C.c_int64), ("b_plane_stride", C.c_int64), ("ldc", C.c_int64)]
+
+
+class ProjProblem(C.Structure):
+    _fields_ = [("A", C.c_void_p), ("W", C.c_void_p), ("C", C.c_void_p), ("bias", C.c_void_p), ("M", C.c_int32),
+                ("N", C.c_int32), ("K", C.c_int32), ("reserved", C.c_int32), ("lda", C.c_int64),
+                ("a_plane_stride", C.c_int64), ("ldw", C.c_int64), ("w_plane_stride", C.c_int64), ("ldc", C.c_int64)]
 
 
 class SplitProblem(C.Structure):
@@ -95,6 +102,7 @@ PROTOTYPES = {
     "fhvae_axpy": [_p, _p, _f, _l, _p],
     "fhvae_wgrad_planes_batch": [C.POINTER(WgradProblem), _i, _i, _p],
     "fhvae_split_planes_batch": [C.POINTER(SplitProblem), _i, _p],
+    "fhvae_proj_planes_batch": [C.POINTER(ProjProblem), _i, _i, _p],
     "fhvae_load_inputs": [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p, _p],
     "fhvae_head_fwd": [_p, _p, _l, _i, _i, _p, _p, _p, _i, _p, _p, _l, _i, _p, _l, _p, _i, _i, _p, _i, _i, _p],
     "fhvae_head_bwd": [_p, _i, _p, _l, _i, _p, _l, _i, _i, _p, _p, _i, _i, _p, _i, _p, _i, _i, _p, _p, _i, _p],

@@ -25,7 +25,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import ColsumProblem, SplitProblem, WgradProblem
+from ._lib import ColsumProblem, ProjProblem, SplitProblem, WgradProblem
 from .plan import CallList, _side_stream, current_stream_ptr, gemm_nn, gemm_nt, gemm_tn, ptr
 
 PZ2_LOGVAR = math.log(0.5 ** 2)      # simple_fhvae.py:88
@@ -974,6 +974,14 @@ class _FHVAEPlan(_Plan):
         self.tma_wgrad = (self.mode != _lib.MODE_F32_SIMT and os.environ.get("FHVAE_TMA_WGRAD", "1") != "0"
                           and F % 8 == 0 and all(h % 8 == 0 for h in self.H.values()) and (T - 1) * B >= 1024)
         self.planes = {}
+        # Optional (FHVAE_TMA_PROJ=1): the short-K products on the critical path (layer-0 projections of x, the decoder head)
+        # on the TMA-fed K-major kernel (gemm_proj.cu): operands = bf16 hi/lo planes of x_tm / h_dec and of the weights (one
+        # split launch at the start of the step).  Measured (tools/proj_bench.py, warm): x projection 21.5 us vs 16.6 us for
+        # gemm_tc, decoder head 12.2 vs 14.4 us; in the step 0.918 vs 0.906 ms -- with ~1 tile per CTA both kernels are bound
+        # by the per-CTA latency chain, not by the operand path, so the default stays gemm_tc.
+        self.tma_proj = (self.mode != _lib.MODE_F32_SIMT and os.environ.get("FHVAE_TMA_PROJ", "0") == "1" and F % 16 == 0
+                         and all(h % 16 == 0 for h in self.H.values()))
+        self.wplanes = {}
         self.Q = {"z1": f(B, 4 * self.H["z1"]), "dec": f(B, 4 * self.H["dec"])}
         self.xchg = f(16, B, max(self.H.values()))      # L2-resident exchange scratch of the cluster kernels
         self.xhead = f(T, B, 2 * F)
@@ -1013,10 +1021,29 @@ class _FHVAEPlan(_Plan):
         # z2 recurrence on side stream 1 (joined before the z1 stack).  (Running them on the TMA-fed kernel over
         # feature-major planes of x was tried: 19.4 us vs 22 us -- both are bound by the 21 MB output, not worth two
         # more operand-preparation kernels.)
-        c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z2), F, ptr(self.P["z2", 0]), 4 * Hz2, TB, 4 * Hz2, F,
-                        bias=self._bs("z2", 0))], mode)
-        c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
-                        4 * Hz1, F, bias=self._bs("z1", 0))], mode, side=1)
+        Hd_, Ld_ = self.H["dec"], self.L["dec"]
+        self.proj_head = bool(self.tma_proj and self.wave["dec"] and self.tma_wgrad)   # h_dec planes come from the wave kernel
+        if self.tma_proj:
+            bf = lambda rows, k: torch.zeros(2, rows * k, dtype=torch.bfloat16, device=self.dev)
+            self.wplanes = {"z2": bf(4 * Hz2, F), "z1": bf(4 * Hz1, F), "dec": bf(2 * F, Hd_)}
+            xp = self.planes_of(self.x_tm)
+            sp = [SplitProblem(ptr(self.x_tm), xp.data_ptr(), F, F, TB * F, TB, F),
+                  SplitProblem(m.poff(wih_z2), self.wplanes["z2"].data_ptr(), F, F, 4 * Hz2 * F, 4 * Hz2, F),
+                  SplitProblem(m.poff(wih_z1), self.wplanes["z1"].data_ptr(), F + Z2, F, 4 * Hz1 * F, 4 * Hz1, F),
+                  SplitProblem(m.poff("dec_gauss_layer.mulayer.weight"), self.wplanes["dec"].data_ptr(), Hd_, Hd_,
+                               2 * F * Hd_, 2 * F, Hd_)]
+            arr = (SplitProblem * len(sp))(*sp)
+            c.keep.append(arr)
+            c.add("fhvae_split_planes_batch", arr, len(sp))
+            pj = lambda k, H_: ProjProblem(xp.data_ptr(), self.wplanes[k].data_ptr(), ptr(self.P[k, 0]), self._bs(k, 0),
+                                           TB, 4 * H_, F, 0, F, TB * F, F, 4 * H_ * F, 4 * H_)
+            c.proj([pj("z2", Hz2)], mode)
+            c.proj([pj("z1", Hz1)], mode, side=1)
+        else:
+            c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z2), F, ptr(self.P["z2", 0]), 4 * Hz2, TB, 4 * Hz2, F,
+                            bias=self._bs("z2", 0))], mode)
+            c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
+                            4 * Hz1, F, bias=self._bs("z1", 0))], mode, side=1)
 
         def stack(k, q0):
             H = self.H[k]
@@ -1074,9 +1101,14 @@ class _FHVAEPlan(_Plan):
         self.n_encode_calls = len(c.calls)
         stack("dec", ptr(self.Q["dec"]))
         Ld = self.L["dec"]
-        c.gemm([gemm_nt(ptr(self.h["dec", Ld - 1]), Hd, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
-                        ptr(self.xhead), 2 * F, TB, 2 * F, Hd,
-                        bias=m.poff("dec_gauss_layer.mulayer.bias"))], mode)
+        if self.proj_head:
+            hp = self.planes_of(self.h["dec", Ld - 1])
+            c.proj([ProjProblem(hp.data_ptr(), self.wplanes["dec"].data_ptr(), ptr(self.xhead),
+                                m.poff("dec_gauss_layer.mulayer.bias"), TB, 2 * F, Hd, 0, Hd, TB * Hd, Hd, 2 * F * Hd, 2 * F)], mode)
+        else:
+            c.gemm([gemm_nt(ptr(self.h["dec", Ld - 1]), Hd, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
+                            ptr(self.xhead), 2 * F, TB, 2 * F, Hd,
+                            bias=m.poff("dec_gauss_layer.mulayer.bias"))], mode)
         self._tail_fwd(self.xhead, 2 * F, B * 2 * F, F, disc=False)
 
     def _build_bwd(self, gflat) -> CallList:
@@ -1147,8 +1179,9 @@ class _FHVAEPlan(_Plan):
                     c.colsum(list(cs), side=3)
                     cs.clear()
         wg = _Side()
-        if use_tma:
-            split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k]) if not self.wave[k]] + [self.x_tm])
+        if use_tma:    # (the planes of x_tm already exist when the forward projections ran on the TMA kernel)
+            split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k]) if not self.wave[k]] +
+                  ([] if self.tma_proj else [self.x_tm]))
 
         split_mode = int(os.environ.get("FHVAE_WGRAD_SPLIT", "1"))     # 0: one launch behind the BPTT; 1: layer-1 half there,
         split_wgrad = split_mode != 0 and self.__dict__.get("_wgrad_split", True)   # layer-0 half deferred; 2: all deferred

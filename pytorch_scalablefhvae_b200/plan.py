@@ -11,7 +11,7 @@ from typing import List
 import torch
 
 from . import _lib
-from ._lib import ColsumProblem, GemmProblem
+from ._lib import ColsumProblem, GemmProblem, ProjProblem
 
 
 def ptr(t: torch.Tensor, off: int = 0) -> int:
@@ -64,6 +64,14 @@ class CallList:
             arr = (GemmProblem * len(chunk))(*chunk)
             self.keep.append(arr)
             self.add("fhvae_gemm_batch", arr, len(chunk), mode, side=side)
+
+    def proj(self, problems: List[ProjProblem], mode: int, side=False):
+        """Projection GEMMs on bf16 hi/lo planes (csrc/gemm_proj.cu), grouped into one launch."""
+        for i in range(0, len(problems), _lib.PROJ_MAX_BATCH):
+            chunk = problems[i:i + _lib.PROJ_MAX_BATCH]
+            arr = (ProjProblem * len(chunk))(*chunk)
+            self.keep.append(arr)
+            self.add("fhvae_proj_planes_batch", arr, len(chunk), mode, side=side)
 
     def colsum(self, problems: List[ColsumProblem], side=False):
         for i in range(0, len(problems), _lib.COLSUM_MAX_BATCH):

@@ -755,3 +755,33 @@ def test_randn_kernel_statistics_and_stream_advance():
         _lib.check(_lib.fn("fhvae_randn")(ptr(out), n, 7, ptr(st), ptr(st, 1), torch.cuda.current_stream().cuda_stream))
     g.replay(); c = out.clone(); g.replay()
     assert float((c == out).float().mean()) < 1e-3
+
+
+def _kplanes(t):
+    """bf16 hi/lo planes [2][rows*ld] of a (rows, K) fp32 tensor (what fhvae_split_planes_batch writes)."""
+    hi = t.to(torch.bfloat16)
+    lo = (t - hi.float()).to(torch.bfloat16)
+    return torch.stack([hi.reshape(-1), lo.reshape(-1)]).contiguous()
+
+
+@pytest.mark.parametrize("mode,tol", [(1, 2e-5), (2, 1.5e-2)])
+@pytest.mark.parametrize("M,N,K", [(5120, 1024, 80), (5120, 160, 256), (200, 72, 16), (128, 128, 32), (1, 8, 48), (333, 200, 112)])
+def test_proj_planes_gemm_matches_fp64(M, N, K, mode, tol):
+    """fhvae_proj_planes_batch (TMA-fed K-major tcgen05 GEMM with the coalesced epilogue) against fp64: the layer-0 input
+    projection (5120 x 1024 x 80), the decoder head (5120 x 160 x 256) and ragged M / N / K tails."""
+    from pytorch_scalablefhvae_b200._lib import ProjProblem
+    A, W, bias = rnd(M, K, seed=1), rnd(N, K, seed=2, scale=0.2), rnd(N, seed=3)
+    pa, pw = _kplanes(A), _kplanes(W)
+    ldc = N + 8
+    C = torch.full((M, ldc), 7.0, device=DEV)
+    prob = ProjProblem(pa.data_ptr(), pw.data_ptr(), ptr(C), ptr(bias), M, N, K, 0, K, M * K, K, N * K, ldc)
+    call("fhvae_proj_planes_batch", (ProjProblem * 1)(prob), 1, mode)
+    ref = A.double() @ W.double().t() + bias.double()
+    assert_close(C[:, :N], ref, tol, f"proj {M}x{N}x{K} mode {mode}")
+    assert float((C[:, N:] - 7.0).abs().max()) == 0.0                      # nothing written beyond N
+    # two problems in one launch, one without bias
+    C1, C2 = torch.zeros(M, N, device=DEV), torch.zeros(M, N, device=DEV)
+    arr = (ProjProblem * 2)(ProjProblem(pa.data_ptr(), pw.data_ptr(), ptr(C1), ptr(bias), M, N, K, 0, K, M * K, K, N * K, N),
+                            ProjProblem(pa.data_ptr(), pw.data_ptr(), ptr(C2), None, M, N, K, 0, K, M * K, K, N * K, N))
+    call("fhvae_proj_planes_batch", arr, 2, mode)
+    assert torch.equal(C1, C[:, :N].contiguous()) and torch.equal(C2 + bias, C1)

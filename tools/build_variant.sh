@@ -12,7 +12,7 @@ OBJ=build_variants/obj
 mkdir -p $OBJ
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 objs=""
-for f in api gemm_simt gemm_tc gemm_wgrad lstm_simt lstm_cluster elbo heads disc table_adam_misc; do
+for f in api gemm_simt gemm_tc gemm_wgrad gemm_proj lstm_simt lstm_cluster elbo heads disc table_adam_misc; do
   o=$OBJ/$f.o
   if [ ! -f $o ] || [ $CS/$f.cu -nt $o ] || [ $CS/common.cuh -nt $o ] || [ $CS/tc_common.cuh -nt $o ] || [ include/fhvae_b200.h -nt $o ]; then
     nvcc $FLAGS -c -o $o $CS/$f.cu &
