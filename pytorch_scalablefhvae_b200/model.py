@@ -1009,10 +1009,15 @@ class _FHVAEPlan(_Plan):
         pre = dict(self.NETS)
         for bi, bh, n, boff in m._bias_blocks:       # fused (b_ih + b_hh), beside the transpose
             c.add("fhvae_add2", ptr(self.bsum, boff), m.poff(bi), m.poff(bh), n, side=2)
-        for k, buf in self.wave_packed.items():      # weight operand images: side stream 3, beside the x projection
+        # weight operand images: one side stream per stack (3, 5, 6), so that all three are built concurrently at the very
+        # start of the step and the first wavefront launch never waits for an image it does not need
+        self._pack_side = {}
+        for i, (k, buf) in enumerate(self.wave_packed.items()):
             _, whh0, _, _ = _lstm_names(dict(self.NETS)[k], 0)
             wih1, whh1, _, _ = _lstm_names(dict(self.NETS)[k], 1)
-            c.add("fhvae_lstm_wave_pack", m.poff(whh0), m.poff(wih1), m.poff(whh1), ptr(buf), self.H[k], 2, mode, side=3)
+            self._pack_side[k] = (3, 5, 6)[i] if os.environ.get("FHVAE_PACK_STREAMS", "3") == "3" else 3
+            c.add("fhvae_lstm_wave_pack", m.poff(whh0), m.poff(wih1), m.poff(whh1), ptr(buf), self.H[k], 2, mode,
+                  side=self._pack_side[k])
         Hz2, Hz1, Hd = self.H["z2"], self.H["z1"], self.H["dec"]
         wih_z2, _, _, _ = _lstm_names(pre["z2"], 0)
         wih_z1, _, _, _ = _lstm_names(pre["z1"], 0)
@@ -1042,8 +1047,15 @@ class _FHVAEPlan(_Plan):
         else:
             c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z2), F, ptr(self.P["z2", 0]), 4 * Hz2, TB, 4 * Hz2, F,
                             bias=self._bs("z2", 0))], mode)
-            c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
-                            4 * Hz1, F, bias=self._bs("z1", 0))], mode, side=1)
+            # The z1 encoder's projection runs beside the z2 recurrence (side stream 1).  It is forked right BEFORE the z2
+            # wavefront launch, behind the same dependencies: both become ready together, the wavefront (high-priority
+            # stream) takes its 128 SMs first and the 320 GEMM CTAs trickle in on the rest.  (Forked right behind the z2
+            # projection it started first and held the SMs: the wavefront launch became resident ~10 us late.)
+            z1_proj = lambda: c.gemm([gemm_nt(ptr(self.x_tm), F, m.poff(wih_z1), F + Z2, ptr(self.P["z1", 0]), 4 * Hz1, TB,
+                                              4 * Hz1, F, bias=self._bs("z1", 0))], mode, side=1)
+            if not self.wave["z2"] or os.environ.get("FHVAE_Z1PROJ_LATE", "1") == "0":
+                z1_proj()
+                z1_proj = None
 
         def stack(k, q0):
             H = self.H[k]
@@ -1088,17 +1100,24 @@ class _FHVAEPlan(_Plan):
             c.gemm([gemm_nt(ptr(self.zcat, qoff), Z1 + Z2, Wq, ld_wq, ptr(Q), NQ, B, NQ, Kq, bias=bq or 0)], mode)
 
         # z2 encoder -> head -> sample (into zcat[:, Z1:]) -> time-invariant z2 part of the z1 encoder's input (Q)
-        c.join(3)              # packed weight operands
+        for k in ("z2",) if "z2" in self.wave_packed else ():
+            c.join(self._pack_side[k])          # this stack's packed weight operands
+        if not self.tma_proj and z1_proj is not None:
+            z1_proj()
         stack("z2", None)
         head_stage("z2", Hz2, "z2_gauss_layer.mulayer.weight", "z2_gauss_layer.mulayer.bias", self.z2head, Z2,
                    self.eps2, Z1, m.poff(wih_z1, F), F + Z2, None, Z1, Z2, self.Q["z1"], 4 * Hz1)
         self._disc_fwd()       # log q(i|z2) only needs the z2 posterior: side stream 2, beside the z1 / decoder stacks
         c.join(1)
+        if "z1" in self.wave_packed:
+            c.join(self._pack_side["z1"])
         stack("z1", ptr(self.Q["z1"]))
         # z1 head -> sample -> the decoder's whole (time-invariant) layer-0 input projection
         head_stage("z1", Hz1, "z1_gauss_layer.mulayer.weight", "z1_gauss_layer.mulayer.bias", self.z1head, Z1,
                    self.eps1, 0, m.poff(wih_d), Z1 + Z2, self._bs("dec", 0), 0, Z1 + Z2, self.Q["dec"], 4 * Hd)
         self.n_encode_calls = len(c.calls)
+        if "dec" in self.wave_packed:
+            c.join(self._pack_side["dec"])
         stack("dec", ptr(self.Q["dec"]))
         Ld = self.L["dec"]
         if self.proj_head:
@@ -1183,7 +1202,7 @@ class _FHVAEPlan(_Plan):
             split([self.h[k, l] for k, _ in self.NETS for l in range(self.L[k]) if not self.wave[k]] +
                   ([] if self.tma_proj else [self.x_tm]))
 
-        split_mode = int(os.environ.get("FHVAE_WGRAD_SPLIT", "1"))     # 0: one launch behind the BPTT; 1: layer-1 half there,
+        split_mode = int(os.environ.get("FHVAE_WGRAD_SPLIT", "2"))     # 0: one launch behind the BPTT; 1: layer-1 half there,
         split_wgrad = split_mode != 0 and self.__dict__.get("_wgrad_split", True)   # layer-0 half deferred; 2: all deferred
 
         def stack_bwd(k, dh_all_top, dh_last_of, extra=None, defer=None):
