@@ -661,7 +661,7 @@ class _Plan:
         fused = nf[-1] == "fhvae_elbo_fwd_bwd"
         jD = max(i for i, c_ in enumerate(bwd.calls) if c_[1] == "join" and c_[2] == 2)
         head = 0 if fused else 2                       # unfused: [step_coef, elbo_bwd] open the backward list
-        assert set(nb[head:head + 4]) == set(self._DISC_BWD), nb[:8]
+        assert sum(n_ in self._DISC_BWD for n_ in nb[:jD]) == 4, nb[:12]
 
         def seg(calls, keep):
             cl = CallList()
@@ -670,7 +670,7 @@ class _Plan:
         s1 = seg(fwd.calls[:iA], fwd.keep)
         s2 = seg(fwd.calls[iA + 4:-1], fwd.keep)
         s3 = seg([fwd.calls[-1]] + (bwd.calls[:2] if not fused else []), fwd.keep + bwd.keep)
-        s4 = seg(bwd.calls[head + 4:jD], bwd.keep)
+        s4 = seg([c_ for c_ in bwd.calls[head:jD] if c_[1] not in self._DISC_BWD], bwd.keep)
         s5 = seg(bwd.calls[jD + 1:], bwd.keep)
         cache[k] = (s1, s2, s3, s4, s5)
         return cache[k]
@@ -885,8 +885,9 @@ class _Plan:
               ptr(self.z2head), ptr(self.mu2), ptr(self.nsegs), ptr(self.out), ptr(self.nan_flag),
               B, self.T, self.F, self.Z1, self.Z2)
 
-    def _tail_bwd(self, c: CallList, gflat, xhead, dxhead, xs_b, xs_t, lv_off):
-        """coef from upstream grads; ELBO bwd; disc bwd; table gradient (dense + sparse rows)."""
+    def _tail_bwd(self, c: CallList, gflat, xhead, dxhead, xs_b, xs_t, lv_off, disc=True):
+        """coef from upstream grads; ELBO bwd; disc bwd; table gradient (dense + sparse rows).  ``disc=False``: the
+        caller issues the discriminative chain itself (``_disc_bwd``) at a later point of the list."""
         m, B, Z2 = self.m, self.B, self.Z2
         f = self.f
         if not hasattr(self, "coef"):
@@ -905,7 +906,14 @@ class _Plan:
         c.add("fhvae_elbo_bwd", ptr(self.x), ptr(xhead), xs_b, xs_t, lv_off, ptr(self.z1head),
               ptr(self.z2head), ptr(self.mu2), ptr(coef), ptr(dxhead), ptr(self.dz1head),
               ptr(self.dz2head), ptr(self.dmu2), B, self.T, self.F, self.Z1, Z2)
-        g_qy = ptr(gout, 5 * B)
+        if disc:
+            self._disc_bwd(c, gflat)
+
+    def _disc_bwd(self, c: CallList, gflat):
+        m, B, Z2 = self.m, self.B, self.Z2
+        dtab = ptr(gflat, m._off["mu2_table"])
+        tab = ptr(m.mu2_table)
+        g_qy = ptr(self.gout, 5 * B)
         # the discriminative / table-gradient chain only meets the main sequence again at the z2 head: side stream 2
         c.add("fhvae_disc_bwd_segs", ptr(self.z2head), 2 * Z2, tab, self.N, Z2, ptr(self.lse),
               ptr(self.sumpm), self.nsplit, B, side=2)
@@ -1148,7 +1156,9 @@ class _FHVAEPlan(_Plan):
                     self.dgsum[k, l] = f(B, 4 * self.H[k])
             self.dzcat = f(B, Z1 + Z2)
             self.dh_rec, self.dc = self.xchg, f(B, Hmax)
-        self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F)
+        # (the discriminative chain is forked right before the decoder's BPTT launch, see below)
+        late_disc = os.environ.get("FHVAE_DISC_LATE", "1") != "0" and not m.detach_px
+        self._tail_bwd(c, gflat, self.xhead, self.dxhead, 2 * F, B * 2 * F, F, disc=not late_disc)
         cs: List = []          # bias column sums (one grouped side launch at the end)
 
         use_tma = self.tma_wgrad
@@ -1312,6 +1322,11 @@ class _FHVAEPlan(_Plan):
             cs.append(ColsumProblem(ptr(self.dxhead), g("dec_gauss_layer.mulayer.bias"), None, 2 * F, TB, 2 * F))
             c.gemm([gemm_nn(ptr(self.dxhead), 2 * F, m.poff("dec_gauss_layer.mulayer.weight"), Hd,
                             ptr(self.dhA), Hd, TB, Hd, 2 * F)], mode)
+            if late_disc:
+                # Forked here, behind the same dependencies as the decoder's BPTT launch: the wavefront (high-priority
+                # stream) takes its SMs first and the chain runs on the rest.  (Forked right behind the ELBO it held the
+                # SMs while the BPTT launch was becoming resident: 127 vs 105 us for that launch.)
+                self._disc_bwd(c, gflat)
             stack_bwd("dec", ptr(self.dhA), lambda l: None, defer=deferred if split_wgrad else None)
             wih_d = _lstm_names(pre["dec"], 0)[0]
             wg.append(gemm_tn(ptr(self.dgsum["dec", 0]), 4 * Hd, ptr(self.zcat), Z1 + Z2, g(wih_d), Z1 + Z2,
