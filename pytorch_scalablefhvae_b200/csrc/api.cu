@@ -1,5 +1,6 @@
 // C-ABI plumbing: error string, version, and the mode dispatch of the GEMM / LSTM entry points.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <atomic>
 #include "common.cuh"
 
@@ -8,6 +9,14 @@ namespace fhvae {
 static thread_local char g_err[512] = "";
 static std::atomic<unsigned long long> g_launches{0};
 void count_launches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+bool pdl_enabled(int family) {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("FHVAE_PDL");
+        v = e ? atoi(e) : 31;
+    }
+    return (v & family) != 0;
+}
 static std::atomic<int> g_deterministic{0};
 bool deterministic_mode() { return g_deterministic.load(std::memory_order_relaxed) != 0; }
 

@@ -58,9 +58,9 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(
         const int F4 = F >> 2;
         for (int e = tid; e < (TF >> 2); e += ELBO_THREADS) {
             const int t = e / F4, f = (e - t * F4) << 2;
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + t * F + f));
-            const float4 mv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
-            const float4 lv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
+            const float4 xv = __ldcg(reinterpret_cast<const float4*>(xb + t * F + f));
+            const float4 mv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
+            const float4 lv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
             float d;
             d = xv.x - mv.x; s += kLog2Pi + lv.x + d * d * expf(-lv.x);
             d = xv.y - mv.y; s += kLog2Pi + lv.y + d * d * expf(-lv.y);
@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwd_kernel(
         }
         for (int d = tid; d < Z2; d += 32) {
             const float mu = z2head[(int64_t)b * 2 * Z2 + d], lv = z2head[(int64_t)b * 2 * Z2 + Z2 + d];
-            const float m2 = __ldg(mu2 + (int64_t)b * Z2 + d);
+            const float m2 = __ldcg(mu2 + (int64_t)b * Z2 + d);
             const float dm = mu - m2;
             k2 += 1.f + lv - kPz2Logvar - (dm * dm + expf(lv)) * kInvS2;
             pm += kLog2Pi + m2 * m2;
@@ -121,9 +121,9 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_bwd_kernel(
         const int F4 = F >> 2;
         for (int e = tid; e < (TF >> 2); e += ELBO_THREADS) {
             const int t = e / F4, f = (e - t * F4) << 2;
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + t * F + f));
-            const float4 mv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
-            const float4 lv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
+            const float4 xv = __ldcg(reinterpret_cast<const float4*>(xb + t * F + f));
+            const float4 mv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
+            const float4 lv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
             float4 gm, gl;
             float d, iv;
             d = xv.x - mv.x; iv = expf(-lv.x); gm.x = c_px * d * iv; gl.x = -0.5f * c_px * (1.f - d * d * iv);
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_bwd_kernel(
     }
     for (int d = tid; d < Z2; d += ELBO_THREADS) {
         const float mu = z2head[(int64_t)b * 2 * Z2 + d], lv = z2head[(int64_t)b * 2 * Z2 + Z2 + d];
-        const float m2 = __ldg(mu2 + (int64_t)b * Z2 + d);
+        const float m2 = __ldcg(mu2 + (int64_t)b * Z2 + d);
         const float dm = mu - m2;
         dz2head[(int64_t)b * 2 * Z2 + d] = -c_k2 * dm * kInvS2;
         dz2head[(int64_t)b * 2 * Z2 + Z2 + d] = 0.5f * c_k2 * (1.f - kInvS2 * expf(lv));
@@ -163,14 +163,16 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_bwd_kernel(
 // expressions in the same order as elbo_fwd_kernel / step_coef_kernel / elbo_bwd_kernel: bit-identical results.
 template <bool VEC>
 __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwdbwd_kernel(
-    const float* __restrict__ x, const float* __restrict__ xhead, int64_t xs_b, int64_t xs_t, int64_t lv_off,
-    const float* __restrict__ z1head, const float* __restrict__ z2head, const float* __restrict__ mu2,
-    const int64_t* __restrict__ nsegs, const float* __restrict__ gout, int detach_px, int prior_grad,
-    float* __restrict__ out5, int* __restrict__ nan_flag, float* __restrict__ dxhead, float* __restrict__ dz1head,
-    float* __restrict__ dz2head, float* __restrict__ dmu2, int B, int T, int F, int Z1, int Z2) {
+    const float* x, const float* xhead, int64_t xs_b, int64_t xs_t, int64_t lv_off,
+    const float* z1head, const float* z2head, const float* mu2,
+    const int64_t* nsegs, const float* gout, int detach_px, int prior_grad,
+    float* out5, int* nan_flag, float* dxhead, float* dz1head,
+    float* dz2head, float* dmu2, int B, int T, int F, int Z1, int Z2) {
     __shared__ float red[4];
     const int b = blockIdx.x, tid = threadIdx.x;
     const int TF = T * F;
+    pdl_launch_dependents();
+    pdl_wait();
     const float g0 = gout[b];
     const float c_px = detach_px ? 0.f : gout[B + b] + g0;
     const float c_k1 = gout[2 * B + b] + g0, c_k2 = gout[3 * B + b] + g0;
@@ -183,9 +185,9 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwdbwd_kernel(
         const int F4 = F >> 2;
         for (int e = tid; e < (TF >> 2); e += ELBO_THREADS) {
             const int t = e / F4, f = (e - t * F4) << 2;
-            const float4 xv = __ldg(reinterpret_cast<const float4*>(xb + t * F + f));
-            const float4 mv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
-            const float4 lv = __ldg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
+            const float4 xv = __ldcg(reinterpret_cast<const float4*>(xb + t * F + f));
+            const float4 mv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + f));
+            const float4 lv = __ldcg(reinterpret_cast<const float4*>(hb + t * xs_t + lv_off + f));
             float4 gm, gl;
             float d, iv;
             d = xv.x - mv.x; iv = expf(-lv.x); s += kLog2Pi + lv.x + d * d * iv; gm.x = c_px * d * iv; gl.x = -0.5f * c_px * (1.f - d * d * iv);
@@ -214,7 +216,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwdbwd_kernel(
         }
         for (int d = tid; d < Z2; d += 32) {
             const float mu = z2head[(int64_t)b * 2 * Z2 + d], lv = z2head[(int64_t)b * 2 * Z2 + Z2 + d];
-            const float m2 = __ldg(mu2 + (int64_t)b * Z2 + d);
+            const float m2 = __ldcg(mu2 + (int64_t)b * Z2 + d);
             const float dm = mu - m2;
             k2 += 1.f + lv - kPz2Logvar - (dm * dm + expf(lv)) * kInvS2;
             pm += kLog2Pi + m2 * m2;
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(ELBO_THREADS) elbo_fwdbwd_kernel(
     }
     for (int d = tid; d < Z2; d += ELBO_THREADS) {
         const float mu = z2head[(int64_t)b * 2 * Z2 + d], lv = z2head[(int64_t)b * 2 * Z2 + Z2 + d];
-        const float m2 = __ldg(mu2 + (int64_t)b * Z2 + d);
+        const float m2 = __ldcg(mu2 + (int64_t)b * Z2 + d);
         const float dm = mu - m2;
         dz2head[(int64_t)b * 2 * Z2 + d] = -c_k2 * dm * kInvS2;
         dz2head[(int64_t)b * 2 * Z2 + Z2 + d] = 0.5f * c_k2 * (1.f - kInvS2 * expf(lv));
@@ -323,11 +325,11 @@ extern "C" int fhvae_elbo_fwd_bwd(const float* x, const float* xhead, int64_t xs
                     "elbo_fwd_bwd: null pointer");
     FHVAE_CHECK_ARG(B > 0 && T > 0 && F > 0 && Z1 > 0 && Z2 > 0, "elbo_fwd_bwd: bad size");
     if (vec_ok(x, xhead, dxhead, F, xs_b, xs_t, lv_off))
-        elbo_fwdbwd_kernel<true><<<B, ELBO_THREADS, 0, as_stream(stream)>>>(
+        launch_pdl(PDL_ELBO, elbo_fwdbwd_kernel<true>, dim3(B), dim3(ELBO_THREADS), 0, as_stream(stream),
             x, xhead, xs_b, xs_t, lv_off, z1head, z2head, mu2, nsegs, gout, detach_px, prior_grad, out5, nan_flag, dxhead,
             dz1head, dz2head, dmu2, B, T, F, Z1, Z2);
     else
-        elbo_fwdbwd_kernel<false><<<B, ELBO_THREADS, 0, as_stream(stream)>>>(
+        launch_pdl(PDL_ELBO, elbo_fwdbwd_kernel<false>, dim3(B), dim3(ELBO_THREADS), 0, as_stream(stream),
             x, xhead, xs_b, xs_t, lv_off, z1head, z2head, mu2, nsegs, gout, detach_px, prior_grad, out5, nan_flag, dxhead,
             dz1head, dz2head, dmu2, B, T, F, Z1, Z2);
     FHVAE_LAUNCH_CHECK("elbo_fwd_bwd");

@@ -50,7 +50,7 @@ __device__ __forceinline__ void load_tile_c(const float* __restrict__ src, long 
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int gr = row0 + warp * (NV * RPW) + i * RPW + rg;
-        v[i] = (gr < rows && gk + 4 <= kend) ? __ldg(reinterpret_cast<const float4*>(src + (long long)gr * rs + gk))
+        v[i] = (gr < rows && gk + 4 <= kend) ? __ldcg(reinterpret_cast<const float4*>(src + (long long)gr * rs + gk))
                                              : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 }
@@ -105,12 +105,12 @@ __device__ __forceinline__ void load_tile_mn(const float* __restrict__ src, long
         if (k < kend && m < rows) {
             const float* p = src + (long long)k * ks + m;
             if (vec && m + 8 <= rows) {
-                x = __ldg(reinterpret_cast<const float4*>(p));
-                y = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                x = __ldcg(reinterpret_cast<const float4*>(p));
+                y = __ldcg(reinterpret_cast<const float4*>(p) + 1);
             } else {
                 float t[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = (m + j < rows) ? __ldg(p + j) : 0.f;
+                for (int j = 0; j < 8; ++j) t[j] = (m + j < rows) ? __ldcg(p + j) : 0.f;
                 x = make_float4(t[0], t[1], t[2], t[3]);
                 y = make_float4(t[4], t[5], t[6], t[7]);
             }
@@ -189,20 +189,20 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ src, long lo
             if (ks == 1) {
                 const float* p = src + (long long)gr * rs + gk;
                 if (vec && gk + 8 <= kend) {
-                    const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-                    const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+                    const float4 a = __ldcg(reinterpret_cast<const float4*>(p));
+                    const float4 b = __ldcg(reinterpret_cast<const float4*>(p) + 1);
                     v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
                     v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
                 } else {
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
-                        if (gk + j < kend) v[i][j] = __ldg(p + j);
+                        if (gk + j < kend) v[i][j] = __ldcg(p + j);
                 }
             } else {   // rows contiguous: coalesced across the warp for every k
                 const float* p = src + (long long)gk * ks + gr;
 #pragma unroll
                 for (int j = 0; j < 8; ++j)
-                    if (gk + j < kend) v[i][j] = __ldg(p + (long long)j * ks);
+                    if (gk + j < kend) v[i][j] = __ldcg(p + (long long)j * ks);
             }
         }
     }
@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
     const int nit = kb1 - kb0;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     GTL(0);
+    pdl_launch_dependents();
 
     if (warp == TCT / 32) tmem_alloc<BN>(tmem_slot);
     if (tid == 0) {
@@ -271,6 +272,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
     tc_fence_after();
     const uint32_t tmem_d = *tmem_slot;
     const uint32_t idesc = make_idesc_bf16(BM, BN) | ((uint32_t)P.a_mn << 15) | ((uint32_t)P.b_mn << 16);
+    pdl_wait();                 // barrier / TMEM setup above overlaps the preceding launch's tail
     GTL(1);
 
     if (warp == TCT / 32) {
@@ -377,7 +379,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
                 __syncwarp();
                 const int gn = n0 + col0 + lane;                  // lane = column now
                 const bool nok = gn < P.N;
-                const float bv = (nok && P.bias && (!atomic || split == 0)) ? __ldg(P.bias + gn) : 0.f;
+                const float bv = (nok && P.bias && (!atomic || split == 0)) ? __ldcg(P.bias + gn) : 0.f;
                 const int mrow0 = m0 + q * 32;
                 const int rmax = min(32, P.M - mrow0);
                 if (nok) {
@@ -387,7 +389,7 @@ __global__ void __launch_bounds__(TCT_ALL, 2) gemm_tc_kernel(const __grid_consta
                         // than scalar atomics: the L2 atomic units were the tail of every weight-gradient GEMM)
                         const int cgp = lane & 7, rr = lane >> 3;
                         float* cq = P.C + (long long)mrow0 * P.ldc + n0 + col0 + cgp * 4;
-                        const float4 b4 = (P.bias && split == 0) ? __ldg(reinterpret_cast<const float4*>(P.bias + n0 + col0 + cgp * 4))
+                        const float4 b4 = (P.bias && split == 0) ? __ldcg(reinterpret_cast<const float4*>(P.bias + n0 + col0 + cgp * 4))
                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
@@ -519,8 +521,8 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         FHVAE_LAUNCH_CHECK("gemm_tc_zero");
     }
     if (total > 0) {
-        if (x3) gemm_tc_kernel<true><<<total, TCT_ALL, Cfg<true>::SMEM, st>>>(tb);
-        else    gemm_tc_kernel<false><<<total, TCT_ALL, Cfg<false>::SMEM, st>>>(tb);
+        if (x3) launch_pdl(PDL_GEMM, gemm_tc_kernel<true>, dim3(total), dim3(TCT_ALL), Cfg<true>::SMEM, st, tb);
+        else    launch_pdl(PDL_GEMM, gemm_tc_kernel<false>, dim3(total), dim3(TCT_ALL), Cfg<false>::SMEM, st, tb);
         FHVAE_LAUNCH_CHECK("gemm_tc");
     }
     if (nsmall > 0) return gemm_batch_simt(small, nsmall, st);

@@ -51,7 +51,7 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ W, int64_t 
             float4 v[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-                if (r0 + i * rpp < rows) v[i] = __ldg(src + (int64_t)(r0 + i * rpp) * ld4);
+                if (r0 + i * rpp < rows) v[i] = __ldcg(src + (int64_t)(r0 + i * rpp) * ld4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int r = r0 + i * rpp;
@@ -69,7 +69,7 @@ __device__ __forceinline__ void stage_tile(const float* __restrict__ W, int64_t 
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int e = e0 + i * HT;
-                if (e < total) { const int r = e / cols, c = e - r * cols; v[i] = __ldg(W + (int64_t)r * ld + c); }
+                if (e < total) { const int r = e / cols, c = e - r * cols; v[i] = __ldcg(W + (int64_t)r * ld + c); }
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -106,6 +106,8 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
     const int b0 = blockIdx.x * HB;
     const int K = a.nsrc * a.H, Z2 = 2 * a.Z;
     const FastDiv dK(K), dH(a.H), dZ(a.Z), dZ2(Z2), dKq(a.Kq > 0 ? a.Kq : 1);
+    pdl_launch_dependents();
+    pdl_wait();
     HTL(0, 0);
     // every independent global read of the CTA is issued up front (they overlap the first weight tile):
     // its HB rows of final hidden states, eps, and the part of the projection input another launch produced
@@ -116,13 +118,13 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
         hreg[i] = 0.f;
         if (e < HB * K) {
             const int r = dK.div(e), k = dK.mod(e), l = dH.div(k), u = dH.mod(k);
-            if (b0 + r < a.B) hreg[i] = __ldg(a.src[l] + (int64_t)(b0 + r) * a.ld_src + u);
+            if (b0 + r < a.B) hreg[i] = __ldcg(a.src[l] + (int64_t)(b0 + r) * a.ld_src + u);
         }
     }
     float epsreg = 0.f, zreg = 0.f;
     if (a.eps && tid < HB * a.Z) {
         const int r = dZ.div(tid), d = dZ.mod(tid);
-        if (b0 + r < a.B) epsreg = __ldg(a.eps + (int64_t)(b0 + r) * a.Z + d);
+        if (b0 + r < a.B) epsreg = __ldcg(a.eps + (int64_t)(b0 + r) * a.Z + d);
     }
     if (a.Q && tid < HB * a.Kq) {
         const int r = dKq.div(tid), col = a.qoff + dKq.mod(tid);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
                     for (int r = 0; r < HB; ++r) acc[r] += __shfl_xor_sync(0xffffffffu, acc[r], d);
                 }
                 if (valid && p == 0) {
-                    const float bv = a.bias ? __ldg(a.bias + n0 + n) : 0.f;
+                    const float bv = a.bias ? __ldcg(a.bias + n0 + n) : 0.f;
 #pragma unroll
                     for (int r = 0; r < HB; ++r) s_head[r][n0 + n] = acc[r] + bv;
                 }
@@ -220,7 +222,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(const __grid_constant__ He
 #pragma unroll
                 for (int r = 0; r < HB; ++r) acc[r] = fmaf(wv, s_z[r][j], acc[r]);
             }
-            const float bv = a.bias_q ? __ldg(a.bias_q + n0 + n) : 0.f;
+            const float bv = a.bias_q ? __ldcg(a.bias_q + n0 + n) : 0.f;
 #pragma unroll
             for (int r = 0; r < HB; ++r)
                 if (b0 + r < a.B) a.Q[(int64_t)(b0 + r) * a.NQ + n0 + n] = acc[r] + bv;
@@ -246,12 +248,14 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
     const int b0 = blockIdx.x * HB;
     const int Z2 = 2 * a.Z;
     const FastDiv dNG(a.NG > 0 ? a.NG : 1), dKq(a.Kq > 0 ? a.Kq : 1), dZ(a.Z), dZ2(Z2), dH(a.H > 0 ? a.H : 1);
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- dz[b][j] = sum_n dgsum[b][n] Wq[n][j]: tiles of TR rows of Wq; lanes along j, the rows of a tile are
     // split across the warps, partial sums combined across warps in a fixed order
     if (a.dgsum) {
         for (int e = tid; e < HB * a.NG; e += HT) {
             const int r = dNG.div(e), n = dNG.mod(e);
-            s_g[r][n] = (b0 + r < a.B) ? __ldg(a.dgsum + (int64_t)(b0 + r) * a.NG + n) : 0.f;
+            s_g[r][n] = (b0 + r < a.B) ? __ldcg(a.dgsum + (int64_t)(b0 + r) * a.NG + n) : 0.f;
         }
         const int TR = min(a.NG, HTILE / a.Kq / 8 * 8);
         float acc[HB][4];                                      // Kq <= 128: up to 4 columns per lane
@@ -304,9 +308,9 @@ __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ He
             const int r = dZ.div(e), d = dZ.mod(e);
             if (b0 + r < a.B) {
                 const int64_t b = b0 + r;
-                const float lv = __ldg(a.head + b * Z2 + a.Z + d);
+                const float lv = __ldcg(a.head + b * Z2 + a.Z + d);
                 const float g = a.dzcat[b * a.ld_dz + a.roff + d];
-                const float gmu = g, glv = g * 0.5f * __ldg(a.eps + b * a.Z + d) * expf(0.5f * lv);
+                const float gmu = g, glv = g * 0.5f * __ldcg(a.eps + b * a.Z + d) * expf(0.5f * lv);
                 float* pm = a.dhead + b * Z2 + d;
                 float* pl = a.dhead + b * Z2 + a.Z + d;
                 if (a.accumulate) { *pm += gmu; *pl += glv; } else { *pm = gmu; *pl = glv; }
@@ -371,10 +375,12 @@ __global__ void step_coef_kernel(const float* __restrict__ gout, const int64_t* 
 }
 
 // loss = -(1/B) sum_b (lb[b] + alpha * log_qy[b])    (train_model.py:243-251); one CTA, fixed order
-__global__ void __launch_bounds__(256) loss_mean_kernel(const float* __restrict__ lb, const float* __restrict__ lqy,
-                                                        float alpha, int B, float* __restrict__ loss) {
+__global__ void __launch_bounds__(256) loss_mean_kernel(const float* lb, const float* lqy,
+                                                        float alpha, int B, float* loss) {
     __shared__ float red[8];
     float s = 0.f;
+    pdl_launch_dependents();
+    pdl_wait();
     for (int b = threadIdx.x; b < B; b += 256) s += lb[b] + alpha * lqy[b];
     s = warp_sum(s);
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -407,7 +413,7 @@ extern "C" int fhvae_head_fwd(const float* src0, const float* src1, int64_t ld_s
         cudaFuncSetAttribute(head_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HTILE * 4);
         attr_f = true;
     }
-    head_fwd_kernel<<<cdiv(B, HB), HT, HTILE * 4, as_stream(stream)>>>(a);
+    launch_pdl(PDL_HEADS, head_fwd_kernel, dim3(cdiv(B, HB)), dim3(HT), HTILE * 4, as_stream(stream), a);
     FHVAE_LAUNCH_CHECK("head_fwd");
     return 0;
 }
@@ -428,7 +434,7 @@ extern "C" int fhvae_head_bwd(const float* dgsum, int NG, const float* Wq, int64
         cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HTILE * 4);
         attr_b = true;
     }
-    head_bwd_kernel<<<cdiv(B, HB), HT, HTILE * 4, as_stream(stream)>>>(a);
+    launch_pdl(PDL_HEADS, head_bwd_kernel, dim3(cdiv(B, HB)), dim3(HT), HTILE * 4, as_stream(stream), a);
     FHVAE_LAUNCH_CHECK("head_bwd");
     return 0;
 }
@@ -443,7 +449,7 @@ extern "C" int fhvae_step_coef(const float* gout, const int64_t* nsegs, float* c
 
 extern "C" int fhvae_loss_mean(const float* lb, const float* log_qy, float alpha, int B, float* loss, void* stream) {
     FHVAE_CHECK_ARG(lb && log_qy && loss && B > 0, "loss_mean: bad argument");
-    loss_mean_kernel<<<1, 256, 0, as_stream(stream)>>>(lb, log_qy, alpha, B, loss);
+    launch_pdl(PDL_HEADS, loss_mean_kernel, dim3(1), dim3(256), 0, as_stream(stream), lb, log_qy, alpha, B, loss);
     FHVAE_LAUNCH_CHECK("loss_mean");
     return 0;
 }

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
         uint32_t hi[HF * 16], lo[HF * 16];
 #pragma unroll
         for (int i = 0; i < KQ / 4; ++i) {
-            const float4 w4 = __ldg(reinterpret_cast<const float4*>(src) + i);
+            const float4 w4 = __ldcg(reinterpret_cast<const float4*>(src) + i);
             const float v[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
@@ -245,8 +245,8 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
         uint8_t* dst = a.out + PK::fwdS(L, rank);
 #pragma unroll 2
         for (int i = 0; i < KQ / 8; ++i) {
-            const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
-            const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
+            const float4 x0 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i);
+            const float4 x1 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
             const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
             const uint32_t off = (uint32_t)(cg * (KQ / 8) + i) * (NC * 16) + (uint32_t)r * 16;
             uint4 hi, lo;
@@ -267,8 +267,8 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
             const int n = hf * 128 + q * 32 + lane;
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-                const float v0 = __ldg(W + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
-                const float v1 = __ldg(W + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
+                const float v0 = __ldcg(W + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
+                const float v1 = __ldcg(W + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
                 const uint32_t h = pack_bf16(v0, v1);
                 hi[hf * 16 + j] = h;
                 lo[hf * 16 + j] = pack_bf16(v0 - __uint_as_float(h << 16), v1 - __uint_as_float(h & 0xffff0000u));
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(WNT) wave_pack_kernel(const __grid_constant__ 
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const int k = kc * 8 + j, g = k >> 5, u = k & 31;
-                v[j] = __ldg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
+                v[j] = __ldcg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
             }
             const uint32_t off = (uint32_t)(n >> 7) * (128 * NC * 2) + (uint32_t)(kc * 128 + (n & 127)) * 16;
             uint4 hi, lo;
@@ -313,7 +313,7 @@ __device__ __forceinline__ void wave_load_T_image(const uint8_t* img, int warp, 
         const uint4* src = reinterpret_cast<const uint4*>(img) + (size_t)(warp * ((X3 ? 2 : 1) * HF * 4) + part * HF * 4) * 32 + lane;
         uint4 u[HF * 4];
 #pragma unroll
-        for (int v = 0; v < HF * 4; ++v) u[v] = __ldg(src + v * 32);
+        for (int v = 0; v < HF * 4; ++v) u[v] = __ldcg(src + v * 32);
 #pragma unroll
         for (int hf = 0; hf < HF; ++hf) {
             const uint32_t w[16] = {u[4 * hf].x,     u[4 * hf].y,     u[4 * hf].z,     u[4 * hf].w,
@@ -455,7 +455,6 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         mbar_init(&hb_full[0], NT / 32 + (WAVE_TMA ? 1 : 0)); mbar_init(&hb_full[1], NT / 32 + (WAVE_TMA ? 1 : 0));
         mbar_init(rec_done, 1); mbar_init(p1_done, 1); mbar_init(w_full, 1);
         fence_mbar_init();
-        *epoch_slot = *cnt;
         *p1_safe = 0;
         if (p1_duty && a.packed)
             wave_load_S_image(a.packed + WavePack<X3, CH>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
@@ -464,7 +463,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t fbase = (*epoch_slot) << 6;
+    uint32_t fbase = 0;              // flag base = launch epoch << 6: read by the compute warps after pdl_wait()
     WTL(3, 15);
     constexpr uint32_t W_LBO = WNC * 16, H_LBO = NB * 16, SBO_ = 128;
     const uint32_t tmem_d = tmem_base + ACOL;                  // recurrent accumulators [NACC][NB]
@@ -537,6 +536,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             // payload (already in the UMMA operand layout) straight into the operand buffer of step t; the issuer's
             // hb_full barrier counts the bytes.  No compute warp touches the exchange.
             const int src = lane + (lane >= rank ? 1 : 0);
+            pdl_wait();
+            fbase = *reinterpret_cast<volatile uint32_t*>(cnt) << 6;
             constexpr uint32_t PART_BYTES = 4 * H_LBO;                       // 4 K-chunks x 32 rows x 16 B = 2 KB
             constexpr uint32_t PULL_MASK = (1u << (WG - 1)) - 1;
             for (int t = 1; t < nsteps; ++t) {
@@ -580,7 +581,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * KQ;
             float4 wv[KQ / 4];
 #pragma unroll
-            for (int i = 0; i < KQ / 4; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = 0; i < KQ / 4; ++i) wv[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
 #pragma unroll
             for (int hf = 0; hf < HF; ++hf) {
                 uint32_t hi[16], lo[16];
@@ -607,8 +608,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
             const int r = q * 32 + lane;
 #pragma unroll 2
             for (int i = 0; i < KQ / 8; ++i) {
-                const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
-                const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
+                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i);
+                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
                 const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t off = (uint32_t)(cg * (KQ / 8) + i) * W_LBO + (uint32_t)r * 16;
                 if (X3) {
@@ -628,13 +629,17 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
         __syncthreads();
         tc_fence_after();
         WTL(7, 15);
+        // everything above touched only this launch's own state and the weight images (older than any launch still
+        // in flight); from here on: outputs of the preceding launches, the exchange buffer and its epoch counter
+        pdl_wait();
+        fbase = *reinterpret_cast<volatile uint32_t*>(cnt) << 6;
         // time-invariant addend for this thread's (gate q, unit lane) column, rows cg*CPW ..
         const int col = q * CH + rank * UC + lane;
         float qv[CPW];
         {
-            const float bias = (layer == 1 && a.b1) ? __ldg(a.b1 + col) : 0.f;
+            const float bias = (layer == 1 && a.b1) ? __ldcg(a.b1 + col) : 0.f;
 #pragma unroll
-            for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
+            for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldcg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
         }
         WTL(1, 15);
         float creg[RPT];
@@ -673,7 +678,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
                     if (layer == 0) {
                         const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
 #pragma unroll
-                        for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+                        for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldcg(Pt + (size_t)b * H4) : 0.f;
                     } else {
 #pragma unroll
                         for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
@@ -911,7 +916,6 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
         mbar_init(&rec_done[0], 1); mbar_init(&rec_done[1], 1);
         mbar_init(&p1_done[0], 1); mbar_init(&p1_done[1], 1); mbar_init(w_full, 1);
         fence_mbar_init();
-        *epoch_slot = *cnt;
         if (p1_duty && a.packed)
             wave_load_S_image(a.packed + WavePack<X3>::fwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
@@ -919,7 +923,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t fbase = (*epoch_slot) << 6;
+    pdl_wait();                      // (experimental kernel: no prologue overlap)
+    const uint32_t fbase = *reinterpret_cast<volatile uint32_t*>(cnt) << 6;
     constexpr uint32_t W_LBO = WNC * 16, H_LBO = NB * 16, SBO_ = 128;
     const uint32_t tmem_d = tmem_base + ACOL;                  // recurrent accumulators [chain][NACC][NBC]
     const uint32_t tmem_p = tmem_d + 2 * NACC * NBC;           // projection accumulators [buffer][NACC][NB]
@@ -1014,7 +1019,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
             const float* src = W_hh + (size_t)(q * CH + rank * UC + lane) * CH + cg * 64;
             float4 wv[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) wv[i] = __ldg(reinterpret_cast<const float4*>(src) + i);
+            for (int i = 0; i < 16; ++i) wv[i] = __ldcg(reinterpret_cast<const float4*>(src) + i);
 #pragma unroll
             for (int hf = 0; hf < 2; ++hf) {
                 uint32_t hi[16], lo[16];
@@ -1039,8 +1044,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
             const int r = q * 32 + lane;
 #pragma unroll 2
             for (int i = 0; i < 8; ++i) {
-                const float4 x0 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i);
-                const float4 x1 = __ldg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
+                const float4 x0 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i);
+                const float4 x1 = __ldcg(reinterpret_cast<const float4*>(s1) + 2 * i + 1);
                 const float v[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
                 const uint32_t off = (uint32_t)(cg * 8 + i) * W_LBO + (uint32_t)r * 16;
                 if (X3) {
@@ -1061,9 +1066,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
         const int col = q * CH + rank * UC + lane;
         float qv[CPW];
         {
-            const float bias = (layer == 1 && a.b1) ? __ldg(a.b1 + col) : 0.f;
+            const float bias = (layer == 1 && a.b1) ? __ldcg(a.b1 + col) : 0.f;
 #pragma unroll
-            for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
+            for (int b = 0; b < CPW; ++b) qv[b] = bias + (Q ? __ldcg(Q + (size_t)(b0 + cg * CPW + b) * H4 + col) : 0.f);
         }
         float creg[RPT];
 #pragma unroll
@@ -1160,7 +1165,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd2_kernel(const __grid_co
                 if (layer == 0) {
                     const float* Pt = P ? P + ((size_t)t * B + b0 + cg * CPW) * H4 + col : nullptr;
 #pragma unroll
-                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldg(Pt + (size_t)b * H4) : 0.f;
+                    for (int b = 0; b < CPW; ++b) pv[b] = Pt ? __ldcg(Pt + (size_t)b * H4) : 0.f;
                 } else {
 #pragma unroll
                     for (int j = 0; j < CPW / 2; ++j) pl[j] = ld_ll(p1x + (size_t)t * (WG * WPSLICE) + llw + j * 128);
@@ -1320,7 +1325,6 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
         mbar_init(&g_full[0], NT / 32); mbar_init(&g_full[1], NT / 32); mbar_init(g_pro, NT / 32);
         mbar_init(rec_done, 1); mbar_init(w_full, 1);
         fence_mbar_init();
-        *epoch_slot = *cnt;
         if (bottom && a.packed)
             wave_load_S_image(a.packed + WavePack<X3, CH>::bwdS(a.L, rank), smem_u32(smem + S::W_OFF), S::W_BYTES, w_full);
     }
@@ -1328,7 +1332,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const uint32_t fbase = (*epoch_slot) << 6;
+    uint32_t fbase = 0;              // flag base = launch epoch << 6: read by the compute warps after pdl_wait()
     const uint32_t tmem_acc = tmem_base + ACOL;
     constexpr uint32_t idesc = make_idesc_bf16(128, NB);
     constexpr uint32_t W_LBO = 128 * 16, G_LBO = NB * 16, SBO_ = 128;
@@ -1418,8 +1422,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
                 uint32_t hi[16], lo[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float v0 = __ldg(W_hh + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
-                    const float v1 = __ldg(W_hh + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
+                    const float v0 = __ldcg(W_hh + (size_t)(g * CH + rank * UC + 2 * j) * CH + n);
+                    const float v1 = __ldcg(W_hh + (size_t)(g * CH + rank * UC + 2 * j + 1) * CH + n);
                     hi[j] = pack_bf16(v0, v1);
                     lo[j] = pack_bf16(v0 - __uint_as_float(hi[j] << 16), v1 - __uint_as_float(hi[j] & 0xffff0000u));
                 }
@@ -1440,7 +1444,7 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int k = kc * 8 + j, g = k >> 5, u = k & 31;
-                    v[j] = __ldg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
+                    v[j] = __ldcg(a.Wih1 + (size_t)(g * CH + rank * UC + u) * CH + n);
                 }
                 const uint32_t off = (uint32_t)(n >> 7) * S::W_HALF + (uint32_t)(kc * 128 + (n & 127)) * 16;
                 if (X3) {
@@ -1458,6 +1462,8 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
+        pdl_wait();                      // (see the forward kernel: the prologue above overlaps the preceding launch)
+        fbase = *reinterpret_cast<volatile uint32_t*>(cnt) << 6;
 
         // dgates1_t slice of the layer above -> G1[buf]: 2048 (1024) LL words, 4 (2) per thread
         auto pull_dg = [&](int t, int buf) {
@@ -1527,14 +1533,14 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
             for (int i = 0; i < RPT; ++i) {
                 const int b = b0 + warp * RPT + i;
                 const size_t r4 = ((size_t)t * B + b) * H4, r1 = ((size_t)t * B + b) * CH;
-                a_i[i] = __ldg(acts + r4 + ucol);
-                a_f[i] = __ldg(acts + r4 + CH + ucol);
-                a_g[i] = __ldg(acts + r4 + 2 * CH + ucol);
-                a_o[i] = __ldg(acts + r4 + 3 * CH + ucol);
-                c_t[i] = __ldg(c_all + r1 + ucol);
-                c_p[i] = t ? __ldg(c_all + r1 - (size_t)B * CH + ucol) : 0.f;
-                float d = dh_all ? __ldg(dh_all + r1 + ucol) : 0.f;
-                if (t == T - 1 && dh_last) d += __ldg(dh_last + (size_t)b * CH + ucol);
+                a_i[i] = __ldcg(acts + r4 + ucol);
+                a_f[i] = __ldcg(acts + r4 + CH + ucol);
+                a_g[i] = __ldcg(acts + r4 + 2 * CH + ucol);
+                a_o[i] = __ldcg(acts + r4 + 3 * CH + ucol);
+                c_t[i] = __ldcg(c_all + r1 + ucol);
+                c_p[i] = t ? __ldcg(c_all + r1 - (size_t)B * CH + ucol) : 0.f;
+                float d = dh_all ? __ldcg(dh_all + r1 + ucol) : 0.f;
+                if (t == T - 1 && dh_last) d += __ldcg(dh_last + (size_t)b * CH + ucol);
                 dh[i] = d;
             }
             if (k > 0 || bottom) {
@@ -1716,8 +1722,13 @@ static int wave_launch(K kern, const char* name, int grid, size_t smem, void* ar
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
     cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = wave_cooperative() ? 1 : 0;
+    if (wave_cooperative()) {
+        at[0].id = cudaLaunchAttributeCooperative;
+        at[0].val.cooperative = 1;
+    } else {                                    // the prologue (barriers, TMEM, weight images) overlaps the launch before
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = pdl_enabled(PDL_WAVE) ? 1 : 0;
+    }
     cfg.attrs = at;
     cfg.numAttrs = 1;
     void* kargs[1] = {args};

@@ -110,12 +110,14 @@ __global__ void rows_copy_kernel(const float* __restrict__ src, const int64_t* _
 
 // ---------------------------------------------------------------- K9: Adam -----------------------
 // torch.optim.Adam (no weight decay / amsgrad): m,v EMA; p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps).
-__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* __restrict__ g,
+__global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, const float* g,
                                                         float* __restrict__ m, float* __restrict__ v,
                                                         int64_t n, float lr, float beta1, float beta2,
                                                         float eps, float gscale, int32_t* step,
                                                         uint32_t* done) {
     __shared__ float s_ss, s_bc2;
+    pdl_launch_dependents();
+    pdl_wait();
     const int t = *reinterpret_cast<volatile int32_t*>(step) + 1;
     if (threadIdx.x == 0) {
         const double bc1 = 1.0 - pow((double)beta1, (double)t);
@@ -130,7 +132,7 @@ __global__ void __launch_bounds__(256) adam_flat_kernel(float* __restrict__ p, c
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
         float4 pv = reinterpret_cast<float4*>(p)[i];
-        float4 gv = __ldg(reinterpret_cast<const float4*>(g) + i);
+        float4 gv = __ldcg(reinterpret_cast<const float4*>(g) + i);   // (not ld.global.nc: see pdl_wait)
         float4 mv = reinterpret_cast<float4*>(m)[i];
         float4 vv = reinterpret_cast<float4*>(v)[i];
 #define ADAM1(c)                                             \
@@ -365,8 +367,8 @@ extern "C" int fhvae_adam_flat(float* p, const float* g, float* m, float* v, int
     const int cap = kNumSM * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    adam_flat_kernel<<<blocks, 256, 0, as_stream(stream)>>>(p, g, m, v, n, lr, beta1, beta2, eps,
-                                                            grad_scale, step, done_counter);
+    launch_pdl(PDL_MISC, adam_flat_kernel, dim3(blocks), dim3(256), 0, as_stream(stream), p, g, m, v, n, lr, beta1, beta2, eps,
+               grad_scale, step, done_counter);
     FHVAE_LAUNCH_CHECK("adam_flat");
     return 0;
 }

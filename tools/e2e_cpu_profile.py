@@ -1,11 +1,11 @@
 import os, sys, time
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, bench
 import pytorch_scalablefhvae_b200 as P
 c = bench.CFG
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
-m = P.FHVAE(c["T"] * c["F"], [c["H"]] * c["L"], [c["H"]] * c["L"], c["Z"], c["Z"], [c["H"]] * c["L"], seg_len=c["T"], num_seqs=c["N"], gemm_mode=P.MODE_BF16X3).to(dev)
+m = P.FHVAE(c["T"] * c["F"], [c["H"]] * c["L"], [c["H"]] * c["L"], c["Z"], c["Z"], [c["H"]] * c["L"], seg_len=c["T"], num_seqs=c["N"], gemm_mode=P.MODE_BF16X3, use_cuda_graphs=True).to(dev)
 opt = P.FusedAdam(m.parameters(), lr=1e-3, betas=(0.95, 0.999))
 x, idx, nsegs = bench.synth(c["B"], c["T"], c["F"], c["N"], 1234)
 xh, idh, nsh = x.pin_memory(), idx.pin_memory(), nsegs.pin_memory()
