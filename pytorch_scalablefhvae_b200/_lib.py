@@ -13,6 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(HERE, "libfhvae_b200.so")
+if os.environ.get("FHVAE_B200_LIB"):          # A/B experiments: a variant build of the same sources (tools/build_variant.sh)
+    LIB_PATH = os.path.abspath(os.environ["FHVAE_B200_LIB"])
 SOURCES = ["api.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_wgrad.cu", "gemm_proj.cu", "lstm_simt.cu", "lstm_cluster.cu", "lstm_wave.cu", "elbo.cu", "heads.cu", "disc.cu",
            "table_adam_misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -296,7 +296,10 @@ extern "C" int fhvae_wgrad_planes_batch(const fhvae_wgrad_problem* problems, int
                         "wgrad_planes: problem %d: planes must be 16-byte aligned with strides multiple of 8 elements", i);
         tiles += cdiv(p.M, WG_BM) * cdiv(p.N, WG_BN);
     }
-    // split K so that the launch is one wave of 1-CTA/SM tiles; at least 4 K-blocks per split
+    // split K so that the launch is one wave of 1-CTA/SM tiles; at least 4 K-blocks per split.  One split count for all
+    // problems (148 / 32 tiles = 4 for a stack's four gradients = 128 CTAs).  Measured alternatives, whole step at config 1:
+    // splits capped at 3 / 2 / 1: +16 / +27 / +58 us; a cost-balanced split filling all 148 SMs (5,5,5,3): +6 us for the
+    // step's last launch only, +15 us everywhere (more CTAs = more prologues and split-K partials per flop).
     const int want = tiles > 0 ? (kNumSM / tiles > 0 ? kNumSM / tiles : 1) : 1;
     int total = 0, ztotal = 0, nzero = 0, max_nit = 0;
     for (int i = 0; i < n; ++i) {

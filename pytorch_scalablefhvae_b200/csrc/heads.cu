@@ -13,11 +13,15 @@
 
 namespace fhvae {
 
-constexpr int HB = 2;            // batch rows per CTA (B = 256 -> 128 CTAs)
+#ifndef HEAD_HB
+#define HEAD_HB 2
+#endif
+constexpr int HB = HEAD_HB;      // batch rows per CTA (B = 256 -> 128 CTAs).  Whole step, config 1: HB = 4: +17 us, HB = 1: +65 us
 constexpr int HT = 512;          // threads per CTA
 constexpr int HMAXK = 1024;      // max L*H of a head / max 4H of dgsum staged in shared memory
 constexpr int HMAXZ = 128;       // max 2Z, max Kq
 constexpr int HTILE = 40960;     // floats of the weight-tile staging buffer (160 KB of dynamic shared memory)
+constexpr int HBWD_SMEM = (HTILE + (HT / 32) * HB * HMAXZ) * 4;   // backward: + the cross-warp partial sums
 
 // e / d and e % d for a CTA-uniform runtime divisor: a shift when d is a power of two (every size of the
 // benchmark configuration is), the ~30-instruction integer division otherwise.  (Measured: not what bounds these
@@ -242,7 +246,7 @@ struct HeadBwdArgs {
 __global__ void __launch_bounds__(HT) head_bwd_kernel(const __grid_constant__ HeadBwdArgs a) {
     extern __shared__ __align__(16) float s_w[];              // [HTILE] weight tile (rows contiguous: threads walk columns)
     __shared__ float s_g[HB][HMAXK];
-    __shared__ float s_part[HT / 32][HB][HMAXZ];
+    float (*s_part)[HB][HMAXZ] = reinterpret_cast<float (*)[HB][HMAXZ]>(s_w + HTILE);   // [HT / 32] cross-warp partials
     __shared__ float s_dhead[HB][HMAXZ];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = blockIdx.x * HB;
@@ -431,10 +435,10 @@ extern "C" int fhvae_head_bwd(const float* dgsum, int NG, const float* Wq, int64
                   W, nsrc, H, {dh0, dh1}, B};
     static bool attr_b = false;
     if (!attr_b) {
-        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HTILE * 4);
+        cudaFuncSetAttribute(head_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, HBWD_SMEM);
         attr_b = true;
     }
-    launch_pdl(PDL_HEADS, head_bwd_kernel, dim3(cdiv(B, HB)), dim3(HT), HTILE * 4, as_stream(stream), a);
+    launch_pdl(PDL_HEADS, head_bwd_kernel, dim3(cdiv(B, HB)), dim3(HT), HBWD_SMEM, as_stream(stream), a);
     FHVAE_LAUNCH_CHECK("head_bwd");
     return 0;
 }

@@ -7,19 +7,25 @@ set -e
 cd "$(dirname "$0")/.."
 NAME=$1; shift
 DEFS="$*"
+VFILES=${VFILES:-lstm_wave}     # translation units compiled with DEFS (space separated); the rest come from the cache
 CS=pytorch_scalablefhvae_b200/csrc
 OBJ=build_variants/obj
 mkdir -p $OBJ
 FLAGS="-gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC"
 objs=""
-for f in api gemm_simt gemm_tc gemm_wgrad gemm_proj lstm_simt lstm_cluster elbo heads disc table_adam_misc; do
+for f in api gemm_simt gemm_tc gemm_wgrad gemm_proj lstm_simt lstm_cluster lstm_wave elbo heads disc table_adam_misc; do
   o=$OBJ/$f.o
+  if [[ " $VFILES " == *" $f "* ]]; then
+    o=$OBJ/${f}_$NAME.o
+    nvcc $FLAGS $DEFS -c -o $o $CS/$f.cu &
+    objs="$objs $o"
+    continue
+  fi
   if [ ! -f $o ] || [ $CS/$f.cu -nt $o ] || [ $CS/common.cuh -nt $o ] || [ $CS/tc_common.cuh -nt $o ] || [ include/fhvae_b200.h -nt $o ]; then
     nvcc $FLAGS -c -o $o $CS/$f.cu &
   fi
   objs="$objs $o"
 done
-nvcc $FLAGS $DEFS -c -o $OBJ/lstm_wave_$NAME.o $CS/lstm_wave.cu &
 wait
-nvcc -shared -o build_variants/lib_$NAME.so $objs $OBJ/lstm_wave_$NAME.o -lcudart
+nvcc -shared -o build_variants/lib_$NAME.so $objs -lcudart
 echo built build_variants/lib_$NAME.so "($DEFS)"
