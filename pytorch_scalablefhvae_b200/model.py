@@ -219,6 +219,11 @@ class _FHVAECore(nn.Module):
         else:
             plan.run_forward()
             out = plan.out.clone().unbind(0)
+        try:
+            self._check_id_range(mu_idx, B, num_seqs)
+        except IndexError:
+            plan.nan_flag.zero_()        # the launches above flagged the same ids on the device: reported here, once
+            raise
         self._publish(plan)
         lb, log_qy, log_px_z, nk1, nk2, log_pmu2 = (out[i] for i in _OUT_ORDER)
         if self.ref_log_qy:                      # reference returns mean(+CE) (simple_fhvae.py:37,122)
@@ -235,7 +240,9 @@ class _FHVAECore(nn.Module):
             raise RuntimeError("train_step takes a CUDA or pinned-host batch (no CPU path)")
         B, T, F = x.shape
         # with a sharded table (parallel.DataParallel(table="sharded")) mu_idx are GLOBAL row ids in [0, num_rows)
-        self._check_ids(mu_idx, num_segs, B, shard.num_rows if shard is not None else self.mu2_table.shape[0])
+        n_rows = shard.num_rows if shard is not None else self.mu2_table.shape[0]
+        self._check_ids(mu_idx, num_segs, B, n_rows)
+        self._check_id_range(mu_idx, B, n_rows)      # before anything is queued: the fused step would apply Adam
         plan = self._plan(B, T, F)
         plan.load_inputs(x, mu_idx, num_segs, eps)
         if shard is not None:
@@ -254,8 +261,15 @@ class _FHVAECore(nn.Module):
             raise IndexError(f"mu_idx has {mu_idx.numel()} entries for a batch of {B} segments")
         if torch.is_tensor(num_segs) and num_segs.numel() != B:
             raise IndexError(f"num_segs has {num_segs.numel()} entries for a batch of {B} segments")
-        if not mu_idx.is_cuda and B and (int(mu_idx.min()) < 0 or int(mu_idx.max()) >= int(N)):
-            raise IndexError("mu_idx out of range for the mu2 table")
+
+    @staticmethod
+    def _check_id_range(mu_idx, B, N):
+        """Range check of host-resident ids.  forward() calls it AFTER the step's launches are queued (the host check then
+        overlaps the GPU; the kernels themselves never index outside the table, see ``_check_ids``)."""
+        if not mu_idx.is_cuda and B:
+            lo, hi = torch.aminmax(mu_idx)
+            if int(lo) < 0 or int(hi) >= int(N):
+                raise IndexError("mu_idx out of range for the mu2 table")
 
     def check_flags(self):
         """Host read (one sync) of the device status word: raises like the reference would have
@@ -428,8 +442,10 @@ class _Plan:
 
     def load_inputs(self, x, mu_idx, num_segs, eps):
         dev = self.dev
-        on_dev = lambda t: (torch.is_tensor(t) and t.device == dev and t.dtype == torch.int64 and t.is_contiguous()
-                            and t.numel() == self.B)
+        # ids the load kernel can read itself: device-resident, or PINNED host tensors (mapped into the device's address
+        # space: 4 KB over PCIe inside the launch instead of two cudaMemcpyAsync calls, ~15 us of host time per step)
+        on_dev = lambda t: (torch.is_tensor(t) and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == self.B
+                            and (t.device == dev or (t.device.type == "cpu" and t.is_pinned())))
         fused_ids = on_dev(mu_idx) and on_dev(num_segs)
         self.set_x(x, mu_idx if fused_ids else None, num_segs if fused_ids else None)
         if not fused_ids:

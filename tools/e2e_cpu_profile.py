@@ -30,3 +30,28 @@ torch.cuda.synchronize()
 tot = time.perf_counter() - t0
 print("per step ms", tot / n * 1e3)
 for k, v in acc.items(): print(f"  {k:12s} {v / n * 1e6:8.1f} us")
+
+# ---- finer: where inside forward() does the host time go, and when does the GPU get its first work?
+import functools
+sub = {}
+def wrap(obj, name, label):
+    f = getattr(obj, name)
+    @functools.wraps(f)
+    def g(*a, **k):
+        t0 = time.perf_counter()
+        try:
+            return f(*a, **k)
+        finally:
+            sub[label] = sub.get(label, 0.0) + time.perf_counter() - t0
+    setattr(obj, name, g)
+plan = list(m._plans.values())[0]
+wrap(m, "_check_ids", "forward._check_ids")
+wrap(plan, "load_inputs", "forward.load_inputs")
+wrap(plan, "run_forward", "forward.run_forward(graph launch)")
+wrap(m, "_publish", "forward._publish")
+wrap(plan, "run_backward", "backward.run_backward")
+wrap(m, "_deliver_grads", "backward._deliver_grads")
+acc.clear()
+for _ in range(n): step(True)
+torch.cuda.synchronize()
+for k, v in sub.items(): print(f"  {k:36s} {v / n * 1e6:8.1f} us")
