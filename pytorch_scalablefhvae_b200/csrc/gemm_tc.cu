@@ -494,7 +494,7 @@ int gemm_batch_tc(const fhvae_gemm_problem* problems, int n, int mode, cudaStrea
         const int nkb = cdiv(p.K, bk);
         int ks = 1;
         if (!p.relu && (p.beta == 0.f || p.beta == 1.f)) {
-            const int max_split = p.K / 128;                 // >= 128 of K per split
+            const int max_split = p.K / 128;                 // >= 128 of K per split (256: the decoder head unsplit, +2 us/step)
             ks = want_split < max_split ? want_split : max_split;
             if (ks > 32) ks = 32;
             if (ks < 1) ks = 1;

@@ -72,6 +72,10 @@ constexpr int WMAXT = 63;          // flag = epoch * 64 + t + 1
 #ifndef WAVE_COOPERATIVE
 #define WAVE_COOPERATIVE -1  // 1 / 0: always / never launch cooperatively; -1: env FHVAE_WAVE_COOPERATIVE=1 decides (default off)
 #endif
+#ifndef WAVE_PDL_EARLY
+#define WAVE_PDL_EARLY 0      // 1: griddepcontrol.launch_dependents at the top of the wavefront kernels (the launches behind them
+#endif                        //    become resident on the free SMs while the recurrence runs): +38 us per step -- they take the
+                              //    SMs the side-stream weight gradients live on
 #ifndef WAVE_SAVE_FIRST
 #define WAVE_SAVE_FIRST 0    // 1: the HBM stores of the previous step are issued before the exchange loads
 #endif
@@ -444,6 +448,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_fwd_kernel(const __grid_con
     uint4* p1x = a.xchg + WHDR + ((size_t)(2 * a.Gs) * T) * (WG * WSLICE) + ((size_t)grp * T) * (WG * WPSLICE) + rank * WPSLICE;
 
     WTL(0, 15);
+#if WAVE_PDL_EARLY
+    pdl_launch_dependents();
+#endif
     // ---- prologue: TMEM, barriers, W_hh slice -> TMEM (lane n = gate*32 + unit, column k/2 = bf16 pair)
     constexpr int NACC = 2;
     constexpr int WCOLS = CH / 2;
@@ -1315,6 +1322,9 @@ __global__ void __launch_bounds__(WNTA, 1) lstm_wave_bwd_kernel(const __grid_con
     uint4* rs = a.xchg + WHDR + ((size_t)(role * a.Gs + grp) * 2) * (WG * WG * WRS);
     uint4* dgx = a.xchg + WHDR + ((size_t)(2 * a.Gs) * 2) * (WG * WG * WRS) + ((size_t)grp * T) * (WG * WDG) + rank * WDG;
 
+#if WAVE_PDL_EARLY
+    pdl_launch_dependents();
+#endif
     constexpr int NACC = 2;
     constexpr int ABUF = HF * NACC * NB;                       // one accumulator set: HF unit halves x NACC x NB columns
     constexpr int WCOLS = NC / 2;                              // 64 columns per (half, part) of the resident W_hh^T
