@@ -13,6 +13,14 @@ try:
 except Exception as e: print("$c N=$n $TAG FAILED", e)
 PY
 }
+# optional argument: a list of "config:N[:tag:extra flags]" items instead of the full set, e.g. "c1:8 c1:1 c3:8"
+if [ -n "$1" ]; then
+  for item in $1; do
+    IFS=: read c n tag extra <<< "$item"
+    TAG="${tag:+_$tag}" run $n $c $extra
+  done
+  exit 0
+fi
 for n in 8 4 2 1; do TAG="" run $n c1; done
 TAG="_overlap" run 8 c1 --overlap
 for n in 8 4 2 1; do TAG="" run $n c3; done
