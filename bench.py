@@ -368,6 +368,9 @@ def main():
 
     if rank != 0:
         if world > 1:
+            for pl in m._plans.values():           # graphs that captured a collective go before their communicator
+                pl.__dict__.pop("_train_graphs", None)
+            torch.cuda.synchronize()
             dist.destroy_process_group()
         return
     cpu, ref_c0 = None, None
@@ -401,6 +404,9 @@ def main():
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        for pl in m._plans.values():
+            pl.__dict__.pop("_train_graphs", None)
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 

@@ -564,12 +564,17 @@ class _Plan:
         else:
             # the captured Adam launch bakes its hyper-parameters in: a changed lr / betas / eps / grad_scale
             # (LR scheduler, load_state_dict, a DataParallel wrapper created later) re-captures
-            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key(), draw)
+            # FHVAE_DP_ONE_GRAPH=1: the collective is captured too (NCCL launches are capturable): one graph per step
+            # instead of graph / eager all-reduce / graph
+            one_graph = allreduce is not None and os.environ.get("FHVAE_DP_ONE_GRAPH", "0") == "1"
+            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key(), draw, one_graph)
             graphs = self.__dict__.setdefault("_train_graphs", {})
             if key not in graphs:
                 optimizer._state_for(m)               # allocate Adam state outside capture
                 if allreduce is None:
                     graphs[key] = (self._capture(lambda: (fwd_bwd(), adam()), restore=optimizer), None)
+                elif one_graph:
+                    graphs[key] = (self._capture(lambda: (fwd_bwd(), allreduce(gflat), adam()), restore=optimizer), None)
                 else:
                     graphs[key] = (self._capture(fwd_bwd), self._capture(adam, restore=optimizer))
             g1, g2 = graphs[key]
