@@ -186,6 +186,13 @@ class _FHVAECore(nn.Module):
         return buf
 
     # ------------------------------------------------------------------ forward
+    def _padded_batch(self, B: int, T: int) -> int:
+        """Rows the plan of a B-segment batch is built for.  The tensor-core recurrence works on groups of 32 batch rows; a
+        ragged batch (the last one of an epoch: the reference's DataLoader keeps it, train_model.py:440) is run on the next
+        multiple of 32 with the extra rows carrying finite filler and ZERO upstream gradient, instead of falling back to
+        the per-step fp32 kernels (~10x slower).  Sub-classes without such kernels return B."""
+        return B
+
     def _plan(self, B: int, T: int, F: int) -> "_Plan":
         self._ensure_flat()
         key = (B, T, F, self.gemm_mode, self._flat.data_ptr(), _lib.load().fhvae_get_deterministic())
@@ -208,8 +215,8 @@ class _FHVAECore(nn.Module):
             raise ValueError(f"num_seqs={num_seqs} but the mu2 table has {self.mu2_table.shape[0]} rows")
         B, T, F = x.shape
         self._check_ids(mu_idx, num_segs, B, num_seqs)
-        plan = self._plan(B, T, F)
-        plan.load_inputs(x, mu_idx, num_segs, eps)
+        plan = self._plan(self._padded_batch(B, T), T, F)
+        plan.load_inputs(x, mu_idx, num_segs, eps, valid=B)
         grad_on = torch.is_grad_enabled() and any(p.requires_grad for p in self._plist)
         if grad_on:
             if self._anchor is None or self._anchor.device != x.device:
@@ -218,7 +225,7 @@ class _FHVAECore(nn.Module):
             out = _StepFn.apply(self, plan, self._anchor, *params)          # six (B,) rows of one buffer
         else:
             plan.run_forward()
-            out = plan.out.clone().unbind(0)
+            out = plan.out[:, :B].clone().unbind(0)
         try:
             self._check_id_range(mu_idx, B, num_seqs)
         except IndexError:
@@ -243,8 +250,9 @@ class _FHVAECore(nn.Module):
         n_rows = shard.num_rows if shard is not None else self.mu2_table.shape[0]
         self._check_ids(mu_idx, num_segs, B, n_rows)
         self._check_id_range(mu_idx, B, n_rows)      # before anything is queued: the fused step would apply Adam
-        plan = self._plan(B, T, F)
-        plan.load_inputs(x, mu_idx, num_segs, eps)
+        fused_dp = shard is not None or (overlap is not None and allreduce is not None)
+        plan = self._plan(B if fused_dp else self._padded_batch(B, T), T, F)    # (the sharded / overlapped runners: no padding)
+        plan.load_inputs(x, mu_idx, num_segs, eps, valid=B)
         if shard is not None:
             return plan.run_train_step_sharded(optimizer, float(alpha), shard)
         if overlap is not None and allreduce is not None and hasattr(self, "_z2_end") and self.use_cuda_graphs:
@@ -290,28 +298,29 @@ class _FHVAECore(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("pytorch_scalablefhvae_b200 has no CPU path")
         B, T, F = x.shape
-        plan = self._plan(B, T, F)
+        plan = self._plan(self._padded_batch(B, T), T, F)
         plan.set_x(x)
         if eps is None:
             plan.eps1.zero_(); plan.eps2.zero_()
         else:
-            plan.eps1.copy_(eps["z1"].reshape(plan.eps1.shape)); plan.eps2.copy_(eps["z2"].reshape(plan.eps2.shape))
+            plan.eps1[:B].copy_(eps["z1"].reshape(B, -1)); plan.eps2[:B].copy_(eps["z2"].reshape(B, -1))
         plan.run_encode()
         Z1, Z2 = self.z1_dim, self.z2_dim
-        return {"z1_mu": plan.z1head[:, :Z1], "z1_logvar": plan.z1head[:, Z1:],
-                "z2_mu": plan.z2head[:, :Z2], "z2_logvar": plan.z2head[:, Z2:]}
+        return {"z1_mu": plan.z1head[:B, :Z1], "z1_logvar": plan.z1head[:B, Z1:],
+                "z2_mu": plan.z2head[:B, :Z2], "z2_logvar": plan.z2head[:B, Z2:]}
 
     def _publish(self, plan: "_Plan"):
         """Attributes the reference's callers read (utils.py:52,58)."""
         pub = plan.__dict__.get("_published")
-        if pub is None:                    # views of the plan's static buffers: built once, not per forward
-            z1h, z2h = plan.z1head, plan.z2head
+        v = plan.valid
+        if pub is None or pub[0] != v:     # views of the plan's static buffers: built once, not per forward
+            z1h, z2h = plan.z1head[:v], plan.z2head[:v]
             Z1, Z2 = self.z1_dim, self.z2_dim
-            pub = plan._published = dict(
+            pub = plan._published = (v, dict(
                 qz1_x=[z1h[:, :Z1], z1h[:, Z1:]], qz2_x=[z2h[:, :Z2], z2h[:, Z2:]], px_z=plan.px_views(),
-                pz2=[plan.mu2, np.float32(PZ2_LOGVAR)], z1_sample=plan.zcat[:, :Z1], z2_sample=plan.zcat[:, Z1:],
-                nan_flag=plan.nan_flag)
-        self.__dict__.update(pub)
+                pz2=[plan.mu2[:v], np.float32(PZ2_LOGVAR)], z1_sample=plan.zcat[:v, :Z1], z2_sample=plan.zcat[:v, Z1:],
+                nan_flag=plan.nan_flag))
+        self.__dict__.update(pub[1])
 
     # subclasses: _make_plan(B, T, F)
 
@@ -328,7 +337,7 @@ class _StepFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)      # unused outputs arrive as None instead of zero tensors
         # rows of the (6,B) buffer: lb, log_px, nk1, nk2, log_pmu2, log_qy -- returned as six outputs so that
         # autograd hands their gradients straight back (no per-row SelectBackward zeros + copy)
-        return tuple(plan.out.clone().unbind(0))
+        return tuple(plan.out[:, :plan.valid].clone().unbind(0))
 
     @staticmethod
     def backward(ctx, *gouts):
@@ -417,6 +426,7 @@ class _Plan:
         self._graph_fwd = None
         self._graph_bwd = [None, None]
         self.generation = 0          # bumped by everything that overwrites the saved activations (see _StepFn.backward)
+        self.valid = B               # rows of the current batch (< B for a ragged batch run on a padded plan)
 
     # ---- inputs / outputs
     def set_x(self, x, mu_idx=None, num_segs=None):
@@ -424,6 +434,13 @@ class _Plan:
         two id vectors in the same launch.  Every entry (forward, train_step, encode) loads x through here."""
         self.generation += 1
         x_tm = self.__dict__.get("x_tm")
+        self.valid = int(x.shape[0])
+        if self.valid < self.B:      # ragged batch on a padded plan: the filler rows keep whatever finite data they hold
+            self.x[:self.valid].copy_(x, non_blocking=True)
+            if x_tm is not None:
+                _lib.check(_lib.fn("fhvae_transpose_bt")(ptr(self.x), ptr(x_tm), self.B, self.T, self.F,
+                                                         current_stream_ptr()), "fhvae_transpose_bt")
+            return
         if (x.device == self.dev and x.dtype == torch.float32 and x.is_contiguous() and x.shape == self.x.shape
                 and self.F % 4 == 0 and x.data_ptr() % 16 == 0):
             _lib.check(_lib.fn("fhvae_load_inputs")(
@@ -440,23 +457,24 @@ class _Plan:
             self.idx.copy_(mu_idx, non_blocking=True)
             self.nsegs.copy_(num_segs, non_blocking=True)
 
-    def load_inputs(self, x, mu_idx, num_segs, eps):
+    def load_inputs(self, x, mu_idx, num_segs, eps, valid=None):
         dev = self.dev
+        v = self.B if valid is None else int(valid)
         # ids the load kernel can read itself: device-resident, or PINNED host tensors (mapped into the device's address
         # space: 4 KB over PCIe inside the launch instead of two cudaMemcpyAsync calls, ~15 us of host time per step)
         on_dev = lambda t: (torch.is_tensor(t) and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == self.B
                             and (t.device == dev or (t.device.type == "cpu" and t.is_pinned())))
-        fused_ids = on_dev(mu_idx) and on_dev(num_segs)
+        fused_ids = v == self.B and on_dev(mu_idx) and on_dev(num_segs)
         self.set_x(x, mu_idx if fused_ids else None, num_segs if fused_ids else None)
         if not fused_ids:
-            self.idx.copy_(mu_idx, non_blocking=True)
+            self.idx[:v].copy_(mu_idx, non_blocking=True)
             if torch.is_tensor(num_segs):
-                self.nsegs.copy_(num_segs, non_blocking=True)
+                self.nsegs[:v].copy_(num_segs, non_blocking=True)
             else:
                 self.nsegs.fill_(int(num_segs))
         if eps is not None:
-            self.eps1.copy_(eps["z1"].reshape(self.eps1.shape), non_blocking=True)
-            self.eps2.copy_(eps["z2"].reshape(self.eps2.shape), non_blocking=True)
+            self.eps1[:v].copy_(eps["z1"].reshape(v, -1), non_blocking=True)
+            self.eps2[:v].copy_(eps["z2"].reshape(v, -1), non_blocking=True)
         self._draw = eps is None                     # True: the step itself draws eps (self.rng, first node of the graph)
 
     # ---- execution
@@ -495,17 +513,20 @@ class _Plan:
         gflat = self.m._grad_buffer(k)
         if self.bwd[k] is None:
             self.bwd[k] = self._build_bwd(gflat)
+        v = self.valid
         if torch.is_tensor(gout):
-            self.gout.copy_(gout)
+            if v < self.B:
+                self.gout.zero_()
+            self.gout[:, :v].copy_(gout)
             self._gout_rows = None
         else:                                  # six per-output gradients, None where an output was not used
-            used = tuple(g_ is not None for g_ in gout)
-            if self.__dict__.get("_gout_rows") != used:      # rows that are None now may hold an older gradient
-                self.gout.zero_()
+            used = (v,) + tuple(g_ is not None for g_ in gout)
+            if self.__dict__.get("_gout_rows") != used:      # rows that are None now may hold an older gradient; the
+                self.gout.zero_()                            # filler rows of a ragged batch must stay zero
                 self._gout_rows = used
             for row, g_ in enumerate(gout):
                 if g_ is not None:
-                    self.gout[row].copy_(g_)
+                    self.gout[row, :v].copy_(g_)
         self._gout_train = None
         if self.m.use_cuda_graphs:
             if self._graph_bwd[k] is None:
@@ -523,19 +544,20 @@ class _Plan:
             self.bwd[k] = self._build_bwd(gflat)
         if not hasattr(self, "loss"):
             self.loss = torch.zeros((), dtype=torch.float32, device=self.dev)
-        B = self.B
+        B, v = self.B, self.valid
 
         # the upstream gradients of a plain train step are constants: filled once, outside the graph
-        if self.__dict__.get("_gout_train") != (alpha, B):
+        # (filler rows of a ragged batch: zero, so that nothing they compute reaches a gradient)
+        if self.__dict__.get("_gout_train") != (alpha, v):
             self.gout.zero_()
-            self.gout[0].fill_(-1.0 / B)                  # d loss / d lower_bound
-            self.gout[5].fill_(-alpha / B)                # d loss / d log_qy
-            self._gout_train = (alpha, B)
+            self.gout[0, :v].fill_(-1.0 / v)              # d loss / d lower_bound
+            self.gout[5, :v].fill_(-alpha / v)            # d loss / d log_qy
+            self._gout_train = (alpha, v)
             self._gout_rows = None
-        if self.__dict__.get("_loss_call") is None or self._loss_call[1] != alpha:
+        if self.__dict__.get("_loss_call") is None or self._loss_call[1] != (alpha, v):
             lc = CallList()
-            lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), B, ptr(self.loss), side=1)
-            self._loss_call = (lc, alpha)
+            lc.add("fhvae_loss_mean", ptr(self.out), ptr(self.out, 5 * B), float(alpha), v, ptr(self.loss), side=1)
+            self._loss_call = (lc, (alpha, v))
         loss_call = self._loss_call[0]
 
         fwd_list, bwd_list = self._train_lists(k)
@@ -567,7 +589,7 @@ class _Plan:
             # FHVAE_DP_ONE_GRAPH=1: the collective is captured too (NCCL launches are capturable): one graph per step
             # instead of graph / eager all-reduce / graph
             one_graph = allreduce is not None and os.environ.get("FHVAE_DP_ONE_GRAPH", "0") == "1"
-            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key(), draw, one_graph)
+            key = ("train", alpha, id(optimizer), allreduce is None, optimizer.hyper_key(), draw, one_graph, v)
             graphs = self.__dict__.setdefault("_train_graphs", {})
             if key not in graphs:
                 optimizer._state_for(m)               # allocate Adam state outside capture
@@ -1025,7 +1047,7 @@ class _FHVAEPlan(_Plan):
 
     def px_views(self):
         F = self.F
-        xh = self.xhead.permute(1, 0, 2)             # (B,T,2F) view of the time-major buffer
+        xh = self.xhead.permute(1, 0, 2)[:self.valid]    # (B,T,2F) view of the time-major buffer
         return [xh[..., :F], xh[..., F:]]
 
     def _bs(self, k, l):                             # fused (b_ih + b_hh) pointer
@@ -1680,6 +1702,15 @@ class FHVAE(_FHVAECore):
         for pfx in ("z1_gauss_layer", "z2_gauss_layer", "dec_gauss_layer"):
             _check_adjacent(self._off, self._shape, pfx + ".mulayer.weight", pfx + ".logvar_layer.weight")
             _check_adjacent(self._off, self._shape, pfx + ".mulayer.bias", pfx + ".logvar_layer.bias")
+
+    def _padded_batch(self, B, T):
+        if B % 32 == 0 or os.environ.get("FHVAE_PAD_BATCH", "1") == "0":
+            return B
+        Bp = (B + 31) // 32 * 32
+        sup = _lib.fn("fhvae_lstm_wave_supported")
+        wave = any(len(h) == 2 and len(set(h)) == 1 and sup(T, Bp, int(h[0]), 2, self.gemm_mode)
+                   for h in (self.z2_hus, self.z1_hus, self.x_hus))
+        return Bp if wave else B
 
     def _make_plan(self, B, T, F):
         if T != self.seg_len or F != self.feat_dim:
