@@ -32,7 +32,7 @@ import torch  # noqa: E402
 CFG = dict(B=256, T=20, F=80, H=256, L=2, Z=32, N=1000, alpha=10.0)
 C0 = dict(B=64, T=20, F=80, H=128, Z=16, N=1000, alpha=10.0)         # BASELINE configs[0]
 C3 = dict(N_master=280_000, K=5000)                                   # BASELINE configs[3]
-C4 = dict(U=10_000, batch=2048, shift=8)                              # BASELINE configs[4]
+C4 = dict(U=10_000, batch=None, shift=8)                              # BASELINE configs[4]; batch: inference.default_batch_size
 REF_DIR = os.path.join(ROOT, "baseline", "_ref")
 FLOP_PER_SEG_TRAIN = 320_073_216          # SURVEY.md §8d canonical (nn.LSTM/nn.Linear count, N=1000)
 METRIC = "train_segments_per_sec"
@@ -595,7 +595,7 @@ def run_c4(args, P, dist, dev, rank, world, local, mode):
             "vs_baseline": None, "dtype": args.mode, "data": "synthetic",
             "config": {"workload": f"BASELINE config 4: posterior extraction over {U} synthetic utterances ({S} segments of 20 "
                                    f"frames, stride 8), FHVAE LSTM 2x256 encoders only + per-utterance mu2 (utils.py:45-60), "
-                                   f"utterances sharded over {world} rank(s), batch {C4['batch']} segments",
+                                   f"utterances sharded over {world} rank(s), batch {C4['batch'] or P.inference.default_batch_size(m)} segments",
                        "gemm_mode": args.mode, "parallelism": f"utterance-sharded x{world}, no data-path collective"},
             "utterances_per_s": U * passes / (ms / 1e3), "clocks": clocks}
     print(json.dumps(line), flush=True)

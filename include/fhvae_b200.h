@@ -112,6 +112,10 @@ int fhvae_lstm_bwd(const float* dh_all, const float* dh_last, const float* W_hh,
  *   written by the caller afterwards.  fhvae_lstm_wave_supported returns 1 if the shape/mode is served.
  * ------------------------------------------------------------------------------------------- */
 int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int mode);
+/* batch rows ONE launch serves on this device (groups of 32 rows x CTAs per group x layers <= SM count): 288 for two
+ * layers of H = 256 on 148 SMs.  A larger batch runs as consecutive launches, so forward-only drivers (posterior
+ * extraction, eval_model.py:41-59) size their batches as multiples of it.  0: shape not served. */
+int fhvae_lstm_wave_rows_per_launch(int H, int nlayers);
 long long fhvae_lstm_wave_xchg_bytes(int T, int B, int H, int nlayers);
 int fhvae_lstm_wave_fwd(const float* P0, const float* Q0, const float* W_hh0, float* h0, float* c0, float* acts0,
                         const float* W_ih1, const float* bias1, const float* W_hh1, float* h1, float* c1,

@@ -67,6 +67,7 @@ PROTOTYPES = {
     "fhvae_lstm_bwd": [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p],
     "fhvae_lstm_wave_supported": [_i, _i, _i, _i, _i],
     "fhvae_lstm_wave_xchg_bytes": [_i, _i, _i, _i],
+    "fhvae_lstm_wave_rows_per_launch": [_i, _i],
     "fhvae_lstm_wave_fwd": [_p] * 13 + [_i, _i, _i, _i, _i, _p],
     "fhvae_lstm_wave_bwd_xchg_bytes": [_i, _i, _i, _i],
     "fhvae_lstm_wave_fwd_planes": [_p] * 15 + [_l, _p, _i, _i, _i, _i, _i, _p],
@@ -116,7 +117,7 @@ PROTOTYPES = {
     "fhvae_built_for_sm": [],
     "fhvae_launch_count": [],
 }
-NO_STATUS = {"fhvae_set_deterministic", "fhvae_get_deterministic", "fhvae_lstm_wave_pack_bytes", "fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
+NO_STATUS = {"fhvae_lstm_wave_rows_per_launch", "fhvae_set_deterministic", "fhvae_get_deterministic", "fhvae_lstm_wave_pack_bytes", "fhvae_disc_nsplit", "fhvae_lstm_wave_supported", "fhvae_lstm_wave_xchg_bytes", "fhvae_lstm_wave_bwd_xchg_bytes", "fhvae_version", "fhvae_built_for_sm", "fhvae_launch_count"}
 EXPORTS = sorted(list(PROTOTYPES) + ["fhvae_last_error_string"])
 
 _lib = None

@@ -45,6 +45,7 @@ int lstm_bwd_cluster(const float* dh_all, const float* dh_last, const float* W_h
 
 bool lstm_wave_supported(int T, int B, int H, int L);
 size_t lstm_wave_xchg_bytes(int T, int B, int H, int L);
+int lstm_wave_rows_per_launch(int H, int L);
 int lstm_wave_fwd(const float* P0, const float* Q0, const float* Whh0, float* h0, float* c0, float* a0,
                   const float* Wih1, const float* b1, const float* Whh1, float* h1, float* c1, float* a1,
                   void* xchg, int T, int B, int H, int L, int mode, cudaStream_t st, void* hp0 = nullptr, void* hp1 = nullptr,
@@ -121,6 +122,8 @@ static constexpr int WAVE_MIN_B = 32;
 extern "C" int fhvae_lstm_wave_supported(int T, int B, int H, int nlayers, int mode) {
     return (mode == FHVAE_MODE_BF16X3 || mode == FHVAE_MODE_BF16) && lstm_wave_supported(T, B, H, nlayers) ? 1 : 0;
 }
+
+extern "C" int fhvae_lstm_wave_rows_per_launch(int H, int nlayers) { return lstm_wave_rows_per_launch(H, nlayers); }
 
 extern "C" long long fhvae_lstm_wave_xchg_bytes(int T, int B, int H, int nlayers) {
     if (!lstm_wave_supported(T, B, H, nlayers)) return 0;

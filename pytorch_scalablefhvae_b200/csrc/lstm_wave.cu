@@ -1756,6 +1756,11 @@ bool lstm_wave_supported(int T, int B, int H, int L) {
            wave_groups_per_launch(L, H) >= 1;
 }
 
+int lstm_wave_rows_per_launch(int H, int L) {      // batch rows one launch serves with every group co-resident
+    if (!(H == 256 || H == 128) || !(L == 1 || L == 2)) return 0;
+    return wave_groups_per_launch(L, H) * WNB;
+}
+
 size_t lstm_wave_xchg_bytes(int T, int B, int H, int L) {
     int gs = B / WNB;
     const int gmax = wave_groups_per_launch(L, H), ng = H / WU;

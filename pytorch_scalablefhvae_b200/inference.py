@@ -32,12 +32,27 @@ def segment_table(lengths: Sequence[int], seg_len: int = 20, seg_shift: int = 8)
     return cat(starts), cat(utts), np.asarray(nsegs, dtype=np.int64)
 
 
+def default_batch_size(model, target: int = 2048) -> int:
+    """Segments per forward-only batch: the tensor-core recurrence serves ``fhvae_lstm_wave_rows_per_launch`` rows per
+    launch (288 for 2x256 on 148 SMs) and runs a larger batch as consecutive launches, so a batch of 2048 = 7 full
+    launches + one with a single 32-row group; 2016 = 7 x 288 does the same work in 7."""
+    hus = [getattr(model, a, None) for a in ("z2_hus", "z1_hus")]
+    if all(h is not None and len(h) == 2 and len(set(h)) == 1 for h in hus) and hus[0][0] == hus[1][0]:
+        rows = _lib.fn("fhvae_lstm_wave_rows_per_launch")(int(hus[0][0]), 2)
+        if rows > 0:
+            return max(rows, target // rows * rows)
+    return target
+
+
 @torch.no_grad()
 def extract_posteriors(model, feats: torch.Tensor, lengths: Sequence[int], seg_shift: int = 8,
-                       batch_size: int = 2048, mean: Optional[torch.Tensor] = None,
+                       batch_size: Optional[int] = None, mean: Optional[torch.Tensor] = None,
                        std: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
     """feats: (sum(lengths), F) fp32 on the model's device (all utterances packed).  Returns z1_mu (S,Z1),
-    z2_mu (S,Z2) per segment, mu2 (U,Z2) per utterance, plus seg_utt (S,) and nsegs (U,)."""
+    z2_mu (S,Z2) per segment, mu2 (U,Z2) per utterance, plus seg_utt (S,) and nsegs (U,).  ``batch_size=None``:
+    ~2048 segments, rounded to a whole number of recurrence launches (``default_batch_size``)."""
+    if batch_size is None:
+        batch_size = default_batch_size(model)
     dev = feats.device
     if not feats.is_cuda:
         raise RuntimeError("extract_posteriors needs the packed features on the GPU (no CPU path)")
