@@ -208,3 +208,21 @@ def test_extract_posteriors_sharded_covers_all_utterances():
     assert sorted(seen) == list(range(13))
     assert_close(mu2, whole["mu2"], 1e-5, "mu2")             # per-utterance results do not depend on the sharding
                                                              # (batch boundaries differ: summation order only)
+
+
+def test_default_extraction_batch_is_a_whole_number_of_recurrence_launches():
+    """Forward-only batches are sized so that no recurrence launch runs with a partial set of groups
+    (fhvae_lstm_wave_rows_per_launch: groups x 32 rows that fit the device), and ragged tails run padded."""
+    rows = P._lib.fn("fhvae_lstm_wave_rows_per_launch")(256, 2)
+    sm = torch.cuda.get_device_properties(0).multi_processor_count
+    assert rows == min(sm // 16, 32) * 32 and rows > 0          # 8 CTAs per group x 2 layers, one CTA per SM
+    assert P._lib.fn("fhvae_lstm_wave_rows_per_launch")(200, 2) == 0
+    m = P.FHVAE(1600, [256, 256], [256, 256], 32, 32, [256, 256], seg_len=20, num_seqs=10, gemm_mode=P.MODE_BF16X3)
+    bs = P.inference.default_batch_size(m)
+    assert bs % rows == 0 and 2048 - rows < bs <= 2048
+    small = P.SimpleFHVAE(1600, [128, 128], [128, 128], 16, 16, [128, 128], num_seqs=10)
+    assert P.inference.default_batch_size(small) == 2048
+    # a ragged extraction batch of the LSTM model (51 segments) is served by the padded plan
+    m = m.to(DEV)
+    enc = m.encode(torch.randn(51, 20, 80, device=DEV))
+    assert enc["z2_mu"].shape == (51, 32) and list(m._plans.values())[0].B == 64
