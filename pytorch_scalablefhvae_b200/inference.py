@@ -37,7 +37,8 @@ def default_batch_size(model, target: int = 2048) -> int:
     launch (288 for 2x256 on 148 SMs) and runs a larger batch as consecutive launches, so a batch of 2048 = 7 full
     launches + one with a single 32-row group; 2016 = 7 x 288 does the same work in 7."""
     hus = [getattr(model, a, None) for a in ("z2_hus", "z1_hus")]
-    if all(h is not None and len(h) == 2 and len(set(h)) == 1 for h in hus) and hus[0][0] == hus[1][0]:
+    if (getattr(model, "model", "") == "fhvae" and all(h is not None and len(h) == 2 and len(set(h)) == 1 for h in hus)
+            and hus[0][0] == hus[1][0]):
         rows = _lib.fn("fhvae_lstm_wave_rows_per_launch")(int(hus[0][0]), 2)
         if rows > 0:
             return max(rows, target // rows * rows)
