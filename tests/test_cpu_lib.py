@@ -39,6 +39,27 @@ def test_built_for_sm100a(lib):
     assert "sm_100a" in sass
 
 
+def test_dependent_launch_kernels_have_no_noncoherent_loads(lib):
+    """Kernels that execute griddepcontrol.wait (SASS: ACQBULK) may start while their predecessor is still running;
+    ld.global.nc (SASS: LDG.E...CONSTANT) carries no ordering and was observed hoisted ABOVE the wait (stale Q rows in
+    the first eager forward).  Rule: no such load in any of these kernels -- checked on the shipped SASS."""
+    sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    cur, wait, nc = None, {}, {}
+    for ln in sass.splitlines():
+        m = re.search(r"Function : (\S+)", ln)
+        if m:
+            cur = m.group(1)
+            wait[cur], nc[cur] = 0, 0
+        elif cur and re.search(r"\bACQBULK\b", ln):
+            wait[cur] += 1
+        elif cur and re.search(r"\bLDG\.[A-Z0-9_.]*CONSTANT", ln):
+            nc[cur] += 1
+    pdl = [k for k, v in wait.items() if v]
+    assert len(pdl) >= 10, pdl                      # wavefront fwd/bwd (x4 each), heads, gemm_tc, fused ELBO, Adam, loss
+    bad = {k: nc[k] for k in pdl if nc[k]}
+    assert not bad, f"ld.global.nc in kernels launched with programmatic serialization: {bad}"
+
+
 def test_argument_errors_are_reported_not_thrown(lib):
     rc = lib.fhvae_gemm_batch(None, 0, 0, None)
     assert rc == -1 and b"gemm_batch" in lib.fhvae_last_error_string()
